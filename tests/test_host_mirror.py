@@ -1,0 +1,45 @@
+"""CPU tests of the host-side mirror of the reference API (types, kinematics tables)."""
+import math
+
+import numpy as np
+
+from cases import c1_surf
+
+
+def test_twodsurf_constructor_matches_reference_formulas(uf):
+    surf, fld, nsteps, dtstar = c1_surf(uf)
+    assert surf.ndiv == 70 and surf.naterm == 35 and len(surf.bv) == 69          # typedefs.jl:68
+    assert abs(surf.theta[-1] - math.pi) < 1e-15 and abs(surf.x[-1] - 1.0) < 1e-15  # :77-82
+    a = 5 * math.pi / 180
+    # :156-159 -- TE at the origin side, LE at -(c - pvt c) - pvt c cos(alpha)
+    assert abs(surf.bnd_x[0] + (0.75 + 0.25 * math.cos(a))) < 1e-15
+    assert abs(surf.bnd_z[0] - 0.25 * math.sin(a)) < 1e-15
+    assert np.all(surf.bv.vc == 0.02) and surf.levflag[0] == 0
+    assert len(fld.tev) == 0 and fld.u[0] == 0
+
+
+def test_vortlist_semantics(uf):
+    v = uf.VortList()
+    for i in range(100):
+        v.append(uf.TwoDVort(i, -i, 0.1 * i, 0.02))
+    assert len(v) == 100 and v[99].x == 99 and v[-1].z == -99
+    v[3].s = 7.0
+    assert v.s[3] == 7.0
+    first = v.popfirst()
+    assert first.x == 0 and len(v) == 99 and v[0].x == 1 and v[2].s == 7.0
+
+
+def test_kinematics_table_running_sum(uf):
+    surf, fld, nsteps, dtstar = c1_surf(uf)
+    tab = uf.kinematics_table(surf, fld, 10, dtstar)
+    t = 0.0
+    for i in range(10):
+        t = t + dtstar                     # solvers.jl:180, not (i+1)*dt
+        assert tab[i, 0] == t
+    assert np.all(tab[:, 1] == 5 * math.pi / 180) and np.all(tab[:, 5] == 1.0) and np.all(tab[:, 3] == 0.0)
+
+
+def test_find_tstep(uf):
+    assert uf.find_tstep(uf.ConstDef(1.0)) == 0.015
+    assert abs(uf.find_tstep(uf.EldUpDef(0.5, 0.4, 0.8)) - 0.0075) < 1e-15
+    assert abs(uf.find_tstep(uf.SinDef(0, 0.5, 0.8, 0)) - 0.015 * 0.2 / 0.4) < 1e-15

@@ -1,0 +1,916 @@
+// ldvm.cu -- device-resident LDVM time stepper (ldvm / ldvm2DOF / ldvmLin / lautat).
+//
+// One time step of the reference's `for istep = 1:nsteps` body (src/lowOrder2D/solvers.jl
+// :178-257, :697-778, :488-644, :76-131) is five launches on one stream, no host round trip:
+//
+//   k_step_head   (1 CTA)  kinematics row / 2DOF Adams-Bashforth, update_boundpos, place_tev
+//   k_induce_direct        bound-point sweep   update_indbound          (70 x N)
+//   k_step_solve  (1 CTA)  Kelvin solve, LESP test, place_lev, Kelvin-Kutta solve, Fourier
+//                          coefficients + rates, update_bv, Spalart merge, calc_forces, mat row
+//   k_induce_direct        wake roll-up        mutual_ind + ind_vel(bv) (N x (N+69))
+//   k_induce_finish        1/2pi, free stream, explicit-Euler convection
+//
+// Vortex counts live in device memory (Regions); grids are sized from host-side upper bounds
+// and surplus blocks exit.  Vortex families are slabs of one SoA allocation with a moving
+// head (popfirst! of the Spalart merge = zero the strength and advance the head).
+#include "../../include/unsflow.h"
+#define UNSFLOW_INDUCE_DECL_ONLY
+#include "induce.cuh"
+#include "runtime.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace unsflow {
+
+constexpr int kNdMax = 256;    // max ndiv
+constexpr int kNaMax = 128;    // max naterm
+constexpr int kSolveThreads = 256;
+
+struct StepState {
+    Regions wake;        // [0] tev, [1] lev, [2] extv, [3] bound vortices (absolute slab indices)
+    Regions bnd;         // [0] = [0, ndiv): targets of the bound sweep
+    long long step;      // steps completed = next row of the kinematics table
+    long long mat_row;   // next row of the mat buffer
+    int levflag;
+    int pad_;
+    double kin[6];       // alpha, h, alphadot, hdot, u, udot
+    double fs[2];        // curfield.u[1], curfield.w[1]
+    double t;
+    double a0, a0dot, a0prev;
+    double cl, cd, cm;
+    double k2[22];       // KinemPar2DOF
+    double sp[11];       // TwoDOFPar
+};
+
+struct LdvmDev {
+    StepState *st;
+    int ndiv, naterm, driver, solve_mode, del_kind;
+    long long del_limit;
+    double del_dist, del_tol;
+    double c, uref, pvt, lespcrit, dt, vc_new, vc4_new;
+    double *theta, *x, *cam, *cam_slope, *bnd_x, *bnd_z, *uind, *wind, *downwash, *aterm, *adot, *aprev;
+    const double *costab, *sintab;   // [(naterm+1)][ndiv]
+    double *wx, *wz, *wg, *wvc4, *wvc, *wvx, *wvz;   // wake slabs
+    const double *kin;
+    long long kin_rows;
+    double *mat;
+    const double *p2u, *p2w;
+    int S2;
+    long long p2stride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// k_step_head
+// ---------------------------------------------------------------------------------------------
+__device__ void dev_update_kinem2dof(const LdvmDev &d, StepState *s) {
+    // update_kinem2DOF, src/lowOrder2D/calcs.jl:604-650 (k2 in KinemPar2DOF field order)
+    double *k = s->k2;
+    const double *p = s->sp;
+    enum { alpha, h, alphadot, hdot, u, udot, alphaddot, hddot, alpha_pr, h_pr, alphadot_pr, alphadot_pr2,
+           alphadot_pr3, hdot_pr, hdot_pr2, hdot_pr3, alphaddot_pr, alphaddot_pr2, alphaddot_pr3, hddot_pr,
+           hddot_pr2, hddot_pr3 };
+    enum { x_alpha, r_alpha, kappa, w_alpha, w_h, w_alphadot, w_hdot, cubic_h_1, cubic_h_3, cubic_alpha_1, cubic_alpha_3 };
+    k[alpha_pr] = k[alpha];
+    k[h_pr] = k[h];
+    k[alphadot_pr3] = k[alphadot_pr2]; k[alphadot_pr2] = k[alphadot_pr]; k[alphadot_pr] = k[alphadot];
+    k[hdot_pr3] = k[hdot_pr2]; k[hdot_pr2] = k[hdot_pr]; k[hdot_pr] = k[hdot];
+    k[alphaddot_pr3] = k[alphaddot_pr2]; k[alphaddot_pr2] = k[alphaddot_pr];
+    k[hddot_pr3] = k[hddot_pr2]; k[hddot_pr2] = k[hddot_pr];
+    const double c = d.c, uref = d.uref, cl = s->cl, cm = s->cm, dt = d.dt;
+    const double m11 = 2. / c;
+    const double m12 = -p[x_alpha] * cos(k[alpha]);
+    const double m21 = -2. * p[x_alpha] * cos(k[alpha]) / c;
+    const double m22 = p[r_alpha] * p[r_alpha];
+    const double R1 = 4 * p[kappa] * uref * uref * cl / (kPi * c * c)
+                      - 2 * p[w_h] * p[w_h] * (p[cubic_h_1] * k[h] + p[cubic_h_3] * (k[h] * k[h] * k[h])) / c
+                      - p[x_alpha] * sin(k[alpha]) * k[alphadot] * k[alphadot];
+    const double R2 = 8 * p[kappa] * uref * uref * cm / (kPi * c * c)
+                      - p[w_alpha] * p[w_alpha] * p[r_alpha] * p[r_alpha]
+                            * (p[cubic_alpha_1] * k[alpha] + p[cubic_alpha_3] * (k[alpha] * k[alpha] * k[alpha]));
+    k[hddot_pr] = (1 / (m11 * m22 - m21 * m12)) * (m22 * R1 - m12 * R2);
+    k[alphaddot_pr] = (1 / (m11 * m22 - m21 * m12)) * (-m21 * R1 + m11 * R2);
+    k[alphadot] = k[alphadot_pr] + (dt / 12.) * (23 * k[alphaddot_pr] - 16 * k[alphaddot_pr2] + 5 * k[alphaddot_pr3]);
+    k[hdot] = k[hdot_pr] + (dt / 12) * (23 * k[hddot_pr] - 16 * k[hddot_pr2] + 5 * k[hddot_pr3]);
+    k[alpha] = k[alpha_pr] + (dt / 12) * (23 * k[alphadot_pr] - 16 * k[alphadot_pr2] + 5 * k[alphadot_pr3]);
+    k[h] = k[h_pr] + (dt / 12) * (23 * k[hdot_pr] - 16 * k[hdot_pr2] + 5 * k[hdot_pr3]);
+    s->kin[2] = k[alphadot]; s->kin[3] = k[hdot]; s->kin[0] = k[alpha]; s->kin[1] = k[h];
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) {
+    StepState *s = d.st;
+    const int tid = threadIdx.x;
+    __shared__ double sh_kin[6];
+    if (tid == 0) {
+        const long long row = s->step < d.kin_rows ? s->step : d.kin_rows - 1;
+        const double *r = d.kin + 9 * row;
+        s->t = r[0];
+        if (d.driver == UNSFLOW_DRIVER_LDVM2DOF) {
+            s->fs[0] = r[7]; s->fs[1] = r[8];
+            dev_update_kinem2dof(d, s);
+        } else {
+            // update_kinem, calcs.jl:97-198 (host-tabulated); update_externalvel :75-92
+            s->kin[0] = r[1]; s->kin[1] = r[2]; s->kin[2] = r[3]; s->kin[3] = r[4]; s->kin[4] = r[5]; s->kin[5] = r[6];
+            if (d.driver != UNSFLOW_DRIVER_LAUTAT) { s->fs[0] = r[7]; s->fs[1] = r[8]; }
+        }
+        for (int k = 0; k < 6; k++) sh_kin[k] = s->kin[k];
+    }
+    __syncthreads();
+    const double alpha = sh_kin[0], alphadot = sh_kin[2], hdot = sh_kin[3], u = sh_kin[4];
+    // update_boundpos, calcs.jl:453-459
+    for (int i = tid; i < d.ndiv; i += blockDim.x) {
+        d.bnd_x[i] = d.bnd_x[i] + d.dt * ((d.pvt * d.c - d.x[i]) * sin(alpha) * alphadot - u + d.cam[i] * cos(alpha) * alphadot);
+        d.bnd_z[i] = d.bnd_z[i] + d.dt * (hdot + (d.pvt * d.c - d.x[i]) * cos(alpha) * alphadot - d.cam[i] * sin(alpha) * alphadot);
+    }
+    __syncthreads();
+    if (tid == 0 && d.driver != UNSFLOW_DRIVER_LDVMLIN) {
+        // place_tev, calcs.jl:375-387
+        const long long b = s->wake.begin[0], e = s->wake.end[0];
+        const int nd = d.ndiv;
+        double xloc, zloc;
+        if (e == b) {
+            xloc = d.bnd_x[nd - 1] + 0.5 * u * d.dt;
+            zloc = d.bnd_z[nd - 1];
+        } else {
+            xloc = d.bnd_x[nd - 1] + (1. / 3.) * (d.wx[e - 1] - d.bnd_x[nd - 1]);
+            zloc = d.bnd_z[nd - 1] + (1. / 3.) * (d.wz[e - 1] - d.bnd_z[nd - 1]);
+        }
+        d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0; d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new;
+        d.wvx[e] = 0.0; d.wvz[e] = 0.0;
+        s->wake.end[0] = e + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_step_solve helpers
+// ---------------------------------------------------------------------------------------------
+// simpleTrapz(y .* cos.(n*theta), theta), utils.jl:105-115, left-to-right like the reference
+__device__ __forceinline__ double trapz_cos(const double *y, const double *theta, const double *cosrow, int nd) {
+    double r = 0.0;
+    double prev = y[0] * cosrow[0];
+    for (int i = 1; i < nd; i++) {
+        const double cur = y[i] * cosrow[i];
+        r += (theta[i] - theta[i - 1]) * (cur + prev);
+        prev = cur;
+    }
+    return r / 2.0;
+}
+
+// unit-strength induced velocity of one vortex at (xv,zv) on bound point i, calcs.jl:469-473
+__device__ __forceinline__ void unit_influence(double xv, double zv, double vc4, double bx, double bz, double *u, double *w) {
+    const double xdist = xv - bx, zdist = zv - bz;
+    const double distsq = xdist * xdist + zdist * zdist;
+    const double den = kTwoPi * sqrt(vc4 + distsq * distsq);
+    *u = -zdist / den;
+    *w = xdist / den;
+}
+
+// downwash at bound point i, calcs.jl:49-54
+__device__ __forceinline__ double downwash_at(const LdvmDev &d, const double *kin, const double *fs, int ib, double ui, double wi) {
+    const double alpha = kin[0], alphadot = kin[2], hdot = kin[3], u = kin[4];
+    const double sa = sin(alpha), ca = cos(alpha);
+    return -(u + fs[0]) * sa - ui * sa + (hdot - fs[1]) * ca - wi * ca - alphadot * (d.x[ib] - d.pvt * d.c)
+           + d.cam_slope[ib] * (ui * ca + (u + fs[0]) * ca + (hdot - fs[1]) * sa - wi * sa);
+}
+
+// one family of the Spalart merge, calcs.jl:550-572 / :577-598
+__device__ void dev_spalart(const LdvmDev &d, long long *begin, long long end, double lx, double lz) {
+    const long long j = *begin;
+    const double gj = d.wg[j], xj = d.wx[j], zj = d.wz[j];
+    const double d_j = sqrt((xj - lx) * (xj - lx) + (zj - lz) * (zj - lz));
+    const double z_j = sqrt(xj * xj + zj * zj);
+    for (long long i = 1; i < 20 && j + i < end; i++) {
+        const long long k = j + i;
+        const double gk = d.wg[k], xk = d.wx[k], zk = d.wz[k];
+        const double d_k = sqrt((xk - lx) * (xk - lx) + (zk - lz) * (zk - lz));
+        const double z_k = sqrt(xk * xk + zk * zk);
+        const double fact = fabs(gj * gk) * fabs(z_j - z_k) / (fabs(gj + gk) * pow(d.del_dist + d_j, 1.5) * pow(d.del_dist + d_k, 1.5));
+        if (fact < d.del_tol) {
+            d.wx[k] = (fabs(gj) * xj + fabs(gk) * xk) / (fabs(gj + gk));
+            d.wz[k] = (fabs(gj) * zj + fabs(gk) * zk) / (fabs(gj + gk));
+            d.wg[k] = gk + gj;
+            d.wg[j] = 0.0;          // popfirst!: dead entry contributes an exact zero
+            *begin = j + 1;
+            break;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) {
+    StepState *s = d.st;
+    const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm;
+    __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
+    __shared__ double uT[kNdMax], wT[kNdMax], uL[kNdMax], wL[kNdMax], gam[kNdMax];
+    __shared__ double aterm[kNaMax + 1];   // aterm[0] unused slot for a0-style indexing: aterm[n] = A_n
+    __shared__ double sc[32];              // scalar scratch
+    __shared__ double kin[6], fs[2];
+    __shared__ int lev_shed;
+    const double urefpi = d.uref * kPi;
+    const double kfac = d.uref * d.c * kPi;
+    const bool lin = d.driver == UNSFLOW_DRIVER_LDVMLIN;
+    const bool lautat = d.driver == UNSFLOW_DRIVER_LAUTAT;
+    const bool twodof = d.driver == UNSFLOW_DRIVER_LDVM2DOF;
+    const double eps_fd = 6.0554544523933395e-06;   // cbrt(eps(Float64))
+
+    if (tid < 6) kin[tid] = s->kin[tid];
+    if (tid < 2) fs[tid] = s->fs[tid];
+    if (tid == 0) lev_shed = 0;
+    // ---- A: induced velocity at the bound points from the sweep partials (update_indbound) ----
+    for (int i = tid; i < nd; i += blockDim.x) {
+        if (lautat) {   // lautat never calls update_indbound: uind/wind persist (solvers.jl:76-92)
+            uind[i] = d.uind[i];
+            wind[i] = d.wind[i];
+        } else {
+            double su = 0.0, sw = 0.0;
+            for (int k = 0; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + i]; sw += d.p2w[(long long)k * d.p2stride + i]; }
+            uind[i] = su * kInvTwoPi;
+            wind[i] = sw * kInvTwoPi;
+        }
+    }
+    __syncthreads();
+
+    // location of the TEV shed this step
+    const long long tb = s->wake.begin[0], te = s->wake.end[0];
+    double xt, zt;
+    if (!lin) {
+        xt = d.wx[te - 1]; zt = d.wz[te - 1];
+    } else {   // ldvmLin places after the solve, solvers.jl:515-523
+        if (te == tb) { xt = d.bnd_x[nd - 1] + 0.5 * kin[4] * d.dt; zt = d.bnd_z[nd - 1]; }
+        else { xt = d.bnd_x[nd - 1] + (1. / 3.) * (d.wx[te - 1] - d.bnd_x[nd - 1]); zt = d.bnd_z[nd - 1] + (1. / 3.) * (d.wz[te - 1] - d.bnd_z[nd - 1]); }
+    }
+    const double a0prev = s->a0prev, aprev1 = d.aprev[0];
+
+    double gt = 0.0, gl = 0.0;      // shed strengths
+    if (!lin) {
+        // ---- B: unit influence of the new TEV; C: affine split of the downwash ----------------
+        for (int i = tid; i < nd; i += blockDim.x) {
+            unit_influence(xt, zt, d.vc4_new, d.bnd_x[i], d.bnd_z[i], &uT[i], &wT[i]);
+            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+            const double sa = sin(kin[0]), ca = cos(kin[0]);
+            dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[i] * (uT[i] * ca - wT[i] * sa);
+        }
+        __syncthreads();
+        // ---- D: A0, A1 as affine functions of the TEV strength --------------------------------
+        if (tid < 4) {
+            const double *y = (tid & 2) ? dw1 : dw;
+            sc[tid] = trapz_cos(y, d.theta, d.costab + (tid & 1) * nd, nd);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi;
+            const double a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
+            const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.);
+            const double Kp = kfac * (a0prev + aprev1 / 2.);
+            // Kelvin condition typedefs.jl:249-251:  K0 + g*K1 - Kp + g = 0
+            const double g = -(K0 - Kp) / (K1 + 1.0);
+            sc[8] = g;
+            // state the reference is left in: at the root (exact) or at NLsolve's last
+            // finite-difference probe g - eps
+            sc[9] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) ? g - eps_fd * fmax(1.0, fabs(g)) : g;
+        }
+        __syncthreads();
+        gt = sc[8];
+        const double gt_applied = sc[9];
+        // ---- F: functor side effects at the applied strength (typedefs.jl:240-247) --------------
+        for (int i = tid; i < nd; i += blockDim.x) {
+            uind[i] += gt_applied * uT[i];
+            wind[i] += gt_applied * wT[i];
+            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+        }
+        __syncthreads();
+        {
+            const int nint = (twodof ? na : 3) + 1;     // update_a2a3adot :2-12 / update_atermdot :14-24
+            for (int n = tid; n < nint; n += blockDim.x) aterm[n] = trapz_cos(dw, d.theta, d.costab + n * nd, nd);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double a0 = -aterm[0] / urefpi;
+            sc[10] = a0;
+            sc[11] = (a0 - a0prev) / d.dt;                        // a0dot, calcs.jl:7
+            lev_shed = (!lautat && fabs(a0) > d.lespcrit) ? 1 : 0;   // solvers.jl:208
+        }
+        {
+            const int nrate = twodof ? na : 3;
+            for (int n = tid + 1; n <= nrate; n += blockDim.x) {
+                const double an = 2. * aterm[n] / urefpi;
+                d.aterm[n - 1] = an;
+                d.adot[n - 1] = (an - d.aprev[n - 1]) / d.dt;     // calcs.jl:8-10 / :20-22
+            }
+        }
+        __syncthreads();
+        if (lautat && tid == 0) {   // lautat saves a0prev/aprev BEFORE update_a2toan (solvers.jl:98-101)
+            // (values are identical either way: a0..a3 do not change afterwards)
+        }
+        if (lev_shed) {
+            // ---- G: place_lev (calcs.jl:409-426) + Kelvin-Kutta 2x2 (typedefs.jl:313-348) ------
+            if (tid == 0) {
+                const long long lb = s->wake.begin[1], le = s->wake.end[1];
+                const double le_vel_x = kin[4] - kin[2] * sin(kin[0]) * d.pvt * d.c + uind[0];
+                const double le_vel_z = -kin[2] * cos(kin[0]) * d.pvt * d.c - kin[3] + wind[0];
+                double xl, zl;
+                if (s->levflag == 0 || le == lb) {
+                    xl = d.bnd_x[0] + 0.5 * le_vel_x * d.dt;
+                    zl = d.bnd_z[0] + 0.5 * le_vel_z * d.dt;
+                } else {
+                    xl = d.bnd_x[0] + (1. / 3.) * (d.wx[le - 1] - d.bnd_x[0]);
+                    zl = d.bnd_z[0] + (1. / 3.) * (d.wz[le - 1] - d.bnd_z[0]);
+                }
+                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = 0.0; d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new;
+                d.wvx[le] = 0.0; d.wvz[le] = 0.0;
+                s->wake.end[1] = le + 1;
+                sc[12] = xl; sc[13] = zl;
+            }
+            __syncthreads();
+            const double xl = sc[12], zl = sc[13];
+            // base for the 2-D solve = current uind minus the STORED tev strength (the functor
+            // subtracts ind_vel of the stored strengths, typedefs.jl:319-328)
+            for (int i = tid; i < nd; i += blockDim.x) {
+                unit_influence(xl, zl, d.vc4_new, d.bnd_x[i], d.bnd_z[i], &uL[i], &wL[i]);
+                uind[i] -= gt * uT[i];
+                wind[i] -= gt * wT[i];
+                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+                const double sa = sin(kin[0]), ca = cos(kin[0]);
+                dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[i] * (uL[i] * ca - wL[i] * sa);
+            }
+            __syncthreads();
+            if (tid < 6) {
+                const double *y = tid < 2 ? dw : (tid < 4 ? dw1 : dw2);
+                sc[tid] = trapz_cos(y, d.theta, d.costab + (tid & 1) * nd, nd);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi;
+                const double a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
+                const double a02 = -sc[4] / urefpi, a12 = 2. * sc[5] / urefpi;
+                const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), K2 = kfac * (a02 + a12 / 2.);
+                const double Kp = kfac * (a0prev + aprev1 / 2.);
+                const double lesp_cond = (sc[10] > 0) ? d.lespcrit : -d.lespcrit;   // typedefs.jl:340-344
+                // (K1+1) gt + (K2+1) gl = Kp - K0 ;   a01 gt + a02 gl = lesp_cond - a00
+                const double m11 = K1 + 1., m12 = K2 + 1., m21 = a01, m22 = a02;
+                const double r1 = Kp - K0, r2 = lesp_cond - a00;
+                const double det = m11 * m22 - m12 * m21;
+                const double g1 = (r1 * m22 - m12 * r2) / det;
+                const double g2 = (m11 * r2 - r1 * m21) / det;
+                sc[8] = g1; sc[14] = g2;
+                sc[9] = g1;
+                sc[15] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) ? g2 - eps_fd * fmax(1.0, fabs(g2)) : g2;
+            }
+            __syncthreads();
+            gt = sc[8]; gl = sc[14];
+            const double gta = sc[9], gla = sc[15];
+            for (int i = tid; i < nd; i += blockDim.x) {
+                uind[i] += gta * uT[i] + gla * uL[i];
+                wind[i] += gta * wT[i] + gla * wL[i];
+                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+            }
+            __syncthreads();
+        }
+        // ---- H: all Fourier coefficients from the final downwash (update_a0anda1 :57-63,
+        //         update_a2toan :66-72) --------------------------------------------------------
+        for (int n = tid; n <= na; n += blockDim.x) aterm[n] = trapz_cos(dw, d.theta, d.costab + n * nd, nd);
+        __syncthreads();
+        if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
+        for (int n = tid + 1; n <= na; n += blockDim.x) d.aterm[n - 1] = aterm[n] = 2. * aterm[n] / urefpi;
+        __syncthreads();
+    } else {
+        // =========================== ldvmLin, solvers.jl:505-613 =================================
+        double *T1 = dw, *T2 = dw1, *T3 = dw2;
+        for (int i = tid; i < nd; i += blockDim.x) {
+            T1[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);                       // :505-510
+            const double xdist = d.bnd_x[i] - xt, zdist = d.bnd_z[i] - zt;             // :525-530
+            const double distsq = xdist * xdist + zdist * zdist;
+            T2[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
+        }
+        __syncthreads();
+        // integrals of T1, T2 against cos(n theta), n = 0..na  -> uL (T1), wL (T2) reused as storage
+        double *c1 = uL, *c2 = wL, *c3 = uT;
+        for (int n = tid; n <= na; n += blockDim.x) {
+            c1[n] = trapz_cos(T1, d.theta, d.costab + n * nd, nd);
+            c2[n] = trapz_cos(T2, d.theta, d.costab + n * nd, nd);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // I = trapz(T.*(cos(theta)-1)) = c[1] - c[0]  (algebraically; :511, :535)
+            const double I1 = d.c * (c1[1] - c1[0]);
+            const double J1 = -c1[0] / urefpi;                                          // :512
+            const double I2 = (c2[1] - c2[0]);
+            const double J2 = -c2[0] / urefpi;                                          // :536
+            const double sig_prev = -kfac * (a0prev + aprev1 / 2.);                     // :533
+            const double tevstr = -(I1 + sig_prev) / (1 + I2);                          // :538
+            const double a0 = J1 + J2 * tevstr;                                         // :541
+            sc[0] = I1; sc[1] = J1; sc[2] = I2; sc[3] = J2; sc[4] = sig_prev;
+            sc[8] = tevstr; sc[10] = a0;
+            lev_shed = fabs(a0) > d.lespcrit ? 1 : 0;                                   // :553
+        }
+        __syncthreads();
+        gt = sc[8];
+        // aterm, a0dot, adot from the TEV-only solution (:542-550)
+        for (int n = tid + 1; n <= na; n += blockDim.x) {
+            const double an = 2. * (c1[n] + gt * c2[n]) / urefpi;
+            aterm[n] = an;
+            d.aterm[n - 1] = an;
+            d.adot[n - 1] = (an - d.aprev[n - 1]) / d.dt;
+        }
+        if (tid == 0) sc[11] = (sc[10] - a0prev) / d.dt;
+        __syncthreads();
+        if (lev_shed) {
+            if (tid == 0) {
+                const long long lb = s->wake.begin[1], le = s->wake.end[1];
+                const double le_vel_x = kin[4] - kin[2] * sin(kin[0]) * d.pvt * d.c + uind[0];
+                const double le_vel_z = -kin[2] * cos(kin[0]) * d.pvt * d.c - kin[3] + wind[0];
+                double xl, zl;
+                if (s->levflag == 0 || le == lb) { xl = d.bnd_x[0] + 0.5 * le_vel_x * d.dt; zl = d.bnd_z[0] + 0.5 * le_vel_z * d.dt; }
+                else { xl = d.bnd_x[0] + (1. / 3.) * (d.wx[le - 1] - d.bnd_x[0]); zl = d.bnd_z[0] + (1. / 3.) * (d.wz[le - 1] - d.bnd_z[0]); }
+                sc[12] = xl; sc[13] = zl;
+            }
+            __syncthreads();
+            const double xl = sc[12], zl = sc[13];
+            for (int i = tid; i < nd; i += blockDim.x) {                                // :572-577
+                const double xdist = d.bnd_x[i] - xl, zdist = d.bnd_z[i] - zl;
+                const double distsq = xdist * xdist + zdist * zdist;
+                T3[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
+            }
+            __syncthreads();
+            for (int n = tid; n <= na; n += blockDim.x) c3[n] = trapz_cos(T3, d.theta, d.costab + n * nd, nd);
+            __syncthreads();
+            if (tid == 0) {
+                const double I1 = sc[0], J1 = sc[1], I2 = sc[2], J2 = sc[3], sig_prev = sc[4];
+                const double lesp_cond = (sc[10] >= 0.) ? d.lespcrit : -d.lespcrit;     // :554-558
+                const double I3 = (c3[1] - c3[0]);                                      // :578
+                const double J3 = -c3[0] / urefpi;                                      // :579
+                const double det = J3 * (I2 + 1.) - J2 * (I3 + 1.);                     // :581
+                const double tevstr = (-J3 * (I1 + sig_prev) + (I3 + 1) * (J1 - lesp_cond)) / det;   // :583
+                const double levstr = (J2 * (I1 + sig_prev) - (I2 + 1) * (J1 - lesp_cond)) / det;    // :584
+                sc[8] = tevstr; sc[14] = levstr;
+                sc[10] = J1 + J2 * tevstr + J3 * levstr;                                // :587
+                const long long le = s->wake.end[1];
+                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = levstr; d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new;
+                d.wvx[le] = 0.0; d.wvz[le] = 0.0;
+                s->wake.end[1] = le + 1;
+            }
+            __syncthreads();
+            gt = sc[8]; gl = sc[14];
+            for (int n = tid + 1; n <= na; n += blockDim.x) {                           // :588-601
+                const double an = 2. * (c1[n] + gt * c2[n] + gl * c3[n]) / urefpi;
+                aterm[n] = an;
+                d.aterm[n - 1] = an;
+            }
+        }
+        if (tid == 0) {   // push the TEV (:594 / :605)
+            d.wx[te] = xt; d.wz[te] = zt; d.wg[te] = gt; d.wvc4[te] = d.vc4_new; d.wvc[te] = d.vc_new;
+            d.wvx[te] = 0.0; d.wvz[te] = 0.0;
+            s->wake.end[0] = te + 1;
+        }
+        __syncthreads();
+    }
+
+    // ---- strengths, flags, previous values (solvers.jl:200, :217-232) ---------------------------
+    if (tid == 0) {
+        if (!lin) {
+            d.wg[s->wake.end[0] - 1] = gt;
+            if (lev_shed) d.wg[s->wake.end[1] - 1] = gl;
+        }
+        s->levflag = lev_shed;
+        s->a0 = sc[10];
+        s->a0dot = sc[11];
+        s->a0prev = sc[10];
+    }
+    {
+        const int nprev = twodof ? na : 3;
+        for (int n = tid; n < nprev; n += blockDim.x) d.aprev[n] = aterm[n + 1];
+    }
+    for (int i = tid; i < nd; i += blockDim.x) { d.uind[i] = uind[i]; d.wind[i] = wind[i]; d.downwash[i] = dw[i]; }
+    __syncthreads();
+
+    // ---- I: update_bv, calcs.jl:204-219 -------------------------------------------------------
+    const double a0 = sc[10];
+    for (int ib = tid; ib < nd; ib += blockDim.x) {
+        double g = (a0 * (1 + d.costab[nd + ib]));
+        const double sth = d.sintab[nd + ib];
+        for (int ia = 1; ia <= na; ia++) g = g + aterm[ia] * d.sintab[ia * nd + ib] * sth;
+        gam[ib] = g * d.uref * d.c;
+    }
+    __syncthreads();
+    const long long bv0 = s->wake.begin[3];
+    for (int ib = tid + 1; ib < nd; ib += blockDim.x) {
+        d.wg[bv0 + ib - 1] = (gam[ib] + gam[ib - 1]) * (d.theta[1] - d.theta[0]) / 2.;
+        d.wx[bv0 + ib - 1] = (d.bnd_x[ib] + d.bnd_x[ib - 1]) / 2.;
+        d.wz[bv0 + ib - 1] = (d.bnd_z[ib] + d.bnd_z[ib - 1]) / 2.;
+    }
+    __syncthreads();
+
+    // ---- J: controlVortCount, calcs.jl:541-602 (thread 0) ; K: calc_forces postprocess.jl:1-32 --
+    if (tid == 0 && d.del_kind == UNSFLOW_DEL_SPALART) {
+        const int mid = (int)nearbyint(nd / 2.0) - 1;    // Int(round(ndiv/2)), solvers.jl:238
+        const double lx = d.bnd_x[mid], lz = d.bnd_z[mid];
+        if (s->wake.end[0] - s->wake.begin[0] > d.del_limit) {
+            dev_spalart(d, &s->wake.begin[0], s->wake.end[0], lx, lz);
+            if (s->wake.end[1] - s->wake.begin[1] > d.del_limit) dev_spalart(d, &s->wake.begin[1], s->wake.end[1], lx, lz);
+        }
+    }
+    if (tid == 32) {
+        const double alpha = kin[0], hdot = kin[3], u = kin[4];
+        const double sa = sin(alpha), ca = cos(alpha);
+        const double a1 = aterm[1], a2 = aterm[2];
+        const double a0dot = sc[11];
+        const double ad1 = d.adot[0], ad2 = d.adot[1], ad3 = d.adot[2];
+        const double ufac = (u + fs[0]) * ca / d.uref + (hdot - fs[1]) * sa / d.uref;
+        const double cnc = 2 * kPi * ufac * (a0 + a1 / 2.);
+        const double cnnc = 2 * kPi * (3 * d.c * a0dot / (4 * d.uref) + d.c * ad1 / (4 * d.uref) + d.c * ad2 / (8 * d.uref));
+        const double cs = 2 * kPi * a0 * a0;
+        double nonl = 0, nonl_m = 0;
+        for (int ib = 0; ib < nd - 1; ib++) {
+            const double gb = (gam[ib + 1] + gam[ib]) * (d.theta[1] - d.theta[0]) / 2.;
+            const double v = (uind[ib] * ca - wind[ib] * sa);
+            nonl = nonl + v * gb;
+            nonl_m = nonl_m + v * d.x[ib] * gb;
+        }
+        nonl = nonl * 2. / (d.uref * d.uref * d.c);
+        nonl_m = nonl_m * 2. / (d.uref * d.uref * d.c * d.c);
+        const double cn = cnc + cnnc + nonl;
+        const double cl = cn * ca + cs * sa;
+        const double cd = cn * sa - cs * ca;
+        const double cm = cn * d.pvt
+                          - 2 * kPi * (ufac * (a0 / 4. + a1 / 4. - a2 / 8.)
+                                       + (d.c / d.uref) * (7. * a0dot / 16. + 3. * ad1 / 16. + ad2 / 16. - ad3 / 64.))
+                          - nonl_m;
+        s->cl = cl; s->cd = cd; s->cm = cm;
+        double *m = d.mat + 8 * s->mat_row;
+        m[0] = s->t; m[1] = kin[0]; m[2] = kin[1]; m[3] = kin[4]; m[4] = a0; m[5] = cl; m[6] = cd; m[7] = cm;   // solvers.jl:255
+        s->mat_row += 1;
+        s->step += 1;
+    }
+}
+
+}  // namespace unsflow
+
+using namespace unsflow;
+
+struct unsflow_ldvm {
+    unsflow_opts opts{};
+    int ndiv = 0, naterm = 0;
+    int64_t cap_t = 0, cap_l = 0, cap_e = 0, bvpad = 0, tot = 0;
+    int64_t off_t = 0, off_l = 0, off_e = 0, off_b = 0;
+    int64_t ntev0 = 0, nlev0 = 0, nextv = 0;
+    int64_t steps_done = 0;          // since create
+    int64_t mat_cap = 0;
+    bool uniform = true;
+    double vc4u = 1.0;
+    // tightened count knowledge (async read-back)
+    int64_t known_step = 0, known_ntev_end = 0, known_nlev_end = 0;
+    DevBuf<StepState> st;
+    DevBuf<double> surf;      // 9*ndiv + 3*naterm
+    DevBuf<double> tabs;      // costab, sintab
+    DevBuf<double> wake;      // 7 slabs
+    DevBuf<double> kin;       // rows x 9
+    DevBuf<double> mat;       // mat_cap x 8
+    DevBuf<double> p2;        // bound-sweep partials [2][S2max][ndivpad]
+    DevBuf<double> p1;        // roll-up partials [2][S1max][tot]
+    int S2max = 1, S1max = 1;
+    int64_t ndivpad = 0;
+    int64_t kin_rows = 0;
+    LdvmDev dev{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc = nullptr;
+    StepState *pinned = nullptr;
+    bool readback_pending = false;
+    int64_t readback_step = 0;
+    int64_t launches = 0;
+    float last_ms = 0;
+};
+
+static int ldvm_sync_counts(unsflow_ldvm *h, StepState *out) {
+    UF_CUDA(cudaMemcpyAsync(out, h->st.p, sizeof(StepState), cudaMemcpyDeviceToHost, h->stream));
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" {
+
+int unsflow_ldvm_destroy(unsflow_ldvm *h) {
+    if (!h) return 0;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evc) cudaEventDestroy(h->evc);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow_field *fl, const unsflow_opts *op) {
+    UF_CHECK(out != nullptr, "unsflow_ldvm_create: null handle pointer");
+    *out = nullptr;
+    UF_CHECK(sf && fl && op, "unsflow_ldvm_create: null argument");
+    UF_CHECK(sf->ndiv >= 3 && sf->ndiv <= kNdMax, "unsflow_ldvm_create: ndiv=%d outside [3,%d]", sf->ndiv, kNdMax);
+    UF_CHECK(sf->naterm >= 3 && sf->naterm <= kNaMax, "unsflow_ldvm_create: naterm=%d outside [3,%d]", sf->naterm, kNaMax);
+    UF_CHECK(op->driver >= 0 && op->driver <= 3, "unsflow_ldvm_create: bad driver %d", op->driver);
+    UF_CHECK(op->solve_mode == 0 || op->solve_mode == 1, "unsflow_ldvm_create: bad solve_mode %d", op->solve_mode);
+    UF_CHECK(op->delvort_kind == 0 || op->delvort_kind == 1, "unsflow_ldvm_create: bad delvort_kind %d", op->delvort_kind);
+    UF_CHECK(op->max_steps >= 0 && op->dt > 0, "unsflow_ldvm_create: need max_steps >= 0 and dt > 0");
+    UF_CHECK(sf->theta && sf->x && sf->cam && sf->cam_slope && sf->bnd_x && sf->bnd_z && sf->uind && sf->wind &&
+                 sf->downwash && sf->aterm && sf->adot && sf->aprev,
+             "unsflow_ldvm_create: null surf array");
+    UF_CHECK(sf->bv.n == sf->ndiv - 1, "unsflow_ldvm_create: surf.bv must hold ndiv-1 vortices");
+    if (int rc = require_device()) return rc;
+    if (op->device >= 0) UF_CUDA(cudaSetDevice(op->device));
+    unsflow_ldvm *h = new (std::nothrow) unsflow_ldvm();
+    UF_CHECK(h != nullptr, "out of host memory");
+    auto fail = [&](int rc) { unsflow_ldvm_destroy(h); return rc; };
+    h->opts = *op;
+    const int nd = h->ndiv = sf->ndiv, na = h->naterm = sf->naterm;
+    h->ntev0 = fl->tev.n; h->nlev0 = fl->lev.n; h->nextv = fl->extv.n;
+    h->cap_t = round_up(h->ntev0 + op->max_steps + 1, kTS);
+    h->cap_l = round_up(h->nlev0 + op->max_steps + 1, kTS);
+    h->cap_e = round_up(std::max<int64_t>(h->nextv, 1), kTS);
+    h->bvpad = round_up(nd - 1, kTS);
+    h->off_t = 0; h->off_l = h->cap_t; h->off_e = h->off_l + h->cap_l; h->off_b = h->off_e + h->cap_e;
+    h->tot = h->off_b + h->bvpad;
+    h->mat_cap = std::max<int64_t>(op->max_steps, 1);
+    h->ndivpad = round_up(nd, 8);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(2); }
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evc);
+    if (cudaMallocHost((void **)&h->pinned, sizeof(StepState)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(2); }
+    const int64_t tot = h->tot;
+    h->S2max = 256;
+    h->S1max = (int)std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)2e9 / (16 * tot)));
+    if (h->st.alloc(1) || h->surf.alloc(9 * nd + 3 * na) || h->tabs.alloc(2 * (na + 1) * nd) || h->wake.alloc(7 * tot) ||
+        h->mat.alloc(8 * h->mat_cap) || h->p2.alloc(2 * (int64_t)h->S2max * h->ndivpad) ||
+        h->p1.alloc(2 * (int64_t)h->S1max * tot))
+        return fail(2);
+    if (h->wake.zero(h->stream) || h->mat.zero(h->stream)) return fail(2);
+
+    // ---- host staging -------------------------------------------------------------------------
+    std::vector<double> hs((size_t)(9 * nd + 3 * na));
+    const double *sarr[9] = {sf->theta, sf->x, sf->cam, sf->cam_slope, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
+    for (int k = 0; k < 9; k++) memcpy(&hs[(size_t)k * nd], sarr[k], sizeof(double) * nd);
+    memcpy(&hs[(size_t)9 * nd], sf->aterm, sizeof(double) * na);
+    memcpy(&hs[(size_t)9 * nd + na], sf->adot, sizeof(double) * na);
+    memcpy(&hs[(size_t)9 * nd + 2 * na], sf->aprev, sizeof(double) * na);
+    std::vector<double> ht((size_t)(2 * (na + 1) * nd));
+    for (int n = 0; n <= na; n++)
+        for (int i = 0; i < nd; i++) {
+            // same expressions as the reference: cos.(ia*theta) calcs.jl:4, sin(ia*theta) :209
+            ht[(size_t)n * nd + i] = n == 0 ? 1.0 : std::cos(n * sf->theta[i]);
+            ht[(size_t)(na + 1) * nd + (size_t)n * nd + i] = std::sin(n * sf->theta[i]);
+        }
+    std::vector<double> hw((size_t)(7 * tot), 0.0);
+    double *wx = &hw[0], *wz = &hw[tot], *wg = &hw[2 * tot], *wv4 = &hw[3 * tot], *wvc = &hw[4 * tot], *wvx = &hw[5 * tot], *wvz = &hw[6 * tot];
+    const double vc_new = 0.02 * sf->c;
+    for (int64_t i = 0; i < tot; i++) { wv4[i] = vc_new * vc_new * vc_new * vc_new; wvc[i] = vc_new; }
+    bool uni = true;
+    auto put = [&](const unsflow_vorts &v, int64_t off) -> int {
+        UF_CHECK(v.n == 0 || (v.x && v.z && v.s && v.vc), "unsflow_ldvm_create: null vortex array");
+        for (int64_t i = 0; i < v.n; i++) {
+            wx[off + i] = v.x[i]; wz[off + i] = v.z[i]; wg[off + i] = v.s[i];
+            wvc[off + i] = v.vc[i]; wv4[off + i] = v.vc[i] * v.vc[i] * v.vc[i] * v.vc[i];
+            wvx[off + i] = v.vx ? v.vx[i] : 0.0; wvz[off + i] = v.vz ? v.vz[i] : 0.0;
+            uni = uni && v.vc[i] == vc_new;
+        }
+        return 0;
+    };
+    if (put(fl->tev, h->off_t) || put(fl->lev, h->off_l) || put(fl->extv, h->off_e) || put(sf->bv, h->off_b)) return fail(1);
+    h->uniform = uni;
+    h->vc4u = vc_new * vc_new * vc_new * vc_new;
+
+    StepState s0;
+    memset(&s0, 0, sizeof(s0));
+    s0.wake.begin[0] = h->off_t; s0.wake.end[0] = h->off_t + h->ntev0;
+    s0.wake.begin[1] = h->off_l; s0.wake.end[1] = h->off_l + h->nlev0;
+    s0.wake.begin[2] = h->off_e; s0.wake.end[2] = h->off_e + h->nextv;
+    s0.wake.begin[3] = h->off_b; s0.wake.end[3] = h->off_b + nd - 1;
+    s0.bnd.begin[0] = 0; s0.bnd.end[0] = nd;
+    s0.levflag = sf->levflag;
+    for (int k = 0; k < 6; k++) s0.kin[k] = sf->kinem[k];
+    s0.fs[0] = fl->u; s0.fs[1] = fl->w;
+    s0.a0 = sf->a0; s0.a0dot = sf->a0dot; s0.a0prev = sf->a0prev;
+    *h->pinned = s0;
+    h->known_step = 0; h->known_ntev_end = h->ntev0; h->known_nlev_end = h->nlev0;
+
+    cudaStream_t st = h->stream;
+    if (cudaMemcpyAsync(h->st.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(h->surf.p, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(h->tabs.p, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(h->wake.p, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("unsflow_ldvm_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(2);
+    }
+
+    LdvmDev &d = h->dev;
+    d.st = h->st.p;
+    d.ndiv = nd; d.naterm = na; d.driver = op->driver; d.solve_mode = op->solve_mode; d.del_kind = op->delvort_kind;
+    d.del_limit = op->del_limit; d.del_dist = op->del_dist; d.del_tol = op->del_tol;
+    d.c = sf->c; d.uref = sf->uref; d.pvt = sf->pvt; d.lespcrit = sf->lespcrit; d.dt = op->dt;
+    d.vc_new = vc_new; d.vc4_new = h->vc4u;
+    double *sp = h->surf.p;
+    d.theta = sp; d.x = sp + nd; d.cam = sp + 2 * nd; d.cam_slope = sp + 3 * nd; d.bnd_x = sp + 4 * nd; d.bnd_z = sp + 5 * nd;
+    d.uind = sp + 6 * nd; d.wind = sp + 7 * nd; d.downwash = sp + 8 * nd;
+    d.aterm = sp + 9 * nd; d.adot = sp + 9 * nd + na; d.aprev = sp + 9 * nd + 2 * na;
+    d.costab = h->tabs.p; d.sintab = h->tabs.p + (int64_t)(na + 1) * nd;
+    double *wp = h->wake.p;
+    d.wx = wp; d.wz = wp + tot; d.wg = wp + 2 * tot; d.wvc4 = wp + 3 * tot; d.wvc = wp + 4 * tot; d.wvx = wp + 5 * tot; d.wvz = wp + 6 * tot;
+    d.kin = nullptr; d.kin_rows = 0;
+    d.mat = h->mat.p;
+    d.p2u = h->p2.p; d.p2w = h->p2.p + (int64_t)h->S2max * h->ndivpad; d.p2stride = h->ndivpad; d.S2 = 1;
+    *out = h;
+    return 0;
+}
+
+int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *table) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_set_kinematics: null handle");
+    UF_CHECK(nrows > 0 && table != nullptr, "unsflow_ldvm_set_kinematics: empty table");
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->kin.alloc(9 * nrows)) return 2;
+    UF_CUDA(cudaMemcpyAsync(h->kin.p, table, sizeof(double) * 9 * nrows, cudaMemcpyHostToDevice, h->stream));
+    // rows are consumed from the start of the new table
+    StepState *zero_step = h->pinned;
+    (void)zero_step;
+    long long z = 0;
+    UF_CUDA(cudaMemcpyAsync(&h->st.p->step, &z, sizeof(z), cudaMemcpyHostToDevice, h->stream));
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    h->kin_rows = nrows;
+    h->dev.kin = h->kin.p;
+    h->dev.kin_rows = nrows;
+    return 0;
+}
+
+int unsflow_ldvm_set_2dof(unsflow_ldvm *h, const double *sp11, const double *k22) {
+    UF_CHECK(h && sp11 && k22, "unsflow_ldvm_set_2dof: null argument");
+    UF_CUDA(cudaMemcpyAsync(h->st.p->sp, sp11, sizeof(double) * 11, cudaMemcpyHostToDevice, h->stream));
+    UF_CUDA(cudaMemcpyAsync(h->st.p->k2, k22, sizeof(double) * 22, cudaMemcpyHostToDevice, h->stream));
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int unsflow_ldvm_get_2dof(unsflow_ldvm *h, double *k22) {
+    UF_CHECK(h && k22, "unsflow_ldvm_get_2dof: null argument");
+    UF_CUDA(cudaMemcpyAsync(k22, h->st.p->k2, sizeof(double) * 22, cudaMemcpyDeviceToHost, h->stream));
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_run: null handle");
+    UF_CHECK(nsteps >= 0, "unsflow_ldvm_run: negative nsteps");
+    UF_CHECK(nsteps == 0 || mat_out != nullptr, "unsflow_ldvm_run: null mat_out");
+    UF_CHECK(h->steps_done + nsteps <= h->opts.max_steps, "unsflow_ldvm_run: %lld steps exceed opts.max_steps=%lld",
+             (long long)(h->steps_done + nsteps), (long long)h->opts.max_steps);
+    UF_CHECK(h->dev.kin != nullptr, "unsflow_ldvm_run: call unsflow_ldvm_set_kinematics first");
+    if (nsteps == 0) return 0;
+    cudaStream_t st = h->stream;
+    const int driver = h->opts.driver;
+    const int smc = sm_count();
+    const int order = rsqrt_order();
+    // mat rows of this call start at row 0 of the device buffer
+    long long z = 0;
+    UF_CUDA(cudaMemcpyAsync(&h->st.p->mat_row, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+    h->launches = 0;
+    UF_CUDA(cudaEventRecord(h->ev0, st));
+    const int64_t tot = h->tot;
+    for (int64_t is = 0; is < nsteps; is++) {
+        // ---- poll the asynchronous count read-back (never blocks) ------------------------------
+        if (h->readback_pending && cudaEventQuery(h->evc) == cudaSuccess) {
+            h->readback_pending = false;
+            h->known_step = h->readback_step;
+            h->known_ntev_end = h->pinned->wake.end[0] - h->off_t;
+            h->known_nlev_end = h->pinned->wake.end[1] - h->off_l;
+        }
+        const int64_t since = h->steps_done - h->known_step + 1;
+        const int64_t ntev_ub = std::min(h->cap_t, h->known_ntev_end + since);
+        const int64_t nlev_ub = std::min(h->cap_l, h->known_nlev_end + since);
+        const int64_t nwake_ub = ntev_ub + nlev_ub + h->nextv;
+
+        k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+        h->launches++;
+        if (driver != UNSFLOW_DRIVER_LAUTAT) {
+            // bound-point sweep (update_indbound, calcs.jl:35-38): targets = bound points
+            InducePlan p2 = plan_induce(h->ndiv, 1, nwake_ub, 3, smc, h->S2max);
+            InduceArgs a;
+            a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
+            a.tx = h->dev.bnd_x; a.tz = h->dev.bnd_z;
+            a.sreg = &h->st.p->wake; a.treg = &h->st.p->bnd; a.nsreg = 3; a.ntreg = 1;
+            a.vc4_uniform = h->vc4u;
+            a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
+            if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
+            h->dev.S2 = p2.S;
+            h->launches++;
+        }
+        k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+        h->launches++;
+        {
+            // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
+            InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + h->ndiv - 1, 4, smc, h->S1max);
+            InduceArgs a;
+            a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
+            a.tx = h->dev.wx; a.tz = h->dev.wz;
+            a.sreg = &h->st.p->wake; a.treg = &h->st.p->wake; a.nsreg = 4; a.ntreg = 3;
+            a.vc4_uniform = h->vc4u;
+            a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
+            if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+            FinishArgs f;
+            memset(&f, 0, sizeof(f));
+            f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
+            f.treg = &h->st.p->wake; f.ntreg = 3;
+            f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
+            f.fs = h->st.p->fs; f.dt = h->opts.dt;
+            if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
+            h->launches += 2;
+        }
+        UF_CUDA(cudaGetLastError());
+        h->steps_done++;
+        if (!h->readback_pending && (h->steps_done % 64) == 0) {
+            UF_CUDA(cudaMemcpyAsync(h->pinned, h->st.p, sizeof(StepState), cudaMemcpyDeviceToHost, st));
+            UF_CUDA(cudaEventRecord(h->evc, st));
+            h->readback_pending = true;
+            h->readback_step = h->steps_done;
+        }
+    }
+    UF_CUDA(cudaEventRecord(h->ev1, st));
+    // mat: device row-major [nsteps][8] -> caller column-major nsteps x 8
+    std::vector<double> hm((size_t)(8 * nsteps));
+    UF_CUDA(cudaMemcpyAsync(hm.data(), h->mat.p, sizeof(double) * 8 * nsteps, cudaMemcpyDeviceToHost, st));
+    UF_CUDA(cudaStreamSynchronize(st));
+    h->readback_pending = false;
+    for (int64_t i = 0; i < nsteps; i++)
+        for (int j = 0; j < 8; j++) mat_out[i + j * nsteps] = hm[(size_t)(8 * i + j)];
+    UF_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    // exact counts are known now
+    StepState s;
+    if (int rc = ldvm_sync_counts(h, &s)) return rc;
+    h->known_step = h->steps_done;
+    h->known_ntev_end = s.wake.end[0] - h->off_t;
+    h->known_nlev_end = s.wake.end[1] - h->off_l;
+    return 0;
+}
+
+int unsflow_ldvm_counts(unsflow_ldvm *h, int64_t *ntev, int64_t *nlev, int64_t *nextv) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_counts: null handle");
+    StepState s;
+    if (int rc = ldvm_sync_counts(h, &s)) return rc;
+    if (ntev) *ntev = s.wake.end[0] - s.wake.begin[0];
+    if (nlev) *nlev = s.wake.end[1] - s.wake.begin[1];
+    if (nextv) *nextv = s.wake.end[2] - s.wake.begin[2];
+    return 0;
+}
+
+int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *sf, unsflow_field *fl) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_get_state: null handle");
+    StepState s;
+    if (int rc = ldvm_sync_counts(h, &s)) return rc;
+    cudaStream_t st = h->stream;
+    const int nd = h->ndiv, na = h->naterm;
+    const int64_t tot = h->tot;
+    if (sf) {
+        UF_CHECK(sf->ndiv == nd && sf->naterm == na, "unsflow_ldvm_get_state: surf dimensions differ from the handle's");
+        std::vector<double> hs((size_t)(9 * nd + 3 * na));
+        UF_CUDA(cudaMemcpyAsync(hs.data(), h->surf.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, st));
+        UF_CUDA(cudaStreamSynchronize(st));
+        double *sarr[9] = {nullptr, nullptr, nullptr, nullptr, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
+        for (int k = 4; k < 9; k++) if (sarr[k]) memcpy(sarr[k], &hs[(size_t)k * nd], sizeof(double) * nd);
+        if (sf->aterm) memcpy(sf->aterm, &hs[(size_t)9 * nd], sizeof(double) * na);
+        if (sf->adot) memcpy(sf->adot, &hs[(size_t)9 * nd + na], sizeof(double) * na);
+        if (sf->aprev) memcpy(sf->aprev, &hs[(size_t)9 * nd + 2 * na], sizeof(double) * na);
+        sf->levflag = s.levflag;
+        for (int k = 0; k < 6; k++) sf->kinem[k] = s.kin[k];
+        sf->a0 = s.a0; sf->a0dot = s.a0dot; sf->a0prev = s.a0prev;
+    }
+    auto get = [&](unsflow_vorts *v, int reg) -> int {
+        if (!v) return 0;
+        const int64_t b = s.wake.begin[reg], n = s.wake.end[reg] - b;
+        UF_CHECK(v->n >= n, "unsflow_ldvm_get_state: vortex array capacity %lld < count %lld", (long long)v->n, (long long)n);
+        double *dst[6] = {v->x, v->z, v->s, v->vc, v->vx, v->vz};
+        const int slab[6] = {0, 1, 2, 4, 5, 6};
+        for (int k = 0; k < 6; k++)
+            if (dst[k] && n > 0)
+                UF_CUDA(cudaMemcpyAsync(dst[k], h->wake.p + slab[k] * tot + b, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        v->n = n;
+        return 0;
+    };
+    if (sf) if (int rc = get(&sf->bv, 3)) return rc;
+    if (fl) {
+        if (int rc = get(&fl->tev, 0)) return rc;
+        if (int rc = get(&fl->lev, 1)) return rc;
+        if (int rc = get(&fl->extv, 2)) return rc;
+        fl->u = s.fs[0]; fl->w = s.fs[1];
+    }
+    UF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_timing: null handle");
+    if (ms_total) *ms_total = h->last_ms;
+    if (n_launches) *n_launches = h->launches;
+    return 0;
+}
+
+int unsflow_ldvm_batch_run(const unsflow_surf *, const unsflow_opts *, int64_t, int64_t, const double *, const double *,
+                           double *, int64_t *, int64_t *) {
+    set_error("unsflow_ldvm_batch_run: not implemented yet");
+    return 5;
+}
+
+}  // extern "C"

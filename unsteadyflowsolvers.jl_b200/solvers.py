@@ -1,0 +1,234 @@
+"""Drop-in `ldvm` / `ldvm2DOF` (+ `ldvmLin`, `lautat`) with the reference's signatures
+(src/lowOrder2D/solvers.jl:144, :657, :448, :42): the whole `for istep` loop runs
+device-resident inside libunsflow_cuda; this host side only tabulates the prescribed
+motion, uploads the state once and downloads it at the end (and at write stamps)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as cabi
+from .delvort import delNone, delSpalart
+from .kinem import KinemPar, eval_externalvel, eval_kinem
+from .typedefs import KinemPar2DOF, TwoDFlowField, TwoDOFPar, TwoDSurf, VortList
+
+
+def _vorts_struct(v: VortList, keep):
+    """unsflow_vorts view of a VortList (arrays kept alive in `keep`)."""
+    arrs = [cabi.f64(getattr(v, k)).copy() for k in ("x", "z", "s", "vc", "vx", "vz")]
+    keep.append(arrs)
+    st = cabi.Vorts()
+    st.n = len(v)
+    for k, a in zip(("x", "z", "s", "vc", "vx", "vz"), arrs):
+        setattr(st, k, cabi.dptr(a) if a.shape[0] else None)
+    return st
+
+
+def surf_struct(surf: TwoDSurf, keep):
+    s = cabi.Surf()
+    s.ndiv, s.naterm = surf.ndiv, surf.naterm
+    s.c, s.uref, s.pvt = surf.c, surf.uref, surf.pvt
+    s.lespcrit = float(surf.lespcrit[0])
+    s.levflag = int(surf.levflag[0])
+    k = surf.kinem
+    s.kinem[:] = [k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot]
+    s.a0, s.a0dot, s.a0prev = float(surf.a0[0]), float(surf.a0dot[0]), float(surf.a0prev[0])
+    for name in ("theta", "x", "cam", "cam_slope", "bnd_x", "bnd_z", "uind", "wind", "downwash", "aterm", "adot", "aprev"):
+        a = cabi.f64(getattr(surf, name))
+        if a is not getattr(surf, name):
+            setattr(surf, name, a)
+        setattr(s, name, cabi.dptr(a))
+    s.bv = _vorts_struct(surf.bv, keep)
+    return s
+
+
+def field_struct(curfield: TwoDFlowField, keep):
+    f = cabi.Field()
+    f.u, f.w = float(curfield.u[0]), float(curfield.w[0])
+    f.tev = _vorts_struct(curfield.tev, keep)
+    f.lev = _vorts_struct(curfield.lev, keep)
+    f.extv = _vorts_struct(curfield.extv, keep)
+    return f
+
+
+def kinematics_table(surf: TwoDSurf, curfield: TwoDFlowField, nsteps: int, dt: float, t0: float = 0.0,
+                     external=True, two_dof=False):
+    """nsteps x 9 table [t, alpha, h, alphadot, hdot, u, udot, U, W] at the running-sum times
+    t = t + dt (solvers.jl:180), i.e. what update_externalvel (calcs.jl:75-92) and update_kinem
+    (calcs.jl:97-198) would set at each step."""
+    tab = np.zeros((nsteps, 9))
+    t = t0
+    k = KinemPar(**vars(surf.kinem))
+    U, W = float(curfield.u[0]), float(curfield.w[0])
+    for i in range(nsteps):
+        t = t + dt
+        if external:
+            U, W = eval_externalvel(curfield.velX, curfield.velZ, t, U, W)
+        if not two_dof:
+            k = eval_kinem(surf.kindef, t, surf.c, surf.uref, k)
+        tab[i] = [t, k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot, U, W]
+    return tab
+
+
+class LdvmHandle:
+    """RAII wrapper of unsflow_ldvm (unsflow_ldvm_create .. unsflow_ldvm_destroy)."""
+
+    def __init__(self, surf, curfield, opts):
+        self._h = C.c_void_p()
+        self._keep = []
+        self.surf, self.curfield = surf, curfield
+        s = surf_struct(surf, self._keep)
+        f = field_struct(curfield, self._keep)
+        cabi.check(cabi.lib().unsflow_ldvm_create(C.byref(self._h), C.byref(s), C.byref(f), C.byref(opts)))
+
+    def close(self):
+        if self._h:
+            cabi.lib().unsflow_ldvm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_kinematics(self, table):
+        t = cabi.f64(table)
+        cabi.check(cabi.lib().unsflow_ldvm_set_kinematics(self._h, t.shape[0], cabi.dptr(t)))
+
+    def set_2dof(self, strpar: TwoDOFPar, kinem: KinemPar2DOF):
+        a, b = strpar.as_array(), kinem.as_array()
+        cabi.check(cabi.lib().unsflow_ldvm_set_2dof(self._h, cabi.dptr(a), cabi.dptr(b)))
+
+    def get_2dof(self, kinem: KinemPar2DOF):
+        b = np.zeros(22)
+        cabi.check(cabi.lib().unsflow_ldvm_get_2dof(self._h, cabi.dptr(b)))
+        kinem.from_array(b)
+
+    def run(self, nsteps):
+        mat = np.zeros((nsteps, 8), order="F")
+        cabi.check(cabi.lib().unsflow_ldvm_run(self._h, nsteps, mat.ctypes.data_as(cabi.c_double_p)))
+        return mat
+
+    def timing(self):
+        ms, nl = C.c_float(0), C.c_int64(0)
+        cabi.check(cabi.lib().unsflow_ldvm_timing(self._h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def counts(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        cabi.check(cabi.lib().unsflow_ldvm_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def download(self):
+        """unsflow_ldvm_get_state -> mutate surf and curfield in place, like the reference."""
+        surf, fld = self.surf, self.curfield
+        nt, nl, ne = self.counts()
+        keep = []
+        for v, n in ((fld.tev, nt), (fld.lev, nl), (fld.extv, ne)):
+            v.resize(n)
+        s = surf_struct(surf, keep)
+        f = field_struct(fld, keep)
+        cabi.check(cabi.lib().unsflow_ldvm_get_state(self._h, C.byref(s), C.byref(f)))
+        surf.levflag[0] = s.levflag
+        k = surf.kinem
+        k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = list(s.kinem)
+        surf.a0[0], surf.a0dot[0], surf.a0prev[0] = s.a0, s.a0dot, s.a0prev
+        fld.u[0], fld.w[0] = f.u, f.w
+        # _vorts_struct made copies: copy back (keep order: bv, tev, lev, extv)
+        for v, arrs in zip((surf.bv, fld.tev, fld.lev, fld.extv), keep):
+            v.assign(*arrs)
+
+
+def _opts(driver, dt, nsteps, delvort, solve_mode):
+    o = cabi.Opts()
+    o.driver, o.solve_mode, o.device = driver, solve_mode, -1
+    if isinstance(delvort, delSpalart):
+        o.delvort_kind, o.del_limit, o.del_dist, o.del_tol = cabi.DEL_SPALART, delvort.limit, delvort.dist, delvort.tol
+    elif delvort is None or isinstance(delvort, delNone):
+        o.delvort_kind = cabi.DEL_NONE
+    else:
+        raise TypeError("delvort must be delNone() or delSpalart(...)")
+    o.dt, o.max_steps = dt, nsteps
+    return o
+
+
+def _write_results_summary(mat):
+    """solvers.jl:261-264"""
+    with open("resultsSummary", "w") as f:
+        f.write("#time \talpha(deg) \th/c \tu/uref \tA0 \tCl \tCd \tCm \n")
+        for row in mat:
+            f.write("\t".join(repr(float(v)) for v in row) + "\n")
+
+
+def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort, maxwrite, nround,
+         solve_mode, strpar=None, kinem=None, write_summary=True):
+    if startflag == 0:
+        t = 0.0
+    elif startflag == 1:
+        raise NotImplementedError("startflag=1 (restart from resultsSummary) is broken in the reference "
+                                  "(solvers.jl:150-155) and not supported")
+    else:
+        raise ValueError("invalid start flag, should be 0 or 1")  # solvers.jl:157
+    dt = dtstar * surf.c / surf.uref  # solvers.jl:161
+    two_dof = driver == cabi.DRIVER_LDVM2DOF
+    table = kinematics_table(surf, curfield, nsteps, dt, t, external=(driver != cabi.DRIVER_LAUTAT), two_dof=two_dof)
+    h = LdvmHandle(surf, curfield, _opts(driver, dt, nsteps, delvort, solve_mode))
+    try:
+        if two_dof:
+            h.set_2dof(strpar, kinem)
+        h.set_kinematics(table)
+        write_steps = []
+        if writeflag == 1:  # solvers.jl:164-175
+            for i in range(1, maxwrite + 1):
+                write_steps.append(int(round(writeInterval * float(i) / dt)))
+        mats, done = [], 0
+        stops = sorted(set(s for s in write_steps if 0 < s <= nsteps) | {nsteps})
+        for stop in stops:
+            if stop > done:
+                mats.append(h.run(stop - done))
+                done = stop
+            if stop in write_steps:
+                h.download()
+                from .postprocess import writeStamp
+                writeStamp(f"{float(np.format_float_positional(table[stop - 1, 0], precision=nround, unique=False, fractional=False, trim='k')):g}",
+                           table[stop - 1, 0], surf, curfield)
+        h.download()
+        if two_dof:
+            h.get_2dof(kinem)
+        _run.last_timing = h.timing()
+    finally:
+        h.close()
+    mat = np.vstack(mats) if mats else np.zeros((0, 8))
+    if write_summary:
+        _write_results_summary(mat)
+    return mat, surf, curfield
+
+
+def ldvm(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
+         maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+    """ldvm(surf::TwoDSurf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort;
+    maxwrite, nround) -> (mat, surf, curfield), solvers.jl:144-268"""
+    return _run(cabi.DRIVER_LDVM, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
+                delvort or delNone(), maxwrite, nround, solve_mode, write_summary=write_summary)
+
+
+def ldvm2DOF(surf, curfield, strpar, kinem, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0,
+             delvort=None, *, maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+    """ldvm2DOF(surf, curfield, strpar::TwoDOFPar, kinem::KinemPar2DOF, ...), solvers.jl:657-788"""
+    return _run(cabi.DRIVER_LDVM2DOF, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
+                delvort or delNone(), maxwrite, nround, solve_mode, strpar=strpar, kinem=kinem,
+                write_summary=write_summary)
+
+
+def ldvmLin(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
+            maxwrite=50, nround=6, write_summary=True):
+    """ldvmLin(...), solvers.jl:448-655 (closed-form linearised shedding)"""
+    return _run(cabi.DRIVER_LDVMLIN, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
+                delvort or delNone(), maxwrite, nround, cabi.SOLVE_EXACT, write_summary=write_summary)
+
+
+def lautat(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
+           maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+    """lautat(...), solvers.jl:42-142 (wakerollup=1)"""
+    return _run(cabi.DRIVER_LAUTAT, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
+                delvort or delNone(), maxwrite, nround, solve_mode, write_summary=write_summary)
