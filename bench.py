@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the UNSflow discrete-vortex hot path on B200.
+
+Metric (BASELINE.json): FP64 vortex interactions/s.  One *interaction* = one ordered
+(target <- source) evaluation of the Vatistas kernel; 13 algorithmic flop each.
+
+Workload (config.workload): C4 -- one `wakeroll` time step (src/lowOrder2D/calcs.jl:222-294:
+all-pairs induction among N = 1e6 free vortices + 69 bound vortices, free stream, explicit
+Euler convection) on the synthetic S-wake(1e6) field, kept device-resident.  With --gpus G > 1
+(launched by torchrun, one process per GPU) the pair work is split over ranks and the step ends
+with the NCCL exchange; total work is fixed => "scaling": "strong".
+
+  value     whole-job interactions/s with state resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the C-ABI with HOST buffers: upload of the vortex state from
+            host memory, one step, download of positions+velocities, all inside the timed region
+  roofline  the dominant kernel against the FP64 (non-tensor) DFMA peak MEASURED in this run
+  cpu_baseline  the reference's own loop (oracle port of mutual_ind) on one host core, bounded sample
+
+`--impl reference` times the reference CPU path (oracle port, all host threads) instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_INTERACTION = 13.0
+NBV = 69                        # ndiv - 1 bound vortices (typedefs.jl:68)
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons DURING the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline_port(O, n_sample=65536):
+    """reference loop (mutual_ind, calcs.jl:491-510) on ONE host core, bounded sample of the
+    same S-wake field (the reference is single-threaded)"""
+    x, z, g, vc = O.s_wake(1_000_000)
+    t, _, _ = O.mutual_ind_time(x[:n_sample], z[:n_sample], g[:n_sample], vc[:n_sample])
+    inter = float(n_sample) * (n_sample - 1)
+    return {"value": inter / t, "unit": "interactions/s", "cores": 1, "kind": "port",
+            "sample": f"oracle port of mutual_ind (symmetric i<j loop, 2 sqrt + 2 div per pair) on the first {n_sample} "
+                      f"vortices of S-wake(1e6): {inter:.3e} interactions in {t:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Julia
+    reference cannot run here) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    n = args.n
+    x, z, g, vc = O.s_wake(n)
+    nth = O.num_threads()
+    nt = 48 * nth                      # targets per step: ~0.3 s of work per thread-step at 1.8e8/s
+    sx = np.concatenate([x, np.linspace(-1, 0, NBV)])
+    sz = np.concatenate([z, np.zeros(NBV)])
+    sg = np.concatenate([g, np.full(NBV, 0.01)])
+    sv = np.concatenate([vc, np.full(NBV, 0.02)])
+    times = []
+    for it in range(args.warmup + args.steps):
+        lo = (it * nt) % (n - nt)
+        t, _, _ = O.ind_vel_slice_mt(sx, sz, sg, sv, x[lo:lo + nt], z[lo:lo + nt])
+        if it >= args.warmup:
+            times.append(t)
+    inter = float(nt) * (n + NBV)
+    T = sum(times)
+    val = inter * len(times) / T
+    cb = {"value": val, "unit": "interactions/s", "cores": nth, "kind": "port",
+          "sample": f"{nt} targets x {n + NBV} sources per step (ind_vel expression of calcs.jl:472-473, target-sliced over "
+                    f"{nth} pthreads); the reference itself is single-threaded Julia and cannot run here"}
+    line = {"impl": "reference", "metric": "FP64 vortex interactions/s", "value": val, "unit": "interactions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 wakeroll step, S-wake(N={n}) + {NBV} bound vortices", "n_vortices": n,
+                       "note": "bounded target sample per step; CPU oracle port"},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="free vortices (C4: 1e6)")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 symmetric")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ldvm-steps", type=int, default=20, help="extra: LDVM steps/s on a 1e5 wake (0 = skip)")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import unsflow_b200 as uf
+    from oracle import oracle as O   # cpu_baseline leg + synthetic field generator only
+
+    cabi = uf._cabi
+    L = uf.lib()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    cabi.check(L.unsflow_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, K, W = args.n, args.steps, args.warmup
+    x, z, g, vc = O.s_wake(n)
+    bx = np.linspace(-1.0, 0.0, NBV); bz = np.zeros(NBV); bs = np.full(NBV, 0.01); bvc = np.full(NBV, 0.02)
+    dt, uinf = 0.015, 1.0
+
+    uid = (C.c_ubyte * 128)()
+    if world > 1:
+        t_uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            cabi.check(L.unsflow_nccl_unique_id(uid))
+            t_uid.copy_(torch.tensor(list(uid), dtype=torch.uint8))
+        dist.broadcast(t_uid, 0)
+        for i, v in enumerate(t_uid.cpu().tolist()):
+            uid[i] = v
+    h = C.c_void_p()
+    cabi.check(L.unsflow_wake_create(C.byref(h), n, NBV, rank, world, uid if world > 1 else None, args.variant))
+    up = [cabi.dptr(a) for a in (x, z, g, vc, bx, bz, bs, bvc)]
+    cabi.check(L.unsflow_wake_upload(h, *up))
+
+    # measured FP64 peak (MEASURED_PEAKS.json has no FP64 figure): DFMA-chain microbenchmark
+    tf, mhz = C.c_double(), C.c_double()
+    cabi.check(L.unsflow_fp64_peak(C.byref(tf), C.byref(mhz)))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        cabi.check(L.unsflow_wake_step(h, 1, uinf, 0.0, dt))
+        ms, msk, nl = C.c_float(), C.c_float(), C.c_int64()
+        cabi.check(L.unsflow_wake_timing(h, C.byref(ms), C.byref(msk), C.byref(nl)))   # synchronises
+        return ms.value, msk.value, nl.value
+
+    for _ in range(W):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    wall0 = time.perf_counter()
+    T_ms = Tk_ms = 0.0
+    launches = 0
+    for _ in range(K):
+        if world > 1:
+            dist.barrier()
+        ms, msk, nl = one_step()
+        T_ms += ms; Tk_ms += msk; launches += nl
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([T_ms, Tk_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    T_ms, Tk_ms = tt.tolist()
+    inter_step = float(n) * (n + NBV)
+    value = inter_step * K / (T_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------
+    xs, zs, vxs, vzs = (np.zeros(n) for _ in range(4))
+    dn = [cabi.dptr(a) for a in (xs, zs, vxs, vzs)]
+    ke = min(K, 2)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(ke):
+        cabi.check(L.unsflow_wake_upload(h, *up))
+        cabi.check(L.unsflow_wake_step(h, 1, uinf, 0.0, dt))
+        cabi.check(L.unsflow_wake_download(h, *dn))
+    barrier()
+    e2e_t = time.perf_counter() - e0
+    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = inter_step * ke / te.item()
+    extra = {}
+    if world == 1:
+        # the drop-in call itself: wakeroll(surf, curfield, dt) -> unsflow_wakeroll, host arrays
+        xx, zz = x.copy(), z.copy()
+        a0 = time.perf_counter()
+        cabi.check(L.unsflow_wakeroll(n, cabi.dptr(xx), cabi.dptr(zz), up[2], up[3], dn[2], dn[3], NBV, up[4], up[5], up[6], up[7],
+                                      uinf, 0.0, dt))
+        extra["e2e_wakeroll_call_interactions_per_s"] = inter_step / (time.perf_counter() - a0)
+    cabi.check(L.unsflow_wake_destroy(h))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- extra: LDVM steps/s with a 1e5-vortex wake (config C2 regime), single GPU ------------
+    if world == 1 and args.ldvm_steps > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from cases import c2_surf
+            from unsflow_b200.solvers import LdvmHandle, _opts
+            surf, fld, dtstar = c2_surf(uf)
+            nw = 100_000
+            wx, wz, wg, wvc = O.s_wake(nw)
+            fld.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
+            ns = args.ldvm_steps
+            hh = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, ns + 3, uf.delNone(), cabi.SOLVE_EXACT))
+            hh.set_kinematics(uf.kinematics_table(surf, fld, ns + 3, dtstar))
+            hh.run(3)
+            hh.run(ns)
+            ms, nl = hh.timing()
+            hh.close()
+            extra["ldvm_steps_per_s_at_N1e5"] = ns / (ms * 1e-3)
+            extra["ldvm_launches_per_step"] = nl / ns
+        except Exception as e:   # never lose the headline line
+            extra["ldvm_error"] = str(e)[:200]
+
+    ach = FLOP_PER_INTERACTION * inter_step * K / (Tk_ms * 1e-3) / 1e12 / 1.0   # per-rank kernel = 1/world of the pairs
+    ach_per_gpu = ach / world
+    line = {
+        "metric": "FP64 vortex interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": T_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 wakeroll step (calcs.jl:222-294), S-wake(N={n}) + {NBV} bound vortices, device-resident",
+                   "n_vortices": n, "interactions_per_step": inter_step, "flop_per_interaction": FLOP_PER_INTERACTION,
+                   "l2": "flushed between timed steps (256 MiB write); per-step partial sums exceed L2 anyway",
+                   "kernel_variant": args.variant, "parallelism": f"pair work split over {world} rank(s), NCCL exchange per step"},
+        "clocks": clocks, "wall_s_timed_region": wall,
+        "e2e": {"value": e2e_val, "unit": "interactions/s", "h2d_bytes_per_step": int(8 * (4 * n + 4 * NBV)),
+                "d2h_bytes_per_step": int(8 * 4 * n), "steps": ke,
+                "how": "unsflow_wake_upload (host arrays) + unsflow_wake_step + unsflow_wake_download per step"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "achieved": ach_per_gpu, "peak": tf.value, "unit": "TFLOP/s",
+                     "frac": ach_per_gpu / tf.value, "traffic": None,
+                     "kernel": "k_induce_* (all-pairs Vatistas induction)",
+                     "peak_source": f"measured in this run: DFMA-chain microbenchmark (unsflow_fp64_peak), ~{mhz.value:.0f} MHz "
+                                    "equivalent; MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                     "algorithmic": f"{FLOP_PER_INTERACTION:.0f} flop/interaction x {inter_step / world:.4e} interactions per launch per GPU"},
+    }
+    line.update(extra)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_port(O)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
