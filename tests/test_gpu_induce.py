@@ -95,14 +95,16 @@ def test_wakeroll_and_update_indbound_parity(gpu_lib, uf, oracle):
         assert np.max(np.abs(v.x - o["x"])) <= 1e-13 and np.max(np.abs(v.z - o["z"])) <= 1e-13
 
 
-def test_device_resident_wake_matches_repeated_wakeroll(gpu_lib, uf, oracle):
-    """unsflow_wake_* (the bench's device-resident path) == the oracle's wakeroll repeated"""
+@pytest.mark.parametrize("variant,n", [(1, 3000), (2, 3000), (2, 5121), (0, 70001)])
+def test_device_resident_wake_matches_repeated_wakeroll(gpu_lib, uf, oracle, variant, n):
+    """unsflow_wake_* (the bench's device-resident path; direct and symmetric pair-tile
+    kernels) == the oracle's wakeroll repeated"""
     cabi = uf._cabi
-    n, nbv, nsteps, dt = 3000, 69, 3, 0.015
+    nbv, nsteps, dt = 69, (3 if n < 10000 else 1), 0.015
     x, z, g, vc = oracle.s_wake(n)
     bx = np.linspace(-1.0, 0.0, nbv); bz = 0.05 * np.ones(nbv); bs = 0.01 * np.cos(np.arange(nbv)); bvc = np.full(nbv, 0.02)
     h = C.c_void_p()
-    cabi.check(gpu_lib.unsflow_wake_create(C.byref(h), n, nbv, 0, 1, None, cabi.KERNEL_AUTO))
+    cabi.check(gpu_lib.unsflow_wake_create(C.byref(h), n, nbv, 0, 1, None, variant))
     try:
         cabi.check(gpu_lib.unsflow_wake_upload(h, *(cabi.dptr(a) for a in (x, z, g, vc, bx, bz, bs, bvc))))
         cabi.check(gpu_lib.unsflow_wake_step(h, nsteps, 0.1, 0.0, dt))

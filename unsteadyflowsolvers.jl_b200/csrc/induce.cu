@@ -1,6 +1,6 @@
 // induce.cu -- launch plumbing for the induction kernels (see induce.cuh).
 #define UNSFLOW_INDUCE_KERNELS
-#include "induce.cuh"
+#include "induce_sym.cuh"
 #include <algorithm>
 
 namespace unsflow {
@@ -50,6 +50,22 @@ int launch_induce_finish(const FinishArgs &a, long long nt_ub, cudaStream_t st) 
     if (nt_ub <= 0) return 0;
     const int blocks = (int)((nt_ub + 255) / 256);
     k_induce_finish<<<blocks, 256, 0, st>>>(a);
+    UF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t sym_smem_bytes() { return sizeof(double) * (2 * 3 * kSymTB + 2 * kSymTB) + 2 * sizeof(uint64_t) + 16; }
+
+int launch_induce_sym(const SymArgs &a, int ctas, int order, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sym_smem_bytes();
+    if (!attr_set) {
+        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (order == 2) k_induce_sym<2><<<ctas, kThreads, smem, st>>>(a);
+    else k_induce_sym<3><<<ctas, kThreads, smem, st>>>(a);
     UF_CUDA(cudaGetLastError());
     return 0;
 }

@@ -55,6 +55,7 @@ struct FinishArgs {
     const double *dtp;      // unused (reserved)
     double dt;              // 0 -> no convection
     int accumulate;         // 1: vx += result (mutual_ind semantics)
+    int raw;                // 1: store the plain plane sum only (no 1/2pi, free stream, convection)
 };
 
 
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) k_induce_finish(const FinishArgs a) {
         su += a.pu[(long long)s * a.tstride + i];
         sw += a.pw[(long long)s * a.tstride + i];
     }
+    if (a.raw) { a.vx[i] = su; a.vz[i] = sw; return; }
     double vx = su * kInvTwoPi, vz = sw * kInvTwoPi;
     const double fu = a.fs ? a.fs[0] : a.fs_u, fw = a.fs ? a.fs[1] : a.fs_w;
     vx += fu;

@@ -1,0 +1,222 @@
+// induce_sym.cuh -- symmetric pair-tile Vatistas induction (uniform core radius), sm_100a FP64.
+//
+// The reference's mutual_ind (src/lowOrder2D/calcs.jl:491-510) evaluates each unordered pair
+// once and updates both vortices; with a uniform core radius the two kernel magnitudes are
+// equal (magitr == magjtr, :499-500), so one rsqrt feeds two interactions.  This kernel keeps
+// that saving on the GPU:
+//
+//   * vortices are cut into blocks of TB = 256*R; the upper triangle of block pairs (I <= J) is
+//     linearised row-major and cut into equal contiguous chunks, one per persistent CTA
+//     (and per rank first, when the pair work is split over GPUs);
+//   * rows (block I) live in registers, R per thread; columns (block J) are staged in shared
+//     memory by 1-D TMA bulk copies, double-buffered on mbarriers;
+//   * inside a tile warp w works on column chunk (w + phase) mod 8 and lane l on column
+//     (k + l) mod 128 of that chunk at step k (a Latin square: no two lanes ever touch the same
+//     column accumulator in one step, no shuffles, no atomics);
+//   * per pair: 16 FP64-pipe instructions for 2 interactions (+2 per R pairs for the
+//     shared-memory accumulator) = 8.25 per interaction instead of 13;
+//   * diagonal tiles (I == J) and the bound-vortex sources are one-sided (13 per interaction);
+//   * every CTA accumulates into its own partial plane P[c][2][n]; k_induce_finish adds the
+//     planes in a fixed order -> bit-reproducible, no floating-point atomics.
+#pragma once
+#include "induce.cuh"
+
+namespace unsflow {
+
+constexpr int kSymR = 4;
+constexpr int kSymTB = kThreads * kSymR;           // 1024 vortices per block
+constexpr int kSymChunk = kSymTB / (kThreads / 32);   // 128 columns per warp per phase
+
+struct SymArgs {
+    const double *x, *z, *g;     // slabs (absolute indexing); dead entries have g = 0
+    const Regions *reg;          // device: live ranges; regions [0, nreg) are free-vortex families
+    int nreg;
+    int bv_reg;                  // index of the bound-vortex region in *reg (one-sided sources) or -1
+    double vc4;
+    double *P;                   // [C][2][n] partial planes (pu then pw per CTA)
+    long long n;                 // plane length
+    int rank, nranks;            // split of the tile list over GPUs
+};
+
+size_t sym_smem_bytes();
+int launch_induce_sym(const SymArgs &a, int ctas, int order, cudaStream_t st);
+
+#if defined(__CUDACC__) && defined(UNSFLOW_INDUCE_KERNELS)
+
+__device__ __forceinline__ long long sym_blocks_in(long long b, long long e) {
+    return e > b ? (e + kSymTB - 1) / kSymTB - b / kSymTB : 0;
+}
+__device__ __forceinline__ long long sym_block_start(const Regions &rg, int nreg, long long k) {
+    for (int r = 0; r < nreg; r++) {
+        const long long n = sym_blocks_in(rg.begin[r], rg.end[r]);
+        if (k < n) return (rg.begin[r] / kSymTB + k) * kSymTB;
+        k -= n;
+    }
+    return -1;
+}
+// row-major upper triangle incl. diagonal: row I starts at I*nb - I*(I-1)/2
+__device__ __forceinline__ long long sym_row_offset(long long I, long long nb) { return I * nb - I * (I - 1) / 2; }
+
+template <int ORDER>
+__global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
+    constexpr int R = kSymR, TB = kSymTB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_col = reinterpret_cast<double *>(smem_raw);             // [2][3][TB]
+    double2 *s_acc = reinterpret_cast<double2 *>(s_col + 2 * 3 * TB); // [TB]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_acc + TB);       // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Regions reg = *a.reg;
+    long long nb = 0;
+    for (int r = 0; r < a.nreg; r++) nb += sym_blocks_in(reg.begin[r], reg.end[r]);
+    const long long W = nb * (nb + 1) / 2;
+    // rank range, then this CTA's contiguous chunk of it
+    const long long r0 = W * a.rank / a.nranks, r1 = W * (a.rank + 1) / a.nranks;
+    const long long t0 = r0 + (r1 - r0) * blockIdx.x / gridDim.x;
+    const long long t1 = r0 + (r1 - r0) * (blockIdx.x + 1) / gridDim.x;
+    if (t0 >= t1) return;
+
+    // (I, J) of tile t0
+    long long I = (long long)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t0)) * 0.5);
+    if (I < 0) I = 0;
+    while (I > 0 && sym_row_offset(I, nb) > t0) I--;
+    while (I + 1 < nb && sym_row_offset(I + 1, nb) <= t0) I++;
+    long long J = I + (t0 - sym_row_offset(I, nb));
+
+    double *Pu = a.P + (long long)blockIdx.x * 2 * a.n;
+    double *Pw = Pu + a.n;
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](long long Jblk, int stage) {
+        const long long e0 = sym_block_start(reg, a.nreg, Jblk);
+        constexpr uint32_t bytes = TB * sizeof(double);
+        double *dst = s_col + stage * 3 * TB;
+        mbar_expect_tx(&s_bar[stage], 3 * bytes);
+        tma_load_1d(dst, a.x + e0, bytes, &s_bar[stage]);
+        tma_load_1d(dst + TB, a.z + e0, bytes, &s_bar[stage]);
+        tma_load_1d(dst + 2 * TB, a.g + e0, bytes, &s_bar[stage]);
+    };
+    if (tid == 0) issue(J, 0);
+
+    double tx[R], tz[R], tg[R], u[R], w[R];
+    long long rowI = -1, row_start = 0;
+    const double vc4 = a.vc4;
+
+    for (long long t = t0; t < t1; t++) {
+        const int k = (int)(t - t0), stage = k & 1;
+        // next tile in row-major order
+        long long In = I, Jn = J + 1;
+        if (Jn >= nb) { In = I + 1; Jn = In; }
+        if (tid == 0 && t + 1 < t1) issue(Jn, stage ^ 1);
+
+        if (I != rowI) {
+            if (rowI >= 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const long long i = row_start + tid + r * kThreads;
+                    Pu[i] += u[r];
+                    Pw[i] += w[r];
+                }
+            }
+            rowI = I;
+            row_start = sym_block_start(reg, a.nreg, I);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const long long i = row_start + tid + r * kThreads;
+                tx[r] = a.x[i]; tz[r] = a.z[i]; tg[r] = a.g[i];
+                u[r] = 0.0; w[r] = 0.0;
+            }
+        }
+        const double *sx = s_col + stage * 3 * TB, *sz = sx + TB, *sg = sx + 2 * TB;
+        if (I == J) {
+            // ---- diagonal tile: one-sided, broadcast column reads (self pair is an exact 0) ----
+            mbar_wait(&s_bar[stage], (k >> 1) & 1);
+#pragma unroll 2
+            for (int j = 0; j < TB; j++) {
+                const double xj = sx[j], zj = sz[j], gj = sg[j];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double dx = xj - tx[r], dz = zj - tz[r];
+                    const double d2 = fma(dz, dz, dx * dx);
+                    const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                    const double m = gj * y;
+                    u[r] = fma(-dz, m, u[r]);
+                    w[r] = fma(dx, m, w[r]);
+                }
+            }
+            if (a.bv_reg >= 0) {   // bound vortices act on this row block exactly once (here)
+                for (long long j = reg.begin[a.bv_reg]; j < reg.end[a.bv_reg]; j++) {
+                    const double xj = __ldg(a.x + j), zj = __ldg(a.z + j), gj = __ldg(a.g + j);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double dx = xj - tx[r], dz = zj - tz[r];
+                        const double d2 = fma(dz, dz, dx * dx);
+                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                        const double m = gj * y;
+                        u[r] = fma(-dz, m, u[r]);
+                        w[r] = fma(dx, m, w[r]);
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
+            // ---- off-diagonal tile: every kernel evaluation feeds row i and column j ------------
+            for (int c = tid; c < TB; c += kThreads) s_acc[c] = make_double2(0.0, 0.0);
+            mbar_wait(&s_bar[stage], (k >> 1) & 1);
+            __syncthreads();
+            for (int p = 0; p < kThreads / 32; p++) {
+                const int base = ((warp + p) & (kThreads / 32 - 1)) * kSymChunk;
+#pragma unroll 1
+                for (int s = 0; s < kSymChunk; s++) {
+                    const int j = base + ((s + lane) & (kSymChunk - 1));
+                    const double xj = sx[j], zj = sz[j], gj = sg[j];
+                    double cu = 0.0, cw = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double dx = xj - tx[r], dz = zj - tz[r];
+                        const double d2 = fma(dz, dz, dx * dx);
+                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                        const double t1v = y * dz, t2v = y * dx;
+                        u[r] = fma(-gj, t1v, u[r]);
+                        w[r] = fma(gj, t2v, w[r]);
+                        cu = fma(tg[r], t1v, cu);
+                        cw = fma(-tg[r], t2v, cw);
+                    }
+                    double2 acc = s_acc[j];
+                    acc.x += cu;
+                    acc.y += cw;
+                    s_acc[j] = acc;
+                    __syncwarp();   // lane l+1 wrote column j+1 in this step; lane l reads it next step
+                }
+                __syncthreads();
+            }
+            // flush the column accumulators into this CTA's private plane
+            const long long cstart = sym_block_start(reg, a.nreg, J);
+            for (int c = tid; c < TB; c += kThreads) {
+                const double2 acc = s_acc[c];
+                Pu[cstart + c] += acc.x;
+                Pw[cstart + c] += acc.y;
+            }
+            __syncthreads();
+        }
+        I = In;
+        J = Jn;
+    }
+    if (rowI >= 0) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const long long i = row_start + tid + r * kThreads;
+            Pu[i] += u[r];
+            Pw[i] += w[r];
+        }
+    }
+}
+
+#endif  // kernels
+}  // namespace unsflow

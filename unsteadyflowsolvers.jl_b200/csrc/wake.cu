@@ -2,7 +2,7 @@
 // without leaving HBM, optionally target-sliced over ranks (one process per GPU) with an NCCL
 // all-gather of the convected positions each step.
 #include "../../include/unsflow.h"
-#include "induce.cuh"
+#include "induce_sym.cuh"
 #include "nccl_dl.h"
 #include "runtime.h"
 #include <dlfcn.h>
@@ -61,6 +61,9 @@ struct unsflow_wake {
     DevBuf<double> src;    // [x | z | g | vc4], each `tot`
     DevBuf<double> vel;    // [vx | vz], each npad
     DevBuf<double> part;   // [pu | pw], each S*npad
+    DevBuf<double> planes; // symmetric kernel: [ctas][2][tot]
+    int ctas = 0;
+    bool want_sym = false;
     DevBuf<Regions> reg;   // [0] sources, [1] my targets
     InducePlan plan{};
     cudaStream_t st = nullptr;
@@ -95,7 +98,7 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     w->n = n; w->nbv = nbv; w->rank = rank; w->nranks = nranks;
     w->variant = variant;
     w->slice = round_up((n + nranks - 1) / nranks, 2);
-    w->npad = round_up(w->slice * nranks, kTS);
+    w->npad = round_up(w->slice * nranks, kSymTB);
     w->bvpad = round_up(std::max<int64_t>(nbv, 1), kTS);
     w->tot = w->npad + w->bvpad;
     auto fail = [&](int rc) { unsflow_wake_destroy(w); return rc; };
@@ -108,6 +111,9 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     const int64_t my_t = std::max<int64_t>(0, std::min(n, (rank + 1) * w->slice) - rank * w->slice);
     w->plan = plan_induce(my_t, 1, n + nbv, 2, sm_count(), 64);
     if (w->part.alloc(2 * (int64_t)w->plan.S * w->npad)) return fail(2);
+    w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= 65536);
+    w->ctas = 2 * sm_count();
+    if (w->want_sym && w->planes.alloc((int64_t)w->ctas * 2 * w->tot)) return fail(2);
     if (w->src.zero(w->st) || w->vel.zero(w->st)) return fail(2);
     Regions h[2];
     memset(h, 0, sizeof(h));
@@ -189,12 +195,48 @@ int unsflow_wake_step(unsflow_wake *w, int64_t nsteps, double u_inf, double w_in
     f.x = w->src.p; f.z = w->src.p + tot;
     f.fs_u = u_inf; f.fs_w = w_inf; f.dt = dt;
     const int64_t my_t = std::max<int64_t>(0, std::min(w->n, (w->rank + 1) * w->slice) - w->rank * w->slice);
+    const bool sym = w->want_sym && w->uniform;
+    UF_CHECK(sym || w->variant != UNSFLOW_KERNEL_SYMMETRIC, "unsflow_wake_step: the symmetric kernel needs a uniform core radius");
+    SymArgs sa;
+    sa.x = a.sx; sa.z = a.sz; sa.g = a.sg;
+    sa.reg = w->reg.p; sa.nreg = 1; sa.bv_reg = w->nbv > 0 ? 1 : -1;
+    sa.vc4 = w->vc4u;
+    sa.P = w->planes.p; sa.n = tot;
+    sa.rank = w->rank; sa.nranks = w->nranks;
     w->ktimed = 0;
     w->launches = 0;
     UF_CUDA(cudaEventRecord(w->ev0, w->st));
     for (int64_t is = 0; is < nsteps; is++) {
         const bool timed = is < unsflow_wake::kMaxTimed;
         if (timed) UF_CUDA(cudaEventRecord(w->kev[2 * is], w->st));
+        if (sym) {
+            // every rank evaluates its share of the unordered pair tiles for ALL vortices
+            UF_CUDA(cudaMemsetAsync(w->planes.p, 0, sizeof(double) * (size_t)w->ctas * 2 * tot, w->st));
+            if (int rc = launch_induce_sym(sa, w->ctas, rsqrt_order(), w->st)) return rc;
+            if (timed) { UF_CUDA(cudaEventRecord(w->kev[2 * is + 1], w->st)); w->ktimed = (int)is + 1; }
+            FinishArgs fsym = f;
+            fsym.pu = w->planes.p; fsym.pw = w->planes.p + tot; fsym.tstride = 2 * tot; fsym.S = w->ctas;
+            fsym.treg = w->reg.p; fsym.ntreg = 1;          // all n free vortices
+            if (w->nranks == 1) {
+                if (int rc = launch_induce_finish(fsym, w->n, w->st)) return rc;
+                w->launches += 2;
+            } else {
+                fsym.raw = 1;
+                if (int rc = launch_induce_finish(fsym, w->n, w->st)) return rc;
+                const NcclApi *nc = nccl_api();
+                if (!nc) return 4;
+                UF_NCCL(nc->GroupStart());
+                UF_NCCL(nc->AllReduce(w->vel.p, w->vel.p, (size_t)w->n, ncclDouble, ncclSum, w->comm, w->st));
+                UF_NCCL(nc->AllReduce(w->vel.p + npad, w->vel.p + npad, (size_t)w->n, ncclDouble, ncclSum, w->comm, w->st));
+                UF_NCCL(nc->GroupEnd());
+                FinishArgs f2 = f;
+                f2.pu = w->vel.p; f2.pw = w->vel.p + npad; f2.tstride = 0; f2.S = 1;
+                f2.treg = w->reg.p; f2.ntreg = 1;
+                if (int rc = launch_induce_finish(f2, w->n, w->st)) return rc;
+                w->launches += 3;
+            }
+            continue;
+        }
         if (int rc = launch_induce_direct(a, w->plan, w->uniform, rsqrt_order(), w->st)) return rc;
         if (timed) { UF_CUDA(cudaEventRecord(w->kev[2 * is + 1], w->st)); w->ktimed = (int)is + 1; }
         if (int rc = launch_induce_finish(f, my_t, w->st)) return rc;
