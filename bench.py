@@ -144,7 +144,8 @@ def main():
     import torch.distributed as dist
 
     import unsflow_b200 as uf
-    from oracle import oracle as O   # cpu_baseline leg + synthetic field generator only
+    from synth import s_wake
+    from oracle import oracle as O   # checker only: cpu_baseline leg and the verify step
 
     cabi = uf._cabi
     L = uf.lib()
@@ -155,7 +156,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, K, W = args.n, args.steps, args.warmup
-    x, z, g, vc = O.s_wake(n)
+    x, z, g, vc = s_wake(n)
     bx = np.linspace(-1.0, 0.0, NBV); bz = np.zeros(NBV); bs = np.full(NBV, 0.01); bvc = np.full(NBV, 0.02)
     dt, uinf = 0.015, 1.0
 
@@ -241,6 +242,22 @@ def main():
         cabi.check(L.unsflow_wakeroll(n, cabi.dptr(xx), cabi.dptr(zz), up[2], up[3], dn[2], dn[3], NBV, up[4], up[5], up[6], up[7],
                                       uinf, 0.0, dt))
         extra["e2e_wakeroll_call_interactions_per_s"] = inter_step / (time.perf_counter() - a0)
+    # ---- verification on the same handle (all ranks take part): one step with dt = 0 on the
+    # original field, 32 sampled targets against the oracle's long-double truth ----------------
+    cabi.check(L.unsflow_wake_upload(h, *up))
+    cabi.check(L.unsflow_wake_step(h, 1, 0.0, 0.0, 0.0))
+    cabi.check(L.unsflow_wake_download(h, None, None, dn[2], dn[3]))
+    verify = None
+    if rank == 0:
+        b_, e_ = C.c_int64(), C.c_int64()
+        cabi.check(L.unsflow_partition(n, world, 0, 1, C.byref(b_), C.byref(e_)))
+        hi = n if args.variant != 1 and n >= 65536 else e_.value    # direct: rank 0 only holds its slice
+        idx = np.arange(0, hi, max(1, hi // 32))[:32]
+        sx = np.concatenate([x, bx]); sz = np.concatenate([z, bz]); sg = np.concatenate([g, bs]); sv = np.concatenate([vc, bvc])
+        tu, tw, au, aw = O.ind_vel_truth(sx, sz, sg, sv, x[idx], z[idx])
+        verify = {"targets": int(len(idx)), "max_normalised_err": float(max(np.max(np.abs(vxs[idx] - tu)) / np.max(au),
+                                                                             np.max(np.abs(vzs[idx] - tw)) / np.max(aw))),
+                  "tolerance": 1e-12, "against": "oracle long-double sum"}
     cabi.check(L.unsflow_wake_destroy(h))
 
     if rank != 0:
@@ -257,7 +274,7 @@ def main():
             from unsflow_b200.solvers import LdvmHandle, _opts
             surf, fld, dtstar = c2_surf(uf)
             nw = 100_000
-            wx, wz, wg, wvc = O.s_wake(nw)
+            wx, wz, wg, wvc = s_wake(nw)
             fld.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
             ns = args.ldvm_steps
             hh = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, ns + 3, uf.delNone(), cabi.SOLVE_EXACT))
@@ -293,6 +310,7 @@ def main():
                                     "equivalent; MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                      "algorithmic": f"{FLOP_PER_INTERACTION:.0f} flop/interaction x {inter_step / world:.4e} interactions per launch per GPU"},
     }
+    line["verify"] = verify
     line.update(extra)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_port(O)

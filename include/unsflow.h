@@ -77,6 +77,10 @@ typedef struct unsflow_wake unsflow_wake;
  * nranks = 1 for a single GPU.  nccl_unique_id: 128 bytes from unsflow_nccl_unique_id() of
  * rank 0, identical on all ranks (ignored when nranks == 1). */
 int unsflow_nccl_unique_id(void *id128);
+/* The share of the step owned by `rank` of `nranks` (pure arithmetic, no GPU needed):
+ * DIRECT: target index range [begin,end) of the n free vortices; SYMMETRIC: range of the
+ * row-major upper-triangle list of pair tiles (2048 wide for n >= 400000, else 1024). */
+int unsflow_partition(int64_t n, int nranks, int rank, int variant, int64_t *begin, int64_t *end);
 int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, int nranks,
                         const void *nccl_unique_id, int kernel_variant);
 /* upload / download full state (host buffers, each n or nbv doubles; NULL = skip) */

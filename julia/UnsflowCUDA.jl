@@ -1,0 +1,240 @@
+# UnsflowCUDA.jl -- the reference-side binding of libunsflow_cuda (include/unsflow.h).
+#
+# Drop-in methods behind the existing UnsteadyFlowSolvers API: `ldvm`, `ldvm2DOF`, `ldvmLin`,
+# `lautat` on TwoDSurf / TwoDFlowField / TwoDVort, plus the fine-grained `ind_vel`,
+# `mutual_ind`, `wakeroll`, `update_indbound`.  Host code stays Julia; every call below is a thin
+# `ccall` into the C ABI.  There is no CPU fallback: a non-zero status becomes `error(msg)`.
+#
+# NOTE: no `julia` binary exists in the build image, so this file is reviewed, not executed,
+# there; tests/ drive exactly the same C symbols through Python ctypes
+# (unsteadyflowsolvers.jl_b200/_cabi.py), struct for struct.
+#
+#   using UnsteadyFlowSolvers; include("UnsflowCUDA.jl"); using .UnsflowCUDA
+#   mat, surf, curfield = UnsflowCUDA.ldvm(surf, curfield, nsteps, dtstar)
+module UnsflowCUDA
+
+using UnsteadyFlowSolvers
+const UFS = UnsteadyFlowSolvers
+import UnsteadyFlowSolvers: TwoDVort, TwoDSurf, TwoDFlowField, TwoDOFPar, KinemPar2DOF, delNone, delSpalart
+import DelimitedFiles
+
+const LIB = get(ENV, "UNSFLOW_CUDA_LIB", joinpath(@__DIR__, "..", "unsteadyflowsolvers.jl_b200", "libunsflow_cuda.so"))
+
+lasterr() = unsafe_string(ccall((:unsflow_last_error, LIB), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error("libunsflow_cuda: " * lasterr())
+
+# ---- struct mirrors of include/unsflow.h -------------------------------------------------------
+struct CVorts            # unsflow_vorts
+    n::Int64
+    x::Ptr{Cdouble}; z::Ptr{Cdouble}; s::Ptr{Cdouble}; vc::Ptr{Cdouble}; vx::Ptr{Cdouble}; vz::Ptr{Cdouble}
+end
+
+struct CSurf             # unsflow_surf
+    ndiv::Int32; naterm::Int32
+    c::Cdouble; uref::Cdouble; pvt::Cdouble
+    lespcrit::Cdouble
+    levflag::Int32; _pad::Int32
+    kinem::NTuple{6,Cdouble}
+    a0::Cdouble; a0dot::Cdouble; a0prev::Cdouble
+    theta::Ptr{Cdouble}; x::Ptr{Cdouble}; cam::Ptr{Cdouble}; cam_slope::Ptr{Cdouble}
+    bnd_x::Ptr{Cdouble}; bnd_z::Ptr{Cdouble}
+    uind::Ptr{Cdouble}; wind::Ptr{Cdouble}; downwash::Ptr{Cdouble}
+    aterm::Ptr{Cdouble}; adot::Ptr{Cdouble}; aprev::Ptr{Cdouble}
+    bv::CVorts
+end
+
+struct CField            # unsflow_field
+    u::Cdouble; w::Cdouble
+    tev::CVorts; lev::CVorts; extv::CVorts
+end
+
+struct COpts             # unsflow_opts
+    driver::Int32; solve_mode::Int32; delvort_kind::Int32; device::Int32
+    del_limit::Int64; del_dist::Cdouble; del_tol::Cdouble
+    dt::Cdouble; max_steps::Int64
+end
+
+# Vector{TwoDVort} (array of boxed mutable structs, typedefs.jl:11-18) <-> SoA
+struct SoA
+    x::Vector{Float64}; z::Vector{Float64}; s::Vector{Float64}; vc::Vector{Float64}; vx::Vector{Float64}; vz::Vector{Float64}
+end
+SoA(v::Vector{TwoDVort}) = SoA(map(q -> q.x, v), map(q -> q.z, v), map(q -> q.s, v), map(q -> q.vc, v), map(q -> q.vx, v), map(q -> q.vz, v))
+SoA(n::Integer) = SoA((zeros(n) for _ = 1:6)...)
+cvorts(a::SoA) = CVorts(length(a.x), pointer(a.x), pointer(a.z), pointer(a.s), pointer(a.vc), pointer(a.vx), pointer(a.vz))
+function unpack!(v::Vector{TwoDVort}, a::SoA, n::Integer)
+    resize!(v, 0)
+    for i = 1:n
+        push!(v, TwoDVort(a.x[i], a.z[i], a.s[i], a.vc[i], a.vx[i], a.vz[i]))
+    end
+    v
+end
+
+# ---- fine-grained drop-ins (calcs.jl) ------------------------------------------------------------
+"ind_vel(src, t_x, t_z) -> (uind, wind)   replaces calcs.jl:462-477"
+function ind_vel(src::Vector{TwoDVort}, t_x::Vector{Float64}, t_z::Vector{Float64})
+    a = SoA(src); uind = zeros(length(t_x)); wind = zeros(length(t_x))
+    check(ccall((:unsflow_ind_vel, LIB), Cint,
+        (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        length(src), a.x, a.z, a.s, a.vc, length(t_x), t_x, t_z, uind, wind))
+    uind, wind
+end
+ind_vel(src::TwoDVort, t_x, t_z) = ind_vel([src], collect(Float64, t_x), collect(Float64, t_z))   # calcs.jl:480-488
+
+"mutual_ind(vorts) -> vorts (accumulates into vx, vz)   replaces calcs.jl:491-510"
+function mutual_ind(vorts::Vector{TwoDVort})
+    a = SoA(vorts)
+    check(ccall((:unsflow_mutual_ind, LIB), Cint,
+        (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        length(vorts), a.x, a.z, a.s, a.vc, a.vx, a.vz))
+    for i = 1:length(vorts)
+        vorts[i].vx = a.vx[i]; vorts[i].vz = a.vz[i]
+    end
+    vorts
+end
+
+"update_indbound(surf, curfield) -> surf   replaces calcs.jl:35-38"
+function update_indbound(surf::TwoDSurf, curfield::TwoDFlowField)
+    surf.uind[1:surf.ndiv], surf.wind[1:surf.ndiv] = ind_vel([curfield.tev; curfield.lev; curfield.extv], surf.bnd_x, surf.bnd_z)
+    surf
+end
+
+"wakeroll(surf, curfield, dt) -> curfield   replaces calcs.jl:222-294"
+function wakeroll(surf::TwoDSurf, curfield::TwoDFlowField, dt)
+    all = [curfield.tev; curfield.lev; curfield.extv]      # same order as calcs.jl:245 (shares the boxes)
+    a = SoA(all); b = SoA(surf.bv)
+    check(ccall((:unsflow_wakeroll, LIB), Cint,
+        (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+         Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Cdouble),
+        length(all), a.x, a.z, a.s, a.vc, a.vx, a.vz, length(surf.bv), b.x, b.z, b.s, b.vc,
+        curfield.u[1], curfield.w[1], dt))
+    for i = 1:length(all)
+        all[i].x = a.x[i]; all[i].z = a.z[i]; all[i].vx = a.vx[i]; all[i].vz = a.vz[i]
+    end
+    curfield
+end
+
+# ---- device-resident drivers (solvers.jl) --------------------------------------------------------
+# host-tabulated prescribed motion: rows [t, alpha, h, alphadot, hdot, u, udot, U, W] at the
+# running-sum times t = t + dt (solvers.jl:180) using the reference's own update_kinem /
+# update_externalvel (calcs.jl:75-198) on scratch copies
+function kinematics_table(surf::TwoDSurf, curfield::TwoDFlowField, nsteps, dt, t0; external = true, twodof = false)
+    tab = zeros(9, nsteps)                      # column per step == row-major nsteps x 9 for C
+    s = deepcopy(surf); f = deepcopy(curfield); t = t0
+    for i = 1:nsteps
+        t = t + dt
+        external && UFS.update_externalvel(f, t)
+        twodof || UFS.update_kinem(s, t)
+        k = s.kinem
+        tab[:, i] = [t, k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot, f.u[1], f.w[1]]
+    end
+    tab
+end
+
+function run_driver(driver::Integer, surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64, dtstar::Float64, startflag,
+                    writeflag, writeInterval, delvort; maxwrite = 50, nround = 6, solve_mode = 0, strpar = nothing, kinem = nothing)
+    startflag == 0 || throw("invalid start flag, should be 0 or 1")        # solvers.jl:157 (restart is broken upstream)
+    t = 0.0
+    dt = dtstar * surf.c / surf.uref                                       # solvers.jl:161
+    tab = kinematics_table(surf, curfield, nsteps, dt, t; external = driver != 3, twodof = driver == 1)
+    tev = SoA(curfield.tev); lev = SoA(curfield.lev); extv = SoA(curfield.extv); bv = SoA(surf.bv)
+    k = surf.kinem
+    mk_surf() = CSurf(surf.ndiv, surf.naterm, surf.c, surf.uref, surf.pvt, surf.lespcrit[1], surf.levflag[1], 0,
+        (k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot), surf.a0[1], surf.a0dot[1], surf.a0prev[1],
+        pointer(surf.theta), pointer(surf.x), pointer(surf.cam), pointer(surf.cam_slope), pointer(surf.bnd_x), pointer(surf.bnd_z),
+        pointer(surf.uind), pointer(surf.wind), pointer(surf.downwash), pointer(surf.aterm), pointer(surf.adot), pointer(surf.aprev),
+        cvorts(bv))
+    kind, lim, dist, tol = typeof(delvort) == delSpalart ? (1, delvort.limit, delvort.dist, delvort.tol) : (0, 0, 0.0, 0.0)
+    opts = Ref(COpts(driver, solve_mode, kind, -1, lim, dist, tol, dt, nsteps))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mat = Matrix{Float64}(undef, nsteps, 8)
+    GC.@preserve surf tev lev extv bv tab mat begin
+        cs = Ref(mk_surf()); cf = Ref(CField(curfield.u[1], curfield.w[1], cvorts(tev), cvorts(lev), cvorts(extv)))
+        check(ccall((:unsflow_ldvm_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ptr{CSurf}, Ptr{CField}, Ptr{COpts}), h, cs, cf, opts))
+        try
+            if driver == 1
+                sp = [getfield(strpar, f) for f in fieldnames(TwoDOFPar)]
+                kk = [getfield(kinem, f) for f in fieldnames(KinemPar2DOF)]
+                check(ccall((:unsflow_ldvm_set_2dof, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], sp, kk))
+            end
+            check(ccall((:unsflow_ldvm_set_kinematics, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], nsteps, tab))
+            # write schedule of solvers.jl:164-175: run up to each stamp, download, writeStamp (postprocess.jl:34-113)
+            stamps = writeflag == 1 ? [Int(round(writeInterval * i / dt)) for i = 1:maxwrite] : Int[]
+            done = 0
+            for stop in sort(unique([filter(s -> 0 < s <= nsteps, stamps); nsteps]))
+                if stop > done
+                    sub = Matrix{Float64}(undef, stop - done, 8)
+                    check(ccall((:unsflow_ldvm_run, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], stop - done, sub))
+                    mat[done+1:stop, :] = sub
+                    done = stop
+                end
+                if stop in stamps
+                    download!(h[], surf, curfield)
+                    UFS.writeStamp("$(round(tab[1, stop], sigdigits=nround))", tab[1, stop], surf, curfield)
+                end
+            end
+            download!(h[], surf, curfield)
+            if driver == 1
+                kk = zeros(22)
+                check(ccall((:unsflow_ldvm_get_2dof, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), h[], kk))
+                for (i, f) in enumerate(fieldnames(KinemPar2DOF))
+                    setfield!(kinem, f, kk[i])
+                end
+            end
+        finally
+            ccall((:unsflow_ldvm_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
+        end
+    end
+    f = open("resultsSummary", "w")                                         # solvers.jl:261-264
+    println(f, "#time \t", "alpha(deg) \t", "h/c \t", "u/uref \t", "A0 \t", "Cl \t", "Cd \t", "Cm ")
+    DelimitedFiles.writedlm(f, mat)
+    close(f)
+    mat, surf, curfield
+end
+
+function download!(h::Ptr{Cvoid}, surf::TwoDSurf, curfield::TwoDFlowField)
+    nt = Ref{Int64}(0); nl = Ref{Int64}(0); ne = Ref{Int64}(0)
+    check(ccall((:unsflow_ldvm_counts, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), h, nt, nl, ne))
+    tev = SoA(nt[]); lev = SoA(nl[]); extv = SoA(ne[]); bv = SoA(surf.ndiv - 1)
+    k = surf.kinem
+    GC.@preserve surf tev lev extv bv begin
+        cs = Ref(CSurf(surf.ndiv, surf.naterm, surf.c, surf.uref, surf.pvt, surf.lespcrit[1], surf.levflag[1], 0,
+            (k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot), 0.0, 0.0, 0.0,
+            pointer(surf.theta), pointer(surf.x), pointer(surf.cam), pointer(surf.cam_slope), pointer(surf.bnd_x), pointer(surf.bnd_z),
+            pointer(surf.uind), pointer(surf.wind), pointer(surf.downwash), pointer(surf.aterm), pointer(surf.adot), pointer(surf.aprev),
+            cvorts(bv)))
+        cf = Ref(CField(0.0, 0.0, cvorts(tev), cvorts(lev), cvorts(extv)))
+        check(ccall((:unsflow_ldvm_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{CSurf}, Ptr{CField}), h, cs, cf))
+        s = cs[]; f = cf[]
+        surf.levflag[1] = s.levflag
+        k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = s.kinem
+        surf.a0[1] = s.a0; surf.a0dot[1] = s.a0dot; surf.a0prev[1] = s.a0prev
+        curfield.u[1] = f.u; curfield.w[1] = f.w
+    end
+    unpack!(curfield.tev, tev, nt[]); unpack!(curfield.lev, lev, nl[]); unpack!(curfield.extv, extv, ne[])
+    for i = 1:surf.ndiv-1
+        surf.bv[i].s = bv.s[i]; surf.bv[i].x = bv.x[i]; surf.bv[i].z = bv.z[i]
+    end
+end
+
+"ldvm(surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite, nround)  replaces solvers.jl:144-268"
+ldvm(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0, writeflag = 0,
+     writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+    run_driver(0, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround, solve_mode = solve_mode)
+
+"ldvm2DOF(surf, curfield, strpar, kinem, ...)  replaces solvers.jl:657-788"
+ldvm2DOF(surf::TwoDSurf, curfield::TwoDFlowField, strpar::TwoDOFPar, kinem::KinemPar2DOF, nsteps::Int64 = 500, dtstar::Float64 = 0.015,
+         startflag = 0, writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+    run_driver(1, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround,
+               solve_mode = solve_mode, strpar = strpar, kinem = kinem)
+
+"ldvmLin(...)  replaces solvers.jl:448-655"
+ldvmLin(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0, writeflag = 0,
+        writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6) =
+    run_driver(2, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround)
+
+"lautat(...)  replaces solvers.jl:42-142 (wakerollup = 1)"
+lautat(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0, writeflag = 0,
+       writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+    run_driver(3, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround, solve_mode = solve_mode)
+
+end # module

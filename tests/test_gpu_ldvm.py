@@ -161,3 +161,34 @@ def test_chunked_runs_equal_one_run(gpu_lib, uf):
         outs.append(np.vstack([h.run(c) for c in chunks]))
         h.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
+    """with >= 65536 free vortices the stepper switches to the symmetric pair-tile kernel;
+    it must agree with the (oracle-validated) direct kernel on the same state.  Run in two
+    subprocesses because the switch threshold is read once per process."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, os, numpy as np
+        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+        import unsflow_b200 as uf
+        from oracle import oracle as O
+        from cases import c2_surf
+        surf, fld, dtstar = c2_surf(uf)
+        x, z, g, vc = O.s_wake(66000)
+        fld.tev = uf.VortList.from_arrays(x[:50000] + 0.5, z[:50000], g[:50000], vc[:50000])
+        fld.lev = uf.VortList.from_arrays(x[50000:] + 0.5, z[50000:], g[50000:], vc[50000:])
+        mat, surf, fld = uf.ldvm(surf, fld, 3, dtstar, write_summary=False)
+        np.savez(sys.argv[1], mat=mat, x=np.concatenate([fld.tev.x, fld.lev.x]), vz=np.concatenate([fld.tev.vz, fld.lev.vz]))
+    """)
+    import tempfile
+    outs = []
+    for thr in ("65536", "100000000"):
+        f = tempfile.mktemp(suffix=".npz")
+        env = dict(os.environ, UNSFLOW_SYM_THRESHOLD=thr)
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+        outs.append(np.load(f))
+    a, b = outs
+    assert np.max(np.abs(a["mat"] - b["mat"])) <= 1e-11
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-12
+    assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-12 * max(1.0, np.max(np.abs(b["vz"])))

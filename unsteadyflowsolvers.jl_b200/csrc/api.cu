@@ -1,6 +1,6 @@
 // api.cu -- C-ABI plumbing, stateless host-buffer entry points and measurement helpers.
 #include "../../include/unsflow.h"
-#include "induce.cuh"
+#include "induce_sym.cuh"
 #include "runtime.h"
 #include <cstdarg>
 #include <cstdlib>
@@ -77,7 +77,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     if (int rc = require_device()) return rc;
     cudaStream_t st = 0;
     int64_t off[4] = {0, 0, 0, 0}, tot = 0;
-    for (int k = 0; k < ng; k++) { off[k] = tot; tot += round_up(std::max<int64_t>(g[k].n, 1), kTS); }
+    for (int k = 0; k < ng; k++) { off[k] = tot; tot += round_up(std::max<int64_t>(g[k].n, 1), kSymTB); }
     const bool self_targets = (tx == nullptr);
     if (self_targets) nt = g[0].n;
     double vcu = 1.0;
@@ -126,7 +126,12 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     int64_t ns = 0;
     for (int k = 0; k < ng; k++) ns += g[k].n;
     InducePlan plan = plan_induce(nt, 1, ns, ng, sm_count(), 64);
-    if (d_part.alloc(2 * (int64_t)plan.S * ntp)) return 2;
+    // large uniform-core mutual induction: symmetric pair-tile kernel (induce_sym.cuh)
+    const bool sym = self_targets && uni && g[0].n >= 65536;
+    const int symR = sym_rows_per_thread(g[0].n);
+    const int ctas = sym ? sym_ctas(symR) : 0;
+    if (sym) { plan.S = ctas; }
+    if (d_part.alloc(sym ? (int64_t)ctas * 2 * tot : 2 * (int64_t)plan.S * ntp)) return 2;
     if (d_out.alloc(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
 
     InduceArgs a;
@@ -137,11 +142,21 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     a.vc4_uniform = vcu * vcu * vcu * vcu;
     a.pu = d_part.p; a.pw = d_part.p + (int64_t)plan.S * ntp;
     a.tstride = ntp;
-    if (int rc = launch_induce_direct(a, plan, uni, rsqrt_order(), st)) return rc;
+    if (sym) {
+        if (d_part.zero(st)) return 2;
+        SymArgs sa;
+        sa.x = a.sx; sa.z = a.sz; sa.g = a.sg;
+        sa.reg = d_reg.p; sa.nreg = 1; sa.bv_reg = ng > 1 ? 1 : -1;
+        sa.vc4 = a.vc4_uniform; sa.P = d_part.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
+        if (int rc = launch_induce_sym(sa, symR, rsqrt_order(), st)) return rc;
+    } else {
+        if (int rc = launch_induce_direct(a, plan, uni, rsqrt_order(), st)) return rc;
+    }
 
     FinishArgs f;
     memset(&f, 0, sizeof(f));
     f.pu = a.pu; f.pw = a.pw; f.tstride = ntp; f.S = plan.S;
+    if (sym) { f.pu = d_part.p; f.pw = d_part.p + tot; f.tstride = 2 * tot; f.S = ctas; }
     f.treg = d_reg.p + 1; f.ntreg = 1;
     f.vx = d_out.p; f.vz = d_out.p + ntp;
     f.fs = nullptr; f.fs_u = fs_u; f.fs_w = fs_w;

@@ -1,7 +1,9 @@
 // induce.cu -- launch plumbing for the induction kernels (see induce.cuh).
 #define UNSFLOW_INDUCE_KERNELS
 #include "induce_sym.cuh"
+#include "runtime.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace unsflow {
 
@@ -54,20 +56,51 @@ int launch_induce_finish(const FinishArgs &a, long long nt_ub, cudaStream_t st) 
     return 0;
 }
 
-size_t sym_smem_bytes() { return sizeof(double) * (2 * 3 * kSymTB + 2 * kSymTB) + 2 * sizeof(uint64_t) + 16; }
+size_t sym_smem_bytes(int R) { return sizeof(double) * (size_t)(2 * 3 + 2) * kThreads * R + 2 * sizeof(uint64_t) + 16; }
 
-int launch_induce_sym(const SymArgs &a, int ctas, int order, cudaStream_t st) {
+int sym_rows_per_thread(long long n) {
+    // env UNSFLOW_SYM_R in {1,2,4,8} forces a tile size (experiments); default: 2048-wide tiles
+    // (R = 8, 1 CTA/SM) once there are enough tiles per CTA, else 1024-wide (R = 4, 2 CTAs/SM)
+    static int forced = [] { const char *e = getenv("UNSFLOW_SYM_R"); int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0; }();
+    if (forced) return forced;
+    return n >= 400000 ? 8 : 4;
+}
+
+template <int R, int O>
+static int launch_sym_one(const SymArgs &a, int ctas, cudaStream_t st) {
     static bool attr_set = false;
-    const size_t smem = sym_smem_bytes();
+    const size_t smem = sym_smem_bytes(R);
     if (!attr_set) {
-        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<R, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    if (order == 2) k_induce_sym<2><<<ctas, kThreads, smem, st>>>(a);
-    else k_induce_sym<3><<<ctas, kThreads, smem, st>>>(a);
+    k_induce_sym<R, O><<<ctas, kThreads, smem, st>>>(a);
     UF_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int R>
+static int sym_occ() {
+    int nb = 0;
+    cudaFuncSetAttribute(k_induce_sym<R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sym_smem_bytes(R));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_induce_sym<R, 3>, kThreads, sym_smem_bytes(R)) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+int sym_ctas(int R) {
+    static int occ[9] = {0};
+    if (!occ[R]) occ[R] = R == 8 ? sym_occ<8>() : (R == 4 ? sym_occ<4>() : (R == 2 ? sym_occ<2>() : sym_occ<1>()));
+    return occ[R] * sm_count();
+}
+
+int sym_ctas_max() { return std::max(std::max(sym_ctas(8), sym_ctas(4)), std::max(sym_ctas(2), sym_ctas(1))); }
+
+int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st) {
+    const int ctas = sym_ctas(R);
+    if (R == 8) return order == 2 ? launch_sym_one<8, 2>(a, ctas, st) : launch_sym_one<8, 3>(a, ctas, st);
+    if (R == 4) return order == 2 ? launch_sym_one<4, 2>(a, ctas, st) : launch_sym_one<4, 3>(a, ctas, st);
+    if (R == 2) return order == 2 ? launch_sym_one<2, 2>(a, ctas, st) : launch_sym_one<2, 3>(a, ctas, st);
+    return order == 2 ? launch_sym_one<1, 2>(a, ctas, st) : launch_sym_one<1, 3>(a, ctas, st);
 }
 
 }  // namespace unsflow

@@ -23,9 +23,8 @@
 
 namespace unsflow {
 
-constexpr int kSymR = 4;
-constexpr int kSymTB = kThreads * kSymR;           // 1024 vortices per block
-constexpr int kSymChunk = kSymTB / (kThreads / 32);   // 128 columns per warp per phase
+constexpr int kSymRMax = 8;
+constexpr int kSymTB = kThreads * kSymRMax;        // slab alignment: largest pair-tile block (2048)
 
 struct SymArgs {
     const double *x, *z, *g;     // slabs (absolute indexing); dead entries have g = 0
@@ -38,18 +37,32 @@ struct SymArgs {
     int rank, nranks;            // split of the tile list over GPUs
 };
 
-size_t sym_smem_bytes();
-int launch_induce_sym(const SymArgs &a, int ctas, int order, cudaStream_t st);
+// contiguous share [begin, end) of `total` work items owned by `part` of `nparts` (ranks, then CTAs)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void split_range(long long total, long long part, long long nparts, long long *begin, long long *end) {
+    *begin = total * part / nparts;
+    *end = total * (part + 1) / nparts;
+}
+
+size_t sym_smem_bytes(int R);
+int sym_rows_per_thread(long long n);   // rows per thread R (tile = 256*R) chosen for n free vortices
+int sym_ctas(int R);                    // persistent CTAs = resident CTAs per SM x SMs (= number of partial planes)
+int sym_ctas_max();
+int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st);
 
 #if defined(__CUDACC__) && defined(UNSFLOW_INDUCE_KERNELS)
 
+template <int TB>
 __device__ __forceinline__ long long sym_blocks_in(long long b, long long e) {
-    return e > b ? (e + kSymTB - 1) / kSymTB - b / kSymTB : 0;
+    return e > b ? (e + TB - 1) / TB - b / TB : 0;
 }
+template <int TB>
 __device__ __forceinline__ long long sym_block_start(const Regions &rg, int nreg, long long k) {
     for (int r = 0; r < nreg; r++) {
-        const long long n = sym_blocks_in(rg.begin[r], rg.end[r]);
-        if (k < n) return (rg.begin[r] / kSymTB + k) * kSymTB;
+        const long long n = sym_blocks_in<TB>(rg.begin[r], rg.end[r]);
+        if (k < n) return (rg.begin[r] / TB + k) * TB;
         k -= n;
     }
     return -1;
@@ -57,9 +70,9 @@ __device__ __forceinline__ long long sym_block_start(const Regions &rg, int nreg
 // row-major upper triangle incl. diagonal: row I starts at I*nb - I*(I-1)/2
 __device__ __forceinline__ long long sym_row_offset(long long I, long long nb) { return I * nb - I * (I - 1) / 2; }
 
-template <int ORDER>
-__global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
-    constexpr int R = kSymR, TB = kSymTB;
+template <int R, int ORDER>
+__global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_induce_sym(const SymArgs a) {
+    constexpr int TB = kThreads * R, kChunk = TB / (kThreads / 32);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_col = reinterpret_cast<double *>(smem_raw);             // [2][3][TB]
     double2 *s_acc = reinterpret_cast<double2 *>(s_col + 2 * 3 * TB); // [TB]
@@ -68,12 +81,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Regions reg = *a.reg;
     long long nb = 0;
-    for (int r = 0; r < a.nreg; r++) nb += sym_blocks_in(reg.begin[r], reg.end[r]);
+    for (int r = 0; r < a.nreg; r++) nb += sym_blocks_in<TB>(reg.begin[r], reg.end[r]);
     const long long W = nb * (nb + 1) / 2;
     // rank range, then this CTA's contiguous chunk of it
-    const long long r0 = W * a.rank / a.nranks, r1 = W * (a.rank + 1) / a.nranks;
-    const long long t0 = r0 + (r1 - r0) * blockIdx.x / gridDim.x;
-    const long long t1 = r0 + (r1 - r0) * (blockIdx.x + 1) / gridDim.x;
+    long long r0, r1, c0, c1;
+    split_range(W, a.rank, a.nranks, &r0, &r1);
+    split_range(r1 - r0, blockIdx.x, gridDim.x, &c0, &c1);
+    const long long t0 = r0 + c0, t1 = r0 + c1;
     if (t0 >= t1) return;
 
     // (I, J) of tile t0
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
     __syncthreads();
 
     auto issue = [&](long long Jblk, int stage) {
-        const long long e0 = sym_block_start(reg, a.nreg, Jblk);
+        const long long e0 = sym_block_start<TB>(reg, a.nreg, Jblk);
         constexpr uint32_t bytes = TB * sizeof(double);
         double *dst = s_col + stage * 3 * TB;
         mbar_expect_tx(&s_bar[stage], 3 * bytes);
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
                 }
             }
             rowI = I;
-            row_start = sym_block_start(reg, a.nreg, I);
+            row_start = sym_block_start<TB>(reg, a.nreg, I);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const long long i = row_start + tid + r * kThreads;
@@ -171,11 +185,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
             __syncthreads();
             for (int p = 0; p < kThreads / 32; p++) {
-                const int base = ((warp + p) & (kThreads / 32 - 1)) * kSymChunk;
+                const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
+                // software pipeline: the column read for step s+1 is issued before the
+                // accumulator read-modify-write of step s (column data is read-only in a tile)
+                int j = base + (lane & (kChunk - 1));
+                double xj = sx[j], zj = sz[j], gj = sg[j];
 #pragma unroll 1
-                for (int s = 0; s < kSymChunk; s++) {
-                    const int j = base + ((s + lane) & (kSymChunk - 1));
-                    const double xj = sx[j], zj = sz[j], gj = sg[j];
+                for (int s = 0; s < kChunk; s++) {
+                    const int jn = base + ((s + 1 + lane) & (kChunk - 1));
+                    const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
                     double cu = 0.0, cw = 0.0;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -193,11 +211,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_induce_sym(const SymArgs a) {
                     acc.y += cw;
                     s_acc[j] = acc;
                     __syncwarp();   // lane l+1 wrote column j+1 in this step; lane l reads it next step
+                    j = jn; xj = xn; zj = zn; gj = gn;
                 }
                 __syncthreads();
             }
             // flush the column accumulators into this CTA's private plane
-            const long long cstart = sym_block_start(reg, a.nreg, J);
+            const long long cstart = sym_block_start<TB>(reg, a.nreg, J);
             for (int c = tid; c < TB; c += kThreads) {
                 const double2 acc = s_acc[c];
                 Pu[cstart + c] += acc.x;

@@ -14,11 +14,11 @@
 // and surplus blocks exit.  Vortex families are slabs of one SoA allocation with a moving
 // head (popfirst! of the Spalart merge = zero the strength and advance the head).
 #include "../../include/unsflow.h"
-#define UNSFLOW_INDUCE_DECL_ONLY
-#include "induce.cuh"
+#include "induce_sym.cuh"
 #include "runtime.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -27,6 +27,11 @@ namespace unsflow {
 constexpr int kNdMax = 256;    // max ndiv
 constexpr int kNaMax = 128;    // max naterm
 constexpr int kSolveThreads = 256;
+// free vortices from which the pair-tile kernel wins (env UNSFLOW_SYM_THRESHOLD overrides, for tests)
+static int64_t sym_threshold() {
+    static int64_t v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? (int64_t)atoll(e) : (int64_t)65536; }();
+    return v;
+}
 
 struct StepState {
     Regions wake;        // [0] tev, [1] lev, [2] extv, [3] bound vortices (absolute slab indices)
@@ -567,6 +572,8 @@ struct unsflow_ldvm {
     DevBuf<double> mat;       // mat_cap x 8
     DevBuf<double> p2;        // bound-sweep partials [2][S2max][ndivpad]
     DevBuf<double> p1;        // roll-up partials [2][S1max][tot]
+    DevBuf<double> planes;    // symmetric kernel partial planes [ctas][2][tot] (allocated on first use)
+    int ctas = 0;
     int S2max = 1, S1max = 1;
     int64_t ndivpad = 0;
     int64_t kin_rows = 0;
@@ -622,10 +629,11 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     h->opts = *op;
     const int nd = h->ndiv = sf->ndiv, na = h->naterm = sf->naterm;
     h->ntev0 = fl->tev.n; h->nlev0 = fl->lev.n; h->nextv = fl->extv.n;
-    h->cap_t = round_up(h->ntev0 + op->max_steps + 1, kTS);
-    h->cap_l = round_up(h->nlev0 + op->max_steps + 1, kTS);
-    h->cap_e = round_up(std::max<int64_t>(h->nextv, 1), kTS);
-    h->bvpad = round_up(nd - 1, kTS);
+    // slabs start on pair-tile boundaries (kSymTB is a multiple of the direct kernel's kTS)
+    h->cap_t = round_up(h->ntev0 + op->max_steps + 1, kSymTB);
+    h->cap_l = round_up(h->nlev0 + op->max_steps + 1, kSymTB);
+    h->cap_e = round_up(std::max<int64_t>(h->nextv, 1), kSymTB);
+    h->bvpad = round_up(nd - 1, kSymTB);
     h->off_t = 0; h->off_l = h->cap_t; h->off_e = h->off_l + h->cap_l; h->off_b = h->off_e + h->cap_e;
     h->tot = h->off_b + h->bvpad;
     h->mat_cap = std::max<int64_t>(op->max_steps, 1);
@@ -802,6 +810,7 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         h->launches++;
         {
             // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
+            const bool sym = h->uniform && nwake_ub >= sym_threshold();
             InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + h->ndiv - 1, 4, smc, h->S1max);
             InduceArgs a;
             a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
@@ -809,10 +818,30 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
             a.sreg = &h->st.p->wake; a.treg = &h->st.p->wake; a.nsreg = 4; a.ntreg = 3;
             a.vc4_uniform = h->vc4u;
             a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
-            if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+            if (sym) {
+                if (!h->planes.p && h->planes.alloc((int64_t)sym_ctas_max() * 2 * tot)) return 2;
+                const int symR = sym_rows_per_thread(nwake_ub);
+                h->ctas = sym_ctas(symR);
+                // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
+                const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
+                const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
+                for (int r = 0; r < 3; r++) {
+                    const int64_t b = lo[r], e = std::min(round_up(hi[r], kSymTB), tot);
+                    if (e > b)
+                        UF_CUDA(cudaMemset2DAsync(h->planes.p + b, sizeof(double) * tot, 0, sizeof(double) * (e - b), (size_t)h->ctas * 2, st));
+                }
+                SymArgs sa;
+                sa.x = h->dev.wx; sa.z = h->dev.wz; sa.g = h->dev.wg;
+                sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
+                sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
+                if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
+            } else {
+                if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+            }
             FinishArgs f;
             memset(&f, 0, sizeof(f));
             f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
+            if (sym) { f.pu = h->planes.p; f.pw = h->planes.p + tot; f.tstride = 2 * tot; f.S = h->ctas; }
             f.treg = &h->st.p->wake; f.ntreg = 3;
             f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
             f.fs = h->st.p->fs; f.dt = h->opts.dt;

@@ -62,7 +62,7 @@ struct unsflow_wake {
     DevBuf<double> vel;    // [vx | vz], each npad
     DevBuf<double> part;   // [pu | pw], each S*npad
     DevBuf<double> planes; // symmetric kernel: [ctas][2][tot]
-    int ctas = 0;
+    int ctas = 0, symR = 4;
     bool want_sym = false;
     DevBuf<Regions> reg;   // [0] sources, [1] my targets
     InducePlan plan{};
@@ -75,7 +75,26 @@ struct unsflow_wake {
     static constexpr int kMaxTimed = 64;
 };
 
+// target slice of the direct kernel: equal slices (NCCL all-gather needs equal counts)
+static int64_t slice_len(int64_t n, int nranks) { return round_up((n + nranks - 1) / nranks, 2); }
+
 extern "C" {
+
+int unsflow_partition(int64_t n, int nranks, int rank, int variant, int64_t *begin, int64_t *end) {
+    UF_CHECK(n > 0 && nranks >= 1 && rank >= 0 && rank < nranks && begin && end, "unsflow_partition: bad arguments");
+    if (variant == UNSFLOW_KERNEL_SYMMETRIC) {
+        const long long tb = (long long)kThreads * sym_rows_per_thread(n);
+        const long long nb = (n + tb - 1) / tb, W = nb * (nb + 1) / 2;
+        long long b, e;
+        split_range(W, rank, nranks, &b, &e);
+        *begin = b; *end = e;
+    } else {
+        const int64_t sl = slice_len(n, nranks);
+        *begin = std::min<int64_t>(n, rank * sl);
+        *end = std::min<int64_t>(n, (rank + 1) * sl);
+    }
+    return 0;
+}
 
 int unsflow_nccl_unique_id(void *id128) {
     UF_CHECK(id128 != nullptr, "unsflow_nccl_unique_id: null argument");
@@ -97,7 +116,7 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     UF_CHECK(w != nullptr, "out of host memory");
     w->n = n; w->nbv = nbv; w->rank = rank; w->nranks = nranks;
     w->variant = variant;
-    w->slice = round_up((n + nranks - 1) / nranks, 2);
+    w->slice = slice_len(n, nranks);
     w->npad = round_up(w->slice * nranks, kSymTB);
     w->bvpad = round_up(std::max<int64_t>(nbv, 1), kTS);
     w->tot = w->npad + w->bvpad;
@@ -112,7 +131,8 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     w->plan = plan_induce(my_t, 1, n + nbv, 2, sm_count(), 64);
     if (w->part.alloc(2 * (int64_t)w->plan.S * w->npad)) return fail(2);
     w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= 65536);
-    w->ctas = 2 * sm_count();
+    w->symR = sym_rows_per_thread(n);
+    w->ctas = sym_ctas(w->symR);
     if (w->want_sym && w->planes.alloc((int64_t)w->ctas * 2 * w->tot)) return fail(2);
     if (w->src.zero(w->st) || w->vel.zero(w->st)) return fail(2);
     Regions h[2];
@@ -212,7 +232,7 @@ int unsflow_wake_step(unsflow_wake *w, int64_t nsteps, double u_inf, double w_in
         if (sym) {
             // every rank evaluates its share of the unordered pair tiles for ALL vortices
             UF_CUDA(cudaMemsetAsync(w->planes.p, 0, sizeof(double) * (size_t)w->ctas * 2 * tot, w->st));
-            if (int rc = launch_induce_sym(sa, w->ctas, rsqrt_order(), w->st)) return rc;
+            if (int rc = launch_induce_sym(sa, w->symR, rsqrt_order(), w->st)) return rc;
             if (timed) { UF_CUDA(cudaEventRecord(w->kev[2 * is + 1], w->st)); w->ktimed = (int)is + 1; }
             FinishArgs fsym = f;
             fsym.pu = w->planes.p; fsym.pw = w->planes.p + tot; fsym.tstride = 2 * tot; fsym.S = w->ctas;
