@@ -183,11 +183,14 @@ int unsflow_ldvm_destroy(unsflow_ldvm *h);
 /* Runs `nmember` independent LDVM simulations (one thread-block cluster per member, member
  * state in shared memory) that share geometry (surf) but differ in kinematics table and
  * lespcrit.  tables: nmember x nsteps x 9 row-major; lespcrit: nmember;
- * mat_out: nmember blocks of COLUMN-major nsteps x 8.  member0/nmember select this rank's
- * shard when members are spread over several GPUs/processes. */
+ * mat_out: nmember blocks of COLUMN-major nsteps x 8.  Members start from `surf` with an empty
+ * wake.  To spread an ensemble over several GPUs/processes each rank passes its own shard of
+ * tables / lespcrit / mat_out (no communication).  Prescribed-motion drivers only. */
 int unsflow_ldvm_batch_run(const unsflow_surf *surf, const unsflow_opts *opts, int64_t nmember,
                            int64_t nsteps, const double *tables, const double *lespcrit,
                            double *mat_out, int64_t *ntev_out, int64_t *nlev_out);
+/* CUDA-event milliseconds of the ensemble kernel of the last unsflow_ldvm_batch_run on this thread */
+int unsflow_ldvm_batch_timing(float *ms_kernel);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* DFMA-chain microbenchmark: measured FP64 (non-tensor) peak of the current device, TFLOP/s

@@ -192,3 +192,27 @@ def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
     assert np.max(np.abs(a["mat"] - b["mat"])) <= 1e-11
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-12
     assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-12 * max(1.0, np.max(np.abs(b["vz"])))
+
+
+def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):
+    """config 3 in miniature: members with different reduced frequency / LESPcrit, one CTA each"""
+    ks = [0.1, 0.4, 0.8]
+    lesps = [0.08, 0.2, 10.0]
+    nsteps, dtstar = 90, 0.015
+    members, tables, lc = [], [], []
+    for k in ks:
+        for l in lesps:
+            kin = uf.KinemDef(uf.SinDef(0.0, 20.0 * math.pi / 180, k, 0.0), uf.ConstDef(0.0), uf.ConstDef(1.0))
+            surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [l])
+            members.append(surf)
+            tables.append(uf.kinematics_table(surf, uf.TwoDFlowField(), nsteps, dtstar))
+            lc.append(l)
+    base = members[0]
+    mats, ntev, nlev, ms = uf.ldvm_batch(base, np.array(tables), np.array(lc), dtstar)
+    assert mats.shape == (9, nsteps, 8) and np.all(ntev == nsteps) and ms > 0
+    for m, surf in enumerate(members):
+        sim = oracle.Sim(surf, uf.TwoDFlowField())
+        omat = sim.run(oracle.DRIVER_LDVM, tables[m], dtstar)
+        assert np.max(np.abs(mats[m] - omat)) <= HTOL, m
+        assert nlev[m] == len(sim.get_vorts(1)["x"])
+    assert nlev.max() > 10 and nlev.min() == 0

@@ -103,7 +103,7 @@ __device__ void dev_update_kinem2dof(const LdvmDev &d, StepState *s) {
     s->kin[2] = k[alphadot]; s->kin[3] = k[hdot]; s->kin[0] = k[alpha]; s->kin[1] = k[h];
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) {
+__device__ void step_head(const LdvmDev &d) {
     StepState *s = d.st;
     const int tid = threadIdx.x;
     __shared__ double sh_kin[6];
@@ -202,7 +202,7 @@ __device__ void dev_spalart(const LdvmDev &d, long long *begin, long long end, d
     }
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) {
+__device__ void step_solve(const LdvmDev &d) {
     StepState *s = d.st;
     const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm;
     __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
@@ -548,9 +548,154 @@ __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) {
     }
 }
 
+
+__global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) { step_head(d); }
+__global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) { step_solve(d); }
+
+// ---------------------------------------------------------------------------------------------
+// Ensemble kernel (config 3): one CTA per member runs the WHOLE step loop; the member's state
+// (a few hundred vortices, <100 KB) stays in L1/L2, induction tiles are staged in shared memory.
+// Members are independent: no inter-CTA communication, any number of GPUs by sharding members.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEnsTile = 256;   // sources staged per shared-memory tile
+constexpr int kEnsR = 4;        // targets per thread in the member roll-up
+
+// pair kernel shared by the two block-level induction loops (13 FP64 instr, cubic rsqrt)
+__device__ __forceinline__ void pair_acc(double xj, double zj, double gj, double vc4, double tx, double tz, double &u, double &w) {
+    const double dx = xj - tx, dz = zj - tz;
+    const double d2 = fma(dz, dz, dx * dx);
+    const double y = rsqrt_full<3>(fma(d2, d2, vc4));
+    const double m = gj * y;
+    u = fma(-dz, m, u);
+    w = fma(dx, m, w);
+}
+
+// cooperative load of sources [b, b+cnt) into a zero-strength-padded tile
+__device__ __forceinline__ void ens_stage(const LdvmDev &d, long long b, int cnt, double *sx, double *sz, double *sg, double *sv) {
+    for (int k = threadIdx.x; k < kEnsTile; k += blockDim.x) {
+        const bool ok = k < cnt;
+        sx[k] = ok ? d.wx[b + k] : 0.0;
+        sz[k] = ok ? d.wz[b + k] : 0.0;
+        sg[k] = ok ? d.wg[b + k] : 0.0;
+        sv[k] = ok ? d.wvc4[b + k] : 1.0;
+    }
+}
+
+// update_indbound (calcs.jl:35-38) inside one CTA: group g of threads owns sources j = g (mod G)
+__device__ void ens_sweep(const LdvmDev &d, double *p2u, double *p2w, int *S2_out, double *tile) {
+    const StepState *s = d.st;
+    const int nd = d.ndiv, G = max(1, (int)blockDim.x / nd);
+    const int grp = threadIdx.x / nd, i = threadIdx.x - grp * nd;
+    const bool act = grp < G;
+    double *sx = tile, *sz = tile + kEnsTile, *sg = tile + 2 * kEnsTile, *sv = tile + 3 * kEnsTile;
+    const double tx = act ? d.bnd_x[i] : 0.0, tz = act ? d.bnd_z[i] : 0.0;
+    double u = 0.0, w = 0.0;
+    for (int r = 0; r < 3; r++) {
+        for (long long b = s->wake.begin[r]; b < s->wake.end[r]; b += kEnsTile) {
+            const int cnt = (int)min((long long)kEnsTile, s->wake.end[r] - b);
+            __syncthreads();
+            ens_stage(d, b, cnt, sx, sz, sg, sv);
+            __syncthreads();
+            if (act)
+                for (int j = grp; j < cnt; j += G) pair_acc(sx[j], sz[j], sg[j], sv[j], tx, tz, u, w);
+        }
+    }
+    if (act) { p2u[grp * d.p2stride + i] = u; p2w[grp * d.p2stride + i] = w; }
+    *S2_out = G;
+    __syncthreads();
+}
+
+// one chunk of RR*blockDim targets of region tr against all sources (free + bound vortices)
+template <int RR>
+__device__ __forceinline__ void ens_rollup_chunk(const LdvmDev &d, const StepState *s, int tr, long long tb, double *tile) {
+    double *sx = tile, *sz = tile + kEnsTile, *sg = tile + 2 * kEnsTile, *sv = tile + 3 * kEnsTile;
+    const long long tend = s->wake.end[tr];
+    double tx[RR], tz[RR], u[RR], w[RR];
+#pragma unroll
+    for (int r = 0; r < RR; r++) {
+        const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
+        const bool ok = i < tend;
+        tx[r] = ok ? d.wx[i] : 0.0; tz[r] = ok ? d.wz[i] : 0.0; u[r] = 0.0; w[r] = 0.0;
+    }
+    // warps without a single live target skip the arithmetic (they still help staging)
+    const bool warp_live = tb + (threadIdx.x & ~31) < tend;
+    for (int sr = 0; sr < 4; sr++) {
+        for (long long b = s->wake.begin[sr]; b < s->wake.end[sr]; b += kEnsTile) {
+            const int cnt = (int)min((long long)kEnsTile, s->wake.end[sr] - b);
+            __syncthreads();
+            ens_stage(d, b, cnt, sx, sz, sg, sv);
+            __syncthreads();
+            if (warp_live) {
+                const int cpad = (cnt + 1) & ~1;
+#pragma unroll 2
+                for (int j = 0; j < cpad; j++) {
+                    const double xj = sx[j], zj = sz[j], gj = sg[j], vj = sv[j];
+#pragma unroll
+                    for (int r = 0; r < RR; r++) pair_acc(xj, zj, gj, vj, tx[r], tz[r], u[r], w[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RR; r++) {
+        const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
+        if (i < tend) {
+            d.wvx[i] = u[r] * kInvTwoPi + s->fs[0];      // calcs.jl:252-277
+            d.wvz[i] = w[r] * kInvTwoPi + s->fs[1];
+        }
+    }
+}
+
+// wakeroll (calcs.jl:222-294) inside one CTA
+__device__ void ens_rollup(const LdvmDev &d, double *tile) {
+    StepState *s = d.st;
+    for (int tr = 0; tr < 3; tr++) {
+        for (long long tb = s->wake.begin[tr]; tb < s->wake.end[tr]; tb += (long long)kEnsR * blockDim.x) {
+            const long long rem = s->wake.end[tr] - tb;
+            const int nrow = (int)min((long long)kEnsR, (rem + blockDim.x - 1) / blockDim.x);   // block-uniform
+            switch (nrow) {
+                case 1: ens_rollup_chunk<1>(d, s, tr, tb, tile); break;
+                case 2: ens_rollup_chunk<2>(d, s, tr, tb, tile); break;
+                case 3: ens_rollup_chunk<3>(d, s, tr, tb, tile); break;
+                default: ens_rollup_chunk<4>(d, s, tr, tb, tile); break;
+            }
+        }
+    }
+    __syncthreads();
+    for (int tr = 0; tr < 3; tr++)                                // calcs.jl:280-291
+        for (long long i = s->wake.begin[tr] + threadIdx.x; i < s->wake.end[tr]; i += blockDim.x) {
+            d.wx[i] += d.dt * d.wvx[i];
+            d.wz[i] += d.dt * d.wvz[i];
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_ensemble(const LdvmDev *members, long long nsteps) {
+    __shared__ double tile[4 * kEnsTile];
+    __shared__ LdvmDev d;
+    if (threadIdx.x == 0) d = members[blockIdx.x];
+    __syncthreads();
+    double *p2u = const_cast<double *>(d.p2u), *p2w = const_cast<double *>(d.p2w);
+    for (long long is = 0; is < nsteps; is++) {
+        step_head(d);
+        __syncthreads();
+        if (d.driver != UNSFLOW_DRIVER_LAUTAT) {
+            int S2;
+            ens_sweep(d, p2u, p2w, &S2, tile);
+            if (threadIdx.x == 0) d.S2 = S2;
+            __syncthreads();
+        }
+        step_solve(d);
+        __syncthreads();
+        ens_rollup(d, tile);
+    }
+}
+
 }  // namespace unsflow
 
 using namespace unsflow;
+
+static thread_local float g_batch_ms = 0.f;   // CUDA-event time of the last k_ensemble launch
 
 struct unsflow_ldvm {
     unsflow_opts opts{};
@@ -936,10 +1081,125 @@ int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {
     return 0;
 }
 
-int unsflow_ldvm_batch_run(const unsflow_surf *, const unsflow_opts *, int64_t, int64_t, const double *, const double *,
-                           double *, int64_t *, int64_t *) {
-    set_error("unsflow_ldvm_batch_run: not implemented yet");
-    return 5;
+int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
+                           const double *tables, const double *lespcrit, double *mat_out, int64_t *ntev_out,
+                           int64_t *nlev_out) {
+    UF_CHECK(sf && op && tables && mat_out, "unsflow_ldvm_batch_run: null argument");
+    UF_CHECK(nmember > 0 && nsteps > 0, "unsflow_ldvm_batch_run: need nmember > 0 and nsteps > 0");
+    UF_CHECK(sf->ndiv >= 3 && sf->ndiv <= kNdMax && sf->naterm >= 3 && sf->naterm <= kNaMax, "unsflow_ldvm_batch_run: bad ndiv/naterm");
+    UF_CHECK(op->driver == UNSFLOW_DRIVER_LDVM || op->driver == UNSFLOW_DRIVER_LDVMLIN || op->driver == UNSFLOW_DRIVER_LAUTAT,
+             "unsflow_ldvm_batch_run: prescribed-motion drivers only (ldvm, ldvmLin, lautat)");
+    UF_CHECK(op->dt > 0, "unsflow_ldvm_batch_run: dt must be > 0");
+    UF_CHECK(sf->bv.n == sf->ndiv - 1, "unsflow_ldvm_batch_run: surf.bv must hold ndiv-1 vortices");
+    if (int rc = require_device()) return rc;
+    if (op->device >= 0) UF_CUDA(cudaSetDevice(op->device));
+    const int nd = sf->ndiv, na = sf->naterm;
+    const int64_t M = nmember;
+    // per-member slabs: [TEV | LEV | EXTV(empty) | BV]
+    const int64_t cap_t = round_up(nsteps + 1, 8), cap_l = round_up(nsteps + 1, 8), cap_e = 8, bvp = round_up(nd - 1, 8);
+    const int64_t off_l = cap_t, off_e = off_l + cap_l, off_b = off_e + cap_e, tot = off_b + bvp;
+    const int64_t nsurf = 9 * nd + 3 * na, ndp = round_up(nd, 8), np2 = 2 * 4 * ndp;
+    DevBuf<StepState> st;
+    DevBuf<LdvmDev> devs;
+    DevBuf<double> surf, tabs, wake, kin, mat, p2;
+    if (st.alloc(M) || devs.alloc(M) || surf.alloc(M * nsurf) || tabs.alloc(2 * (na + 1) * nd) || wake.alloc(M * 7 * tot) ||
+        kin.alloc(M * nsteps * 9) || mat.alloc(M * nsteps * 8) || p2.alloc(M * np2))
+        return 2;
+    cudaStream_t stream = 0;
+    // ---- host staging of ONE member, replicated ------------------------------------------------
+    std::vector<double> hs((size_t)nsurf);
+    const double *sarr[9] = {sf->theta, sf->x, sf->cam, sf->cam_slope, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
+    for (int k = 0; k < 9; k++) memcpy(&hs[(size_t)k * nd], sarr[k], sizeof(double) * nd);
+    memcpy(&hs[(size_t)9 * nd], sf->aterm, sizeof(double) * na);
+    memcpy(&hs[(size_t)9 * nd + na], sf->adot, sizeof(double) * na);
+    memcpy(&hs[(size_t)9 * nd + 2 * na], sf->aprev, sizeof(double) * na);
+    std::vector<double> ht((size_t)(2 * (na + 1) * nd));
+    for (int n = 0; n <= na; n++)
+        for (int i = 0; i < nd; i++) {
+            ht[(size_t)n * nd + i] = n == 0 ? 1.0 : std::cos(n * sf->theta[i]);
+            ht[(size_t)(na + 1) * nd + (size_t)n * nd + i] = std::sin(n * sf->theta[i]);
+        }
+    const double vc_new = 0.02 * sf->c, vc4 = vc_new * vc_new * vc_new * vc_new;
+    std::vector<double> hw((size_t)(7 * tot), 0.0);
+    for (int64_t i = 0; i < tot; i++) { hw[3 * tot + i] = vc4; hw[4 * tot + i] = vc_new; }
+    for (int64_t i = 0; i < nd - 1; i++) {
+        hw[0 * tot + off_b + i] = sf->bv.x[i]; hw[1 * tot + off_b + i] = sf->bv.z[i]; hw[2 * tot + off_b + i] = sf->bv.s[i];
+        hw[4 * tot + off_b + i] = sf->bv.vc[i];
+        hw[3 * tot + off_b + i] = sf->bv.vc[i] * sf->bv.vc[i] * sf->bv.vc[i] * sf->bv.vc[i];
+    }
+    std::vector<StepState> hst((size_t)M);
+    std::vector<LdvmDev> hd((size_t)M);
+    StepState s0;
+    memset(&s0, 0, sizeof(s0));
+    s0.wake.begin[0] = 0; s0.wake.end[0] = 0;
+    s0.wake.begin[1] = off_l; s0.wake.end[1] = off_l;
+    s0.wake.begin[2] = off_e; s0.wake.end[2] = off_e;
+    s0.wake.begin[3] = off_b; s0.wake.end[3] = off_b + nd - 1;
+    s0.bnd.begin[0] = 0; s0.bnd.end[0] = nd;
+    s0.levflag = sf->levflag;
+    for (int k = 0; k < 6; k++) s0.kin[k] = sf->kinem[k];
+    s0.a0 = sf->a0; s0.a0dot = sf->a0dot; s0.a0prev = sf->a0prev;
+    for (int64_t m = 0; m < M; m++) {
+        hst[m] = s0;
+        LdvmDev &d = hd[m];
+        memset(&d, 0, sizeof(d));
+        d.st = st.p + m;
+        d.ndiv = nd; d.naterm = na; d.driver = op->driver; d.solve_mode = op->solve_mode; d.del_kind = op->delvort_kind;
+        d.del_limit = op->del_limit; d.del_dist = op->del_dist; d.del_tol = op->del_tol;
+        d.c = sf->c; d.uref = sf->uref; d.pvt = sf->pvt; d.lespcrit = lespcrit ? lespcrit[m] : sf->lespcrit; d.dt = op->dt;
+        d.vc_new = vc_new; d.vc4_new = vc4;
+        double *sp = surf.p + m * nsurf;
+        d.theta = sp; d.x = sp + nd; d.cam = sp + 2 * nd; d.cam_slope = sp + 3 * nd; d.bnd_x = sp + 4 * nd; d.bnd_z = sp + 5 * nd;
+        d.uind = sp + 6 * nd; d.wind = sp + 7 * nd; d.downwash = sp + 8 * nd;
+        d.aterm = sp + 9 * nd; d.adot = sp + 9 * nd + na; d.aprev = sp + 9 * nd + 2 * na;
+        d.costab = tabs.p; d.sintab = tabs.p + (int64_t)(na + 1) * nd;
+        double *wp = wake.p + m * 7 * tot;
+        d.wx = wp; d.wz = wp + tot; d.wg = wp + 2 * tot; d.wvc4 = wp + 3 * tot; d.wvc = wp + 4 * tot; d.wvx = wp + 5 * tot; d.wvz = wp + 6 * tot;
+        d.kin = kin.p + m * nsteps * 9; d.kin_rows = nsteps;
+        d.mat = mat.p + m * nsteps * 8;
+        d.p2u = p2.p + m * np2; d.p2w = p2.p + m * np2 + 4 * ndp; d.p2stride = ndp; d.S2 = 1;
+    }
+    UF_CUDA(cudaMemcpyAsync(st.p, hst.data(), sizeof(StepState) * M, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(devs.p, hd.data(), sizeof(LdvmDev) * M, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(tabs.p, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(kin.p, tables, sizeof(double) * M * nsteps * 9, cudaMemcpyHostToDevice, stream));
+    // replicate the member image on the device: upload once, then D2D copies with doubling
+    UF_CUDA(cudaMemcpyAsync(surf.p, hs.data(), sizeof(double) * nsurf, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(wake.p, hw.data(), sizeof(double) * 7 * tot, cudaMemcpyHostToDevice, stream));
+    for (int64_t have = 1; have < M; have *= 2) {
+        const int64_t cnt = std::min(have, M - have);
+        UF_CUDA(cudaMemcpyAsync(surf.p + have * nsurf, surf.p, sizeof(double) * nsurf * cnt, cudaMemcpyDeviceToDevice, stream));
+        UF_CUDA(cudaMemcpyAsync(wake.p + have * 7 * tot, wake.p, sizeof(double) * 7 * tot * cnt, cudaMemcpyDeviceToDevice, stream));
+    }
+    cudaEvent_t e0, e1;
+    UF_CUDA(cudaEventCreate(&e0));
+    UF_CUDA(cudaEventCreate(&e1));
+    UF_CUDA(cudaEventRecord(e0, stream));
+    k_ensemble<<<(unsigned)M, kSolveThreads, 0, stream>>>(devs.p, nsteps);
+    UF_CUDA(cudaGetLastError());
+    UF_CUDA(cudaEventRecord(e1, stream));
+    std::vector<double> hm((size_t)(M * nsteps * 8));
+    UF_CUDA(cudaMemcpyAsync(hm.data(), mat.p, sizeof(double) * hm.size(), cudaMemcpyDeviceToHost, stream));
+    UF_CUDA(cudaMemcpyAsync(hst.data(), st.p, sizeof(StepState) * M, cudaMemcpyDeviceToHost, stream));
+    UF_CUDA(cudaStreamSynchronize(stream));
+    UF_CUDA(cudaEventElapsedTime(&g_batch_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (int64_t m = 0; m < M; m++) {
+        double *mo = mat_out + m * nsteps * 8;
+        const double *mi = &hm[(size_t)(m * nsteps * 8)];
+        for (int64_t i = 0; i < nsteps; i++)
+            for (int j = 0; j < 8; j++) mo[i + j * nsteps] = mi[8 * i + j];
+        if (ntev_out) ntev_out[m] = hst[m].wake.end[0] - hst[m].wake.begin[0];
+        if (nlev_out) nlev_out[m] = hst[m].wake.end[1] - hst[m].wake.begin[1];
+    }
+    return 0;
+}
+
+int unsflow_ldvm_batch_timing(float *ms_kernel) {
+    UF_CHECK(ms_kernel != nullptr, "unsflow_ldvm_batch_timing: null argument");
+    *ms_kernel = g_batch_ms;
+    return 0;
 }
 
 }  // extern "C"

@@ -232,3 +232,30 @@ def lautat(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, w
     """lautat(...), solvers.jl:42-142 (wakerollup=1)"""
     return _run(cabi.DRIVER_LAUTAT, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
                 delvort or delNone(), maxwrite, nround, solve_mode, write_summary=write_summary)
+
+
+def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM, delvort=None, solve_mode=cabi.SOLVE_EXACT):
+    """Batched ensemble of independent LDVM runs (BASELINE config 3): one thread-block per member
+    runs the whole `for istep` loop of solvers.jl:178-257 on the GPU.  All members share the
+    geometry / initial state of `surf` (empty wake); member m follows tables[m] (nsteps x 9, see
+    kinematics_table) with LESP threshold lespcrit[m].
+    Returns (mats [nmember, nsteps, 8], ntev [nmember], nlev [nmember], kernel_ms)."""
+    tables = cabi.f64(tables)
+    nmember, nsteps, ncol = tables.shape
+    if ncol != 9:
+        raise ValueError("tables must be nmember x nsteps x 9")
+    lesp = cabi.f64(np.broadcast_to(np.asarray(lespcrit, dtype=np.float64), (nmember,)))
+    dt = dtstar * surf.c / surf.uref
+    keep = []
+    sst = surf_struct(surf, keep)
+    opts = _opts(driver, dt, nsteps, delvort or delNone(), solve_mode)
+    mats = np.zeros((nmember, 8, nsteps))            # member blocks of column-major nsteps x 8
+    ntev = np.zeros(nmember, dtype=np.int64)
+    nlev = np.zeros(nmember, dtype=np.int64)
+    i64p = C.POINTER(C.c_int64)
+    cabi.check(cabi.lib().unsflow_ldvm_batch_run(C.byref(sst), C.byref(opts), nmember, nsteps, cabi.dptr(tables), cabi.dptr(lesp),
+                                                 mats.ctypes.data_as(cabi.c_double_p), ntev.ctypes.data_as(i64p),
+                                                 nlev.ctypes.data_as(i64p)))
+    ms = C.c_float(0)
+    cabi.check(cabi.lib().unsflow_ldvm_batch_timing(C.byref(ms)))
+    return np.ascontiguousarray(mats.transpose(0, 2, 1)), ntev, nlev, ms.value
