@@ -10,12 +10,15 @@ namespace unsflow {
 InducePlan plan_induce(long long nt_ub, int ntreg, long long ns_ub, int nsreg, int sm_count, int max_S) {
     InducePlan p;
     const long long slots = (long long)sm_count * 2;
-    const long long tsrc = std::max<long long>(1, (ns_ub + kTS - 1) / kTS + nsreg);
+    auto tsrc_of = [&](int ts) { return std::max<long long>(1, (ns_ub + ts - 1) / ts + nsreg); };
     auto tiles = [&](int R) { return (nt_ub + (long long)kThreads * R - 1) / ((long long)kThreads * R) + ntreg; };
     int R = 1;
-    if (tiles(4) * tsrc >= 4 * slots) R = 4;
-    else if (tiles(2) * tsrc >= 4 * slots) R = 2;
+    if (tiles(4) * tsrc_of(kTS) >= 4 * slots) R = 4;
+    else if (tiles(2) * tsrc_of(kTS) >= 4 * slots) R = 2;
     p.R = R;
+    // latency regime: few targets (bound sweep) or a small wake -> 64-source tiles, more CTAs
+    p.ts = (R == 1 && (nt_ub <= kThreads || ns_ub <= 16384)) ? 64 : kTS;
+    const long long tsrc = tsrc_of(p.ts);
     p.ntiles = (int)std::max<long long>(1, tiles(R));
     long long S = (8 * slots + p.ntiles - 1) / p.ntiles;
     S = std::min<long long>(S, tsrc);
@@ -25,25 +28,30 @@ InducePlan plan_induce(long long nt_ub, int ntreg, long long ns_ub, int nsreg, i
     return p;
 }
 
-template <int R, bool U, int O>
+template <int R, bool U, int O, int TS>
 static void launch_one(const InduceArgs &a, const InducePlan &p, cudaStream_t st) {
     dim3 grid(p.ntiles, p.S);
-    k_induce_direct<R, U, O><<<grid, kThreads, 0, st>>>(a);
+    k_induce_direct<R, U, O, TS><<<grid, kThreads, 0, st>>>(a);
+}
+
+template <int R, int TS>
+static void launch_ru(const InduceArgs &a, const InducePlan &p, bool uniform, int order, cudaStream_t st) {
+    if (uniform) { if (order == 2) launch_one<R, true, 2, TS>(a, p, st); else launch_one<R, true, 3, TS>(a, p, st); }
+    else         { if (order == 2) launch_one<R, false, 2, TS>(a, p, st); else launch_one<R, false, 3, TS>(a, p, st); }
 }
 
 int launch_induce_direct(const InduceArgs &a, const InducePlan &p, bool uniform, int order, cudaStream_t st) {
-#define UF_CASE(R_)                                                                   \
-    case R_:                                                                          \
-        if (uniform) { if (order == 2) launch_one<R_, true, 2>(a, p, st); else launch_one<R_, true, 3>(a, p, st); } \
-        else         { if (order == 2) launch_one<R_, false, 2>(a, p, st); else launch_one<R_, false, 3>(a, p, st); } \
-        break;
-    switch (p.R) {
-        UF_CASE(1)
-        UF_CASE(2)
-        UF_CASE(4)
-        default: set_error("launch_induce_direct: unsupported R=%d", p.R); return 1;
+    if (p.ts == 64) {
+        if (p.R != 1) { set_error("launch_induce_direct: 64-source tiles need R=1"); return 1; }
+        launch_ru<1, 64>(a, p, uniform, order, st);
+    } else {
+        switch (p.R) {
+            case 1: launch_ru<1, kTS>(a, p, uniform, order, st); break;
+            case 2: launch_ru<2, kTS>(a, p, uniform, order, st); break;
+            case 4: launch_ru<4, kTS>(a, p, uniform, order, st); break;
+            default: set_error("launch_induce_direct: unsupported R=%d", p.R); return 1;
+        }
     }
-#undef UF_CASE
     UF_CUDA(cudaGetLastError());
     return 0;
 }

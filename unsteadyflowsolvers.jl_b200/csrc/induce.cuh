@@ -66,18 +66,22 @@ __device__ __forceinline__ long long tiles_in(long long b, long long e, long lon
 }
 
 // linear source-tile index -> first absolute element of that tile
+template <int TS>
 __device__ __forceinline__ long long src_tile_start(const Regions &rg, int nreg, long long lin) {
     for (int r = 0; r < nreg; r++) {
-        const long long n = tiles_in(rg.begin[r], rg.end[r], kTS);
-        if (lin < n) return (rg.begin[r] / kTS + lin) * kTS;
+        const long long n = tiles_in(rg.begin[r], rg.end[r], TS);
+        if (lin < n) return (rg.begin[r] / TS + lin) * TS;
         lin -= n;
     }
     return -1;
 }
 
-template <int R, bool UNIFORM, int ORDER>
+// TS = sources per TMA tile: 512 for throughput (large N), 64 for latency (small N and the
+// 70-target bound sweep: many short CTAs, 4 independent source chains per thread)
+template <int R, bool UNIFORM, int ORDER, int TS>
 __global__ void __launch_bounds__(kThreads) k_induce_direct(const InduceArgs a) {
     constexpr int NARR = UNIFORM ? 3 : 4;
+    constexpr int kTS = TS;
     __shared__ __align__(128) double s_buf[2][NARR][kTS];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) k_induce_direct(const InduceArgs a) 
     __syncthreads();
 
     auto issue = [&](long long lin, int stage) {
-        const long long e0 = src_tile_start(sreg, a.nsreg, lin);
+        const long long e0 = src_tile_start<TS>(sreg, a.nsreg, lin);
         constexpr uint32_t bytes = kTS * sizeof(double);
         mbar_expect_tx(&s_bar[stage], NARR * bytes);
         tma_load_1d(&s_buf[stage][0][0], a.sx + e0, bytes, &s_bar[stage]);
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) k_induce_direct(const InduceArgs a) 
         mbar_wait(&s_bar[stage], (k >> 1) & 1);
         const double *sx = s_buf[stage][0], *sz = s_buf[stage][1], *sg = s_buf[stage][2];
         const double *sv = s_buf[stage][NARR - 1];
-#pragma unroll 2
+#pragma unroll(TS >= 512 ? 2 : 4)
         for (int j = 0; j < kTS; j++) {
             const double xj = sx[j], zj = sz[j], gj = sg[j];
             const double vc4 = UNIFORM ? vc4u : sv[j];
@@ -203,6 +207,7 @@ struct InducePlan {
     int R;        // targets per thread
     int S;        // source splits (gridDim.y)
     int ntiles;   // target tiles (gridDim.x)
+    int ts;       // sources per tile: 512 (throughput) or 64 (latency)
 };
 // ntargets_ub / nsrc_ub: host-side upper bounds of live targets / sources; nregions of each
 InducePlan plan_induce(long long ntargets_ub, int ntreg, long long nsrc_ub, int nsreg, int sm_count, int max_S);

@@ -123,10 +123,12 @@ __device__ void step_head(const LdvmDev &d) {
     }
     __syncthreads();
     const double alpha = sh_kin[0], alphadot = sh_kin[2], hdot = sh_kin[3], u = sh_kin[4];
+    double sa, ca;
+    sincos(alpha, &sa, &ca);
     // update_boundpos, calcs.jl:453-459
     for (int i = tid; i < d.ndiv; i += blockDim.x) {
-        d.bnd_x[i] = d.bnd_x[i] + d.dt * ((d.pvt * d.c - d.x[i]) * sin(alpha) * alphadot - u + d.cam[i] * cos(alpha) * alphadot);
-        d.bnd_z[i] = d.bnd_z[i] + d.dt * (hdot + (d.pvt * d.c - d.x[i]) * cos(alpha) * alphadot - d.cam[i] * sin(alpha) * alphadot);
+        d.bnd_x[i] = d.bnd_x[i] + d.dt * ((d.pvt * d.c - d.x[i]) * sa * alphadot - u + d.cam[i] * ca * alphadot);
+        d.bnd_z[i] = d.bnd_z[i] + d.dt * (hdot + (d.pvt * d.c - d.x[i]) * ca * alphadot - d.cam[i] * sa * alphadot);
     }
     __syncthreads();
     if (tid == 0 && d.driver != UNSFLOW_DRIVER_LDVMLIN) {
@@ -150,16 +152,16 @@ __device__ void step_head(const LdvmDev &d) {
 // ---------------------------------------------------------------------------------------------
 // k_step_solve helpers
 // ---------------------------------------------------------------------------------------------
-// simpleTrapz(y .* cos.(n*theta), theta), utils.jl:105-115, left-to-right like the reference
-__device__ __forceinline__ double trapz_cos(const double *y, const double *theta, const double *cosrow, int nd) {
-    double r = 0.0;
-    double prev = y[0] * cosrow[0];
-    for (int i = 1; i < nd; i++) {
-        const double cur = y[i] * cosrow[i];
-        r += (theta[i] - theta[i - 1]) * (cur + prev);
-        prev = cur;
-    }
-    return r / 2.0;
+// simpleTrapz(y .* cos.(n*theta), theta), utils.jl:105-115: one WARP per integral, lanes strided
+// over the panels, butterfly reduction (the reference sums left to right; the reordering moves
+// the result by ~1e-16 relative, far inside the 1e-8 history tolerance).  dth[i] = theta[i]-theta[i-1].
+__device__ __forceinline__ double warp_trapz_cos(const double *y, const double *dth, const double *cosrow, int nd) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i = 1 + lane; i < nd; i += 32) acc += dth[i] * (y[i] * cosrow[i] + y[i - 1] * cosrow[i - 1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc * 0.5;
 }
 
 // unit-strength induced velocity of one vortex at (xv,zv) on bound point i, calcs.jl:469-473
@@ -171,10 +173,10 @@ __device__ __forceinline__ void unit_influence(double xv, double zv, double vc4,
     *w = xdist / den;
 }
 
-// downwash at bound point i, calcs.jl:49-54
-__device__ __forceinline__ double downwash_at(const LdvmDev &d, const double *kin, const double *fs, int ib, double ui, double wi) {
-    const double alpha = kin[0], alphadot = kin[2], hdot = kin[3], u = kin[4];
-    const double sa = sin(alpha), ca = cos(alpha);
+// downwash at bound point i, calcs.jl:49-54 (sa, ca = sin, cos of alpha, evaluated once per thread)
+__device__ __forceinline__ double downwash_at(const LdvmDev &d, const double *kin, const double *fs, int ib, double ui, double wi,
+                                              double sa, double ca) {
+    const double alphadot = kin[2], hdot = kin[3], u = kin[4];
     return -(u + fs[0]) * sa - ui * sa + (hdot - fs[1]) * ca - wi * ca - alphadot * (d.x[ib] - d.pvt * d.c)
            + d.cam_slope[ib] * (ui * ca + (u + fs[0]) * ca + (hdot - fs[1]) * sa - wi * sa);
 }
@@ -208,6 +210,7 @@ __device__ void step_solve(const LdvmDev &d) {
     __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
     __shared__ double uT[kNdMax], wT[kNdMax], uL[kNdMax], wL[kNdMax], gam[kNdMax];
     __shared__ double aterm[kNaMax + 1];   // aterm[0] unused slot for a0-style indexing: aterm[n] = A_n
+    __shared__ double dth[kNdMax];
     __shared__ double sc[32];              // scalar scratch
     __shared__ double kin[6], fs[2];
     __shared__ int lev_shed;
@@ -218,9 +221,13 @@ __device__ void step_solve(const LdvmDev &d) {
     const bool twodof = d.driver == UNSFLOW_DRIVER_LDVM2DOF;
     const double eps_fd = 6.0554544523933395e-06;   // cbrt(eps(Float64))
 
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     if (tid < 6) kin[tid] = s->kin[tid];
     if (tid < 2) fs[tid] = s->fs[tid];
     if (tid == 0) lev_shed = 0;
+    for (int i = tid; i < nd; i += blockDim.x) dth[i] = i > 0 ? d.theta[i] - d.theta[i - 1] : 0.0;
+    double sa, ca;
+    sincos(s->kin[0], &sa, &ca);
     // ---- A: induced velocity at the bound points from the sweep partials (update_indbound) ----
     for (int i = tid; i < nd; i += blockDim.x) {
         if (lautat) {   // lautat never calls update_indbound: uind/wind persist (solvers.jl:76-92)
@@ -251,15 +258,14 @@ __device__ void step_solve(const LdvmDev &d) {
         // ---- B: unit influence of the new TEV; C: affine split of the downwash ----------------
         for (int i = tid; i < nd; i += blockDim.x) {
             unit_influence(xt, zt, d.vc4_new, d.bnd_x[i], d.bnd_z[i], &uT[i], &wT[i]);
-            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
-            const double sa = sin(kin[0]), ca = cos(kin[0]);
+            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);
             dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[i] * (uT[i] * ca - wT[i] * sa);
         }
         __syncthreads();
         // ---- D: A0, A1 as affine functions of the TEV strength --------------------------------
-        if (tid < 4) {
-            const double *y = (tid & 2) ? dw1 : dw;
-            sc[tid] = trapz_cos(y, d.theta, d.costab + (tid & 1) * nd, nd);
+        for (int q = warp; q < 4; q += nwarps) {
+            const double v = warp_trapz_cos((q & 2) ? dw1 : dw, dth, d.costab + (q & 1) * nd, nd);
+            if (lane == 0) sc[q] = v;
         }
         __syncthreads();
         if (tid == 0) {
@@ -281,12 +287,15 @@ __device__ void step_solve(const LdvmDev &d) {
         for (int i = tid; i < nd; i += blockDim.x) {
             uind[i] += gt_applied * uT[i];
             wind[i] += gt_applied * wT[i];
-            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+            dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);
         }
         __syncthreads();
         {
             const int nint = (twodof ? na : 3) + 1;     // update_a2a3adot :2-12 / update_atermdot :14-24
-            for (int n = tid; n < nint; n += blockDim.x) aterm[n] = trapz_cos(dw, d.theta, d.costab + n * nd, nd);
+            for (int n = warp; n < nint; n += nwarps) {
+                const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+                if (lane == 0) aterm[n] = v;
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -311,8 +320,8 @@ __device__ void step_solve(const LdvmDev &d) {
             // ---- G: place_lev (calcs.jl:409-426) + Kelvin-Kutta 2x2 (typedefs.jl:313-348) ------
             if (tid == 0) {
                 const long long lb = s->wake.begin[1], le = s->wake.end[1];
-                const double le_vel_x = kin[4] - kin[2] * sin(kin[0]) * d.pvt * d.c + uind[0];
-                const double le_vel_z = -kin[2] * cos(kin[0]) * d.pvt * d.c - kin[3] + wind[0];
+                const double le_vel_x = kin[4] - kin[2] * sa * d.pvt * d.c + uind[0];
+                const double le_vel_z = -kin[2] * ca * d.pvt * d.c - kin[3] + wind[0];
                 double xl, zl;
                 if (s->levflag == 0 || le == lb) {
                     xl = d.bnd_x[0] + 0.5 * le_vel_x * d.dt;
@@ -334,14 +343,13 @@ __device__ void step_solve(const LdvmDev &d) {
                 unit_influence(xl, zl, d.vc4_new, d.bnd_x[i], d.bnd_z[i], &uL[i], &wL[i]);
                 uind[i] -= gt * uT[i];
                 wind[i] -= gt * wT[i];
-                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
-                const double sa = sin(kin[0]), ca = cos(kin[0]);
-                dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[i] * (uL[i] * ca - wL[i] * sa);
+                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);
+                    dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[i] * (uL[i] * ca - wL[i] * sa);
             }
             __syncthreads();
-            if (tid < 6) {
-                const double *y = tid < 2 ? dw : (tid < 4 ? dw1 : dw2);
-                sc[tid] = trapz_cos(y, d.theta, d.costab + (tid & 1) * nd, nd);
+            for (int q = warp; q < 6; q += nwarps) {
+                const double v = warp_trapz_cos(q < 2 ? dw : (q < 4 ? dw1 : dw2), dth, d.costab + (q & 1) * nd, nd);
+                if (lane == 0) sc[q] = v;
             }
             __syncthreads();
             if (tid == 0) {
@@ -367,13 +375,16 @@ __device__ void step_solve(const LdvmDev &d) {
             for (int i = tid; i < nd; i += blockDim.x) {
                 uind[i] += gta * uT[i] + gla * uL[i];
                 wind[i] += gta * wT[i] + gla * wL[i];
-                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);
+                dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);
             }
             __syncthreads();
         }
         // ---- H: all Fourier coefficients from the final downwash (update_a0anda1 :57-63,
         //         update_a2toan :66-72) --------------------------------------------------------
-        for (int n = tid; n <= na; n += blockDim.x) aterm[n] = trapz_cos(dw, d.theta, d.costab + n * nd, nd);
+        for (int n = warp; n <= na; n += nwarps) {
+            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+            if (lane == 0) aterm[n] = v;
+        }
         __syncthreads();
         if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
         for (int n = tid + 1; n <= na; n += blockDim.x) d.aterm[n - 1] = aterm[n] = 2. * aterm[n] / urefpi;
@@ -382,7 +393,7 @@ __device__ void step_solve(const LdvmDev &d) {
         // =========================== ldvmLin, solvers.jl:505-613 =================================
         double *T1 = dw, *T2 = dw1, *T3 = dw2;
         for (int i = tid; i < nd; i += blockDim.x) {
-            T1[i] = downwash_at(d, kin, fs, i, uind[i], wind[i]);                       // :505-510
+            T1[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);                       // :505-510
             const double xdist = d.bnd_x[i] - xt, zdist = d.bnd_z[i] - zt;             // :525-530
             const double distsq = xdist * xdist + zdist * zdist;
             T2[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
@@ -390,9 +401,10 @@ __device__ void step_solve(const LdvmDev &d) {
         __syncthreads();
         // integrals of T1, T2 against cos(n theta), n = 0..na  -> uL (T1), wL (T2) reused as storage
         double *c1 = uL, *c2 = wL, *c3 = uT;
-        for (int n = tid; n <= na; n += blockDim.x) {
-            c1[n] = trapz_cos(T1, d.theta, d.costab + n * nd, nd);
-            c2[n] = trapz_cos(T2, d.theta, d.costab + n * nd, nd);
+        for (int n = warp; n <= na; n += nwarps) {
+            const double v1 = warp_trapz_cos(T1, dth, d.costab + n * nd, nd);
+            const double v2 = warp_trapz_cos(T2, dth, d.costab + n * nd, nd);
+            if (lane == 0) { c1[n] = v1; c2[n] = v2; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -422,8 +434,8 @@ __device__ void step_solve(const LdvmDev &d) {
         if (lev_shed) {
             if (tid == 0) {
                 const long long lb = s->wake.begin[1], le = s->wake.end[1];
-                const double le_vel_x = kin[4] - kin[2] * sin(kin[0]) * d.pvt * d.c + uind[0];
-                const double le_vel_z = -kin[2] * cos(kin[0]) * d.pvt * d.c - kin[3] + wind[0];
+                const double le_vel_x = kin[4] - kin[2] * sa * d.pvt * d.c + uind[0];
+                const double le_vel_z = -kin[2] * ca * d.pvt * d.c - kin[3] + wind[0];
                 double xl, zl;
                 if (s->levflag == 0 || le == lb) { xl = d.bnd_x[0] + 0.5 * le_vel_x * d.dt; zl = d.bnd_z[0] + 0.5 * le_vel_z * d.dt; }
                 else { xl = d.bnd_x[0] + (1. / 3.) * (d.wx[le - 1] - d.bnd_x[0]); zl = d.bnd_z[0] + (1. / 3.) * (d.wz[le - 1] - d.bnd_z[0]); }
@@ -437,7 +449,10 @@ __device__ void step_solve(const LdvmDev &d) {
                 T3[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
             }
             __syncthreads();
-            for (int n = tid; n <= na; n += blockDim.x) c3[n] = trapz_cos(T3, d.theta, d.costab + n * nd, nd);
+            for (int n = warp; n <= na; n += nwarps) {
+                const double v3 = warp_trapz_cos(T3, dth, d.costab + n * nd, nd);
+                if (lane == 0) c3[n] = v3;
+            }
             __syncthreads();
             if (tid == 0) {
                 const double I1 = sc[0], J1 = sc[1], I2 = sc[2], J2 = sc[3], sig_prev = sc[4];
@@ -493,6 +508,7 @@ __device__ void step_solve(const LdvmDev &d) {
     for (int ib = tid; ib < nd; ib += blockDim.x) {
         double g = (a0 * (1 + d.costab[nd + ib]));
         const double sth = d.sintab[nd + ib];
+#pragma unroll 7
         for (int ia = 1; ia <= na; ia++) g = g + aterm[ia] * d.sintab[ia * nd + ib] * sth;
         gam[ib] = g * d.uref * d.c;
     }
@@ -514,9 +530,8 @@ __device__ void step_solve(const LdvmDev &d) {
             if (s->wake.end[1] - s->wake.begin[1] > d.del_limit) dev_spalart(d, &s->wake.begin[1], s->wake.end[1], lx, lz);
         }
     }
-    if (tid == 32) {
-        const double alpha = kin[0], hdot = kin[3], u = kin[4];
-        const double sa = sin(alpha), ca = cos(alpha);
+    if (warp == 1 % nwarps) {
+        const double hdot = kin[3], u = kin[4];
         const double a1 = aterm[1], a2 = aterm[2];
         const double a0dot = sc[11];
         const double ad1 = d.adot[0], ad2 = d.adot[1], ad3 = d.adot[2];
@@ -525,11 +540,16 @@ __device__ void step_solve(const LdvmDev &d) {
         const double cnnc = 2 * kPi * (3 * d.c * a0dot / (4 * d.uref) + d.c * ad1 / (4 * d.uref) + d.c * ad2 / (8 * d.uref));
         const double cs = 2 * kPi * a0 * a0;
         double nonl = 0, nonl_m = 0;
-        for (int ib = 0; ib < nd - 1; ib++) {
+        for (int ib = lane; ib < nd - 1; ib += 32) {      // postprocess.jl:15-18, lanes strided + butterfly
             const double gb = (gam[ib + 1] + gam[ib]) * (d.theta[1] - d.theta[0]) / 2.;
             const double v = (uind[ib] * ca - wind[ib] * sa);
             nonl = nonl + v * gb;
             nonl_m = nonl_m + v * d.x[ib] * gb;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nonl += __shfl_xor_sync(0xffffffffu, nonl, o);
+            nonl_m += __shfl_xor_sync(0xffffffffu, nonl_m, o);
         }
         nonl = nonl * 2. / (d.uref * d.uref * d.c);
         nonl_m = nonl_m * 2. / (d.uref * d.uref * d.c * d.c);
@@ -540,11 +560,13 @@ __device__ void step_solve(const LdvmDev &d) {
                           - 2 * kPi * (ufac * (a0 / 4. + a1 / 4. - a2 / 8.)
                                        + (d.c / d.uref) * (7. * a0dot / 16. + 3. * ad1 / 16. + ad2 / 16. - ad3 / 64.))
                           - nonl_m;
-        s->cl = cl; s->cd = cd; s->cm = cm;
-        double *m = d.mat + 8 * s->mat_row;
-        m[0] = s->t; m[1] = kin[0]; m[2] = kin[1]; m[3] = kin[4]; m[4] = a0; m[5] = cl; m[6] = cd; m[7] = cm;   // solvers.jl:255
-        s->mat_row += 1;
-        s->step += 1;
+        if (lane == 0) {
+            s->cl = cl; s->cd = cd; s->cm = cm;
+            double *m = d.mat + 8 * s->mat_row;
+            m[0] = s->t; m[1] = kin[0]; m[2] = kin[1]; m[3] = kin[4]; m[4] = a0; m[5] = cl; m[6] = cd; m[7] = cm;   // solvers.jl:255
+            s->mat_row += 1;
+            s->step += 1;
+        }
     }
 }
 
@@ -730,6 +752,10 @@ struct unsflow_ldvm {
     int64_t readback_step = 0;
     int64_t launches = 0;
     float last_ms = 0;
+    // CUDA-graph cache for the launch-bound regime
+    cudaGraphExec_t gexec = nullptr;
+    int64_t gkey_t = -1, gkey_l = -1;
+    const double *gkey_kin = nullptr;
 };
 
 static int ldvm_sync_counts(unsflow_ldvm *h, StepState *out) {
@@ -743,6 +769,7 @@ extern "C" {
 int unsflow_ldvm_destroy(unsflow_ldvm *h) {
     if (!h) return 0;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evc) cudaEventDestroy(h->evc);
@@ -884,6 +911,7 @@ int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *ta
     long long z = 0;
     UF_CUDA(cudaMemcpyAsync(&h->st.p->step, &z, sizeof(z), cudaMemcpyHostToDevice, h->stream));
     UF_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // kernel params are baked into the graph
     h->kin_rows = nrows;
     h->dev.kin = h->kin.p;
     h->dev.kin_rows = nrows;
@@ -905,6 +933,94 @@ int unsflow_ldvm_get_2dof(unsflow_ldvm *h, double *k22) {
     return 0;
 }
 
+// upper bounds of the live end offsets at `ahead` steps from now (known counts + steps since)
+static void step_bounds(const unsflow_ldvm *h, int64_t ahead, int64_t *ntev_ub, int64_t *nlev_ub) {
+    const int64_t since = h->steps_done - h->known_step + ahead;
+    *ntev_ub = std::min(h->cap_t, h->known_ntev_end + since);
+    *nlev_ub = std::min(h->cap_l, h->known_nlev_end + since);
+}
+
+// one time step = 5 launches on the handle's stream (also used under stream capture)
+static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaStream_t st) {
+    const int driver = h->opts.driver, smc = sm_count(), order = rsqrt_order();
+    const int64_t tot = h->tot, nwake_ub = ntev_ub + nlev_ub + h->nextv;
+    k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+    h->launches++;
+    if (driver != UNSFLOW_DRIVER_LAUTAT) {
+        // bound-point sweep (update_indbound, calcs.jl:35-38): targets = bound points
+        InducePlan p2 = plan_induce(h->ndiv, 1, nwake_ub, 3, smc, h->S2max);
+        InduceArgs a;
+        a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
+        a.tx = h->dev.bnd_x; a.tz = h->dev.bnd_z;
+        a.sreg = &h->st.p->wake; a.treg = &h->st.p->bnd; a.nsreg = 3; a.ntreg = 1;
+        a.vc4_uniform = h->vc4u;
+        a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
+        if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
+        h->dev.S2 = p2.S;
+        h->launches++;
+    }
+    k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+    h->launches++;
+    // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
+    const bool sym = h->uniform && nwake_ub >= sym_threshold();
+    InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + h->ndiv - 1, 4, smc, h->S1max);
+    InduceArgs a;
+    a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
+    a.tx = h->dev.wx; a.tz = h->dev.wz;
+    a.sreg = &h->st.p->wake; a.treg = &h->st.p->wake; a.nsreg = 4; a.ntreg = 3;
+    a.vc4_uniform = h->vc4u;
+    a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
+    if (sym) {
+        if (!h->planes.p && h->planes.alloc((int64_t)sym_ctas_max() * 2 * tot)) return 2;
+        const int symR = sym_rows_per_thread(nwake_ub);
+        h->ctas = sym_ctas(symR);
+        // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
+        const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
+        const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
+        for (int r = 0; r < 3; r++) {
+            const int64_t b = lo[r], e = std::min(round_up(hi[r], kSymTB), tot);
+            if (e > b)
+                UF_CUDA(cudaMemset2DAsync(h->planes.p + b, sizeof(double) * tot, 0, sizeof(double) * (e - b), (size_t)h->ctas * 2, st));
+        }
+        SymArgs sa;
+        sa.x = h->dev.wx; sa.z = h->dev.wz; sa.g = h->dev.wg;
+        sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
+        sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
+        if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
+    } else {
+        if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+    }
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
+    if (sym) { f.pu = h->planes.p; f.pw = h->planes.p + tot; f.tstride = 2 * tot; f.S = h->ctas; }
+    f.treg = &h->st.p->wake; f.ntreg = 3;
+    f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
+    f.fs = h->st.p->fs; f.dt = h->opts.dt;
+    if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
+    h->launches += 2;
+    return 0;
+}
+
+static void poll_readback(unsflow_ldvm *h) {
+    if (h->readback_pending && cudaEventQuery(h->evc) == cudaSuccess) {
+        h->readback_pending = false;
+        h->known_step = h->readback_step;
+        h->known_ntev_end = h->pinned->wake.end[0] - h->off_t;
+        h->known_nlev_end = h->pinned->wake.end[1] - h->off_l;
+    }
+}
+
+// Launch-bound regime (small wakes): replay a CUDA graph of kGraphChunk steps whose grids are
+// sized for a quantised upper bound at the END of the chunk; the graph is re-captured only when
+// that quantised bound (the key) changes.
+constexpr int64_t kGraphChunk = 32;
+constexpr int64_t kGraphQuant = 512;
+static bool graphs_enabled() {
+    static bool v = [] { const char *e = getenv("UNSFLOW_NO_GRAPH"); return !(e && atoi(e) != 0); }();
+    return v;
+}
+
 int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
     UF_CHECK(h != nullptr, "unsflow_ldvm_run: null handle");
     UF_CHECK(nsteps >= 0, "unsflow_ldvm_run: negative nsteps");
@@ -914,88 +1030,46 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
     UF_CHECK(h->dev.kin != nullptr, "unsflow_ldvm_run: call unsflow_ldvm_set_kinematics first");
     if (nsteps == 0) return 0;
     cudaStream_t st = h->stream;
-    const int driver = h->opts.driver;
-    const int smc = sm_count();
-    const int order = rsqrt_order();
     // mat rows of this call start at row 0 of the device buffer
     long long z = 0;
     UF_CUDA(cudaMemcpyAsync(&h->st.p->mat_row, &z, sizeof(z), cudaMemcpyHostToDevice, st));
     h->launches = 0;
     UF_CUDA(cudaEventRecord(h->ev0, st));
-    const int64_t tot = h->tot;
-    for (int64_t is = 0; is < nsteps; is++) {
-        // ---- poll the asynchronous count read-back (never blocks) ------------------------------
-        if (h->readback_pending && cudaEventQuery(h->evc) == cudaSuccess) {
-            h->readback_pending = false;
-            h->known_step = h->readback_step;
-            h->known_ntev_end = h->pinned->wake.end[0] - h->off_t;
-            h->known_nlev_end = h->pinned->wake.end[1] - h->off_l;
-        }
-        const int64_t since = h->steps_done - h->known_step + 1;
-        const int64_t ntev_ub = std::min(h->cap_t, h->known_ntev_end + since);
-        const int64_t nlev_ub = std::min(h->cap_l, h->known_nlev_end + since);
-        const int64_t nwake_ub = ntev_ub + nlev_ub + h->nextv;
-
-        k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
-        h->launches++;
-        if (driver != UNSFLOW_DRIVER_LAUTAT) {
-            // bound-point sweep (update_indbound, calcs.jl:35-38): targets = bound points
-            InducePlan p2 = plan_induce(h->ndiv, 1, nwake_ub, 3, smc, h->S2max);
-            InduceArgs a;
-            a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
-            a.tx = h->dev.bnd_x; a.tz = h->dev.bnd_z;
-            a.sreg = &h->st.p->wake; a.treg = &h->st.p->bnd; a.nsreg = 3; a.ntreg = 1;
-            a.vc4_uniform = h->vc4u;
-            a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
-            if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
-            h->dev.S2 = p2.S;
-            h->launches++;
-        }
-        k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
-        h->launches++;
-        {
-            // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
-            const bool sym = h->uniform && nwake_ub >= sym_threshold();
-            InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + h->ndiv - 1, 4, smc, h->S1max);
-            InduceArgs a;
-            a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
-            a.tx = h->dev.wx; a.tz = h->dev.wz;
-            a.sreg = &h->st.p->wake; a.treg = &h->st.p->wake; a.nsreg = 4; a.ntreg = 3;
-            a.vc4_uniform = h->vc4u;
-            a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
-            if (sym) {
-                if (!h->planes.p && h->planes.alloc((int64_t)sym_ctas_max() * 2 * tot)) return 2;
-                const int symR = sym_rows_per_thread(nwake_ub);
-                h->ctas = sym_ctas(symR);
-                // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
-                const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
-                const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
-                for (int r = 0; r < 3; r++) {
-                    const int64_t b = lo[r], e = std::min(round_up(hi[r], kSymTB), tot);
-                    if (e > b)
-                        UF_CUDA(cudaMemset2DAsync(h->planes.p + b, sizeof(double) * tot, 0, sizeof(double) * (e - b), (size_t)h->ctas * 2, st));
-                }
-                SymArgs sa;
-                sa.x = h->dev.wx; sa.z = h->dev.wz; sa.g = h->dev.wg;
-                sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
-                sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
-                if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
-            } else {
-                if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+    int64_t is = 0;
+    while (is < nsteps) {
+        poll_readback(h);
+        int64_t tev_ub, lev_ub;
+        step_bounds(h, kGraphChunk, &tev_ub, &lev_ub);
+        const bool small = tev_ub + lev_ub + h->nextv < 16384;
+        if (graphs_enabled() && small && nsteps - is >= kGraphChunk) {
+            const int64_t qt = std::min(h->cap_t, round_up(tev_ub, kGraphQuant)), ql = std::min(h->cap_l, round_up(lev_ub, kGraphQuant));
+            if (!h->gexec || h->gkey_t != qt || h->gkey_l != ql || h->gkey_kin != h->dev.kin) {
+                if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+                cudaGraph_t g = nullptr;
+                const int64_t l0 = h->launches;
+                UF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int64_t k = 0; k < kGraphChunk && rc == 0; k++) rc = enqueue_step(h, qt, ql, st);
+                cudaError_t ce = cudaStreamEndCapture(st, &g);
+                h->launches = l0;
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                UF_CUDA(ce);
+                UF_CUDA(cudaGraphInstantiate(&h->gexec, g, 0));
+                cudaGraphDestroy(g);
+                h->gkey_t = qt; h->gkey_l = ql; h->gkey_kin = h->dev.kin;
             }
-            FinishArgs f;
-            memset(&f, 0, sizeof(f));
-            f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
-            if (sym) { f.pu = h->planes.p; f.pw = h->planes.p + tot; f.tstride = 2 * tot; f.S = h->ctas; }
-            f.treg = &h->st.p->wake; f.ntreg = 3;
-            f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
-            f.fs = h->st.p->fs; f.dt = h->opts.dt;
-            if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
-            h->launches += 2;
+            UF_CUDA(cudaGraphLaunch(h->gexec, st));
+            h->launches += kGraphChunk * (h->opts.driver == UNSFLOW_DRIVER_LAUTAT ? 4 : 5);
+            h->steps_done += kGraphChunk;
+            is += kGraphChunk;
+        } else {
+            step_bounds(h, 1, &tev_ub, &lev_ub);
+            if (int rc = enqueue_step(h, tev_ub, lev_ub, st)) return rc;
+            UF_CUDA(cudaGetLastError());
+            h->steps_done++;
+            is++;
         }
-        UF_CUDA(cudaGetLastError());
-        h->steps_done++;
-        if (!h->readback_pending && (h->steps_done % 64) == 0) {
+        if (!h->readback_pending && h->steps_done - h->readback_step >= 64) {
             UF_CUDA(cudaMemcpyAsync(h->pinned, h->st.p, sizeof(StepState), cudaMemcpyDeviceToHost, st));
             UF_CUDA(cudaEventRecord(h->evc, st));
             h->readback_pending = true;
@@ -1003,6 +1077,8 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         }
     }
     UF_CUDA(cudaEventRecord(h->ev1, st));
+    const int64_t tot = h->tot;
+    (void)tot;
     // mat: device row-major [nsteps][8] -> caller column-major nsteps x 8
     std::vector<double> hm((size_t)(8 * nsteps));
     UF_CUDA(cudaMemcpyAsync(hm.data(), h->mat.p, sizeof(double) * 8 * nsteps, cudaMemcpyDeviceToHost, st));
