@@ -40,6 +40,16 @@ def env_int(k, d):
     return int(os.environ.get(k, d))
 
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner,
+# torchrun notices) are redirected to stderr for the life of the process.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 class ClockSampler(threading.Thread):
     """samples nvidia-smi clocks / throttle reasons DURING the timed region"""
 
@@ -120,7 +130,7 @@ def run_reference(args, rank, world):
                        "note": "bounded target sample per step; CPU oracle port"},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -133,6 +143,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 symmetric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ldvm-steps", type=int, default=20, help="extra: LDVM steps/s on a 1e5 wake (0 = skip)")
+    ap.add_argument("--ensemble-members", type=int, default=4096, help="extra: config C3 ensemble (0 = skip)")
+    ap.add_argument("--ensemble-steps", type=int, default=500)
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
@@ -260,6 +272,33 @@ def main():
                   "tolerance": 1e-12, "against": "oracle long-double sum"}
     cabi.check(L.unsflow_wake_destroy(h))
 
+    # ---- extra: config C3, 4096 independent LDVM members x 500 steps, members sharded over
+    # ranks (no communication); aggregate member-steps/s from the slowest rank's kernel time ----
+    ens = None
+    if args.ensemble_members > 0:
+        try:
+            import math
+            nk = nl = int(round(math.sqrt(args.ensemble_members)))
+            ens_steps = args.ensemble_steps
+            tabs, lesp, base = [], [], None
+            for k in np.linspace(0.05, 1.0, nk):
+                kin = uf.KinemDef(uf.SinDef(0.0, 20.0 * math.pi / 180, float(k), 0.0), uf.ConstDef(0.0), uf.ConstDef(1.0))
+                sf = uf.TwoDSurf("FlatPlate", 0.25, kin, [0.1])
+                base = base or sf
+                tb = uf.kinematics_table(sf, uf.TwoDFlowField(), ens_steps, 0.015)
+                for lc in np.linspace(0.05, 0.35, nl):
+                    tabs.append(tb); lesp.append(float(lc))
+            mine = slice(rank, None, world)
+            mats, ntev, nlev, ems = uf.ldvm_batch(base, np.array(tabs[mine]), np.array(lesp[mine]), 0.015)
+            tm = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ens = {"members": nk * nl, "steps": ens_steps, "kernel_ms_max_over_ranks": tm.item(),
+                   "member_steps_per_s": nk * nl * ens_steps / (tm.item() * 1e-3), "finite": bool(np.all(np.isfinite(mats))),
+                   "workload": "C3: 64 reduced frequencies x 64 LESPcrit, SinDef pitch 20 deg, one CTA per member"}
+        except Exception as e:
+            ens = {"error": str(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -311,10 +350,11 @@ def main():
                      "algorithmic": f"{FLOP_PER_INTERACTION:.0f} flop/interaction x {inter_step / world:.4e} interactions per launch per GPU"},
     }
     line["verify"] = verify
+    line["ensemble_C3"] = ens
     line.update(extra)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_port(O)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

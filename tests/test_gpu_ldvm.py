@@ -219,3 +219,22 @@ def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):
         assert np.max(np.abs(mats[m] - omat)) <= HTOL, m
         assert nlev[m] == len(sim.get_vorts(1)["x"])
     assert nlev.max() > 10 and nlev.min() == 0
+
+
+def test_write_stamps_from_device_snapshots(gpu_lib, uf, tmp_path, monkeypatch):
+    """writeflag = 1: the write schedule of solvers.jl:164-175 and the `Step Files/<t>/...`
+    layout of postprocess.jl:34-113, produced from device snapshots"""
+    monkeypatch.chdir(tmp_path)
+    surf, fld, _, dtstar = c1r_surf(uf)
+    mat, surf, fld = uf.ldvm(surf, fld, 120, dtstar, 0, 1, 0.6, uf.delNone(), maxwrite=5)
+    dirs = sorted(os.listdir("Step Files"), key=float)
+    assert dirs == ["0.6", "1.2", "1.8"]
+    for name in ("timeKinem", "FourierCoeffs", "tev", "lev", "boundv", "delcp_edgevel"):
+        assert os.path.exists(os.path.join("Step Files", "1.2", name))
+    tev = np.loadtxt(os.path.join("Step Files", "1.2", "tev"))
+    assert tev.shape == (80, 3)                       # 80 steps at t = 1.2
+    four = np.loadtxt(os.path.join("Step Files", "1.8", "FourierCoeffs"))
+    assert four.shape == (36, 2) and abs(four[0, 0] - mat[119, 4]) < 1e-15
+    dc = np.loadtxt(os.path.join("Step Files", "1.8", "delcp_edgevel"))
+    assert dc.shape == (70, 6) and np.all(np.isfinite(dc))
+    assert os.path.exists("resultsSummary")

@@ -43,3 +43,22 @@ def test_find_tstep(uf):
     assert uf.find_tstep(uf.ConstDef(1.0)) == 0.015
     assert abs(uf.find_tstep(uf.EldUpDef(0.5, 0.4, 0.8)) - 0.0075) < 1e-15
     assert abs(uf.find_tstep(uf.SinDef(0, 0.5, 0.8, 0)) - 0.015 * 0.2 / 0.4) < 1e-15
+
+
+def test_writestamp_layout_cpu(uf, tmp_path, monkeypatch):
+    """postprocess.jl:34-113 file layout from a host-side state (no GPU involved)"""
+    import os
+    monkeypatch.chdir(tmp_path)
+    surf, fld, _, _ = c1_surf(uf)
+    surf.a0[0], surf.a0dot[0] = 0.05, 0.01
+    surf.aterm[:] = 0.01 / (1 + np.arange(35))
+    fld.tev.append(uf.TwoDVort(0.1, 0.0, -0.02, 0.02))
+    uf.writeStamp("0.015", 0.015, surf, fld)
+    d = os.path.join("Step Files", "0.015")
+    assert sorted(os.listdir(d)) == ["FourierCoeffs", "boundv", "delcp_edgevel", "lev", "tev", "timeKinem"]
+    assert np.loadtxt(os.path.join(d, "boundv")).shape == (69, 3)
+    assert np.loadtxt(os.path.join(d, "tev")).reshape(-1, 3).shape == (1, 3)
+    dc = np.loadtxt(os.path.join(d, "delcp_edgevel"))
+    assert dc.shape == (70, 6) and np.all(np.isfinite(dc))
+    qu, ql = uf.calc_edgeVel(surf, [0.0, 0.0])
+    assert abs(qu[0] - 0.05 / math.sqrt(0.5 * 0.016)) < 1e-14          # postprocess.jl:230

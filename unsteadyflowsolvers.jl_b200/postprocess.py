@@ -1,0 +1,104 @@
+"""Host-side mirror of the snapshot writers (src/lowOrder2D/postprocess.jl:34-244).
+
+Runs on the HOST from a state downloaded with unsflow_ldvm_get_state at the scheduled write
+steps (solvers.jl:164-175, :247-252); in the Julia drop-in the reference's own `writeStamp` is
+called instead (julia/UnsflowCUDA.jl).  Output-only code, not on the GPU path; the on-disk
+layout `Step Files/<t>/{timeKinem,FourierCoeffs,tev,lev,boundv,delcp_edgevel}` is what
+`makeVortPlots2D` and the UI read (plots2D.jl:32-175).
+"""
+import math
+import os
+import shutil
+
+import numpy as np
+
+
+def _writedlm(f, mat):
+    mat = np.atleast_2d(np.asarray(mat, dtype=np.float64))
+    for row in mat:
+        f.write("\t".join(repr(float(v)) for v in row) + "\n")
+
+
+def calc_delcp(surf, vels):
+    """calc_delcp, postprocess.jl:184-222 -> (p_com, p_in, p_out)"""
+    nd = surf.ndiv
+    k = surf.kinem
+    a0, a0dot = float(surf.a0[0]), float(surf.a0dot[0])
+    p_in, p_out, gam, gamint, p_com, gammod = (np.zeros(nd) for _ in range(6))
+    ca, sa = math.cos(k.alpha), math.sin(k.alpha)
+    for i in range(nd):
+        udash = k.u * ca + k.hdot * sa + surf.uind[i] * ca - surf.wind[i] * sa
+        p_in[i] = (8 * surf.uref * math.sqrt(surf.c) * a0 * math.sqrt(surf.x[i]) * udash / (surf.rho * surf.c + 2 * surf.x[i])
+                   + 4 * surf.uref * math.sqrt(surf.c) * a0dot * math.sqrt(surf.x[i]))
+    for i in range(1, nd):
+        th = surf.theta[i]
+        udash = k.u * ca + k.hdot * sa + surf.uind[i] * ca - surf.wind[i] * sa
+        gam[i] = a0 / math.tan(th / 2)
+        gamint[i] = a0dot * (th + math.sin(th))
+        for n in range(1, surf.naterm + 1):
+            gam[i] += surf.aterm[n - 1] * math.sin(n * th)
+            gammod[i] += surf.aterm[n - 1] * math.sin(n * th)
+            if n == 1:
+                gamint[i] += surf.adot[0] * (th / 2 - math.sin(2 * th) / 4)
+            else:
+                gamint[i] += surf.adot[n - 1] / 2 * (math.sin((n - 1) * th) / (n - 1) - math.sin((n + 1) * th) / (n + 1))
+        gam[i] *= surf.uref
+        gammod[i] *= surf.uref
+        gamint[i] *= surf.uref * surf.c
+        p_out[i] = 2 * udash * gam[i] + gamint[i]
+        p_com[i] = (2 * udash * surf.uref * a0 * (math.cos(th / 2) - 1) / math.sin(th / 2) + 2 * udash * gammod[i] + gamint[i]
+                    + 8 * surf.uref * udash * surf.c * a0 * math.sin(th / 2) / (surf.rho * surf.c + 2 * surf.c * (math.sin(th / 2)) ** 2))
+    return p_com, p_in, p_out
+
+
+def calc_edgeVel(surf, vels):
+    """calc_edgeVel, postprocess.jl:224-244 -> (q_com_u, q_com_l)"""
+    nd = surf.ndiv
+    k = surf.kinem
+    a0 = float(surf.a0[0])
+    gammod, qu, ql = (np.zeros(nd) for _ in range(3))
+    qu[0] = surf.uref * a0 / math.sqrt(0.5 * surf.rho)
+    ql[0] = surf.uref * a0 / math.sqrt(0.5 * surf.rho)
+    ca, sa = math.cos(k.alpha), math.sin(k.alpha)
+    for i in range(1, nd):
+        th = surf.theta[i]
+        udash = (k.u + vels[0]) * ca + (k.hdot - vels[1]) * sa + surf.uind[i] * ca - surf.wind[i] * sa
+        for n in range(1, surf.naterm + 1):
+            gammod[i] += surf.aterm[n - 1] * math.sin(n * th)
+        gammod[i] *= surf.uref
+        t1 = surf.uref * a0 * (math.cos(th / 2) - 1) / math.sin(th / 2)
+        den = math.sqrt(surf.x[i] + surf.rho * surf.c / 2)
+        qu[i] = t1 + surf.uref * gammod[i] + (math.sqrt(surf.c) * surf.uref * a0 + math.sqrt(surf.x[i]) * udash) / den
+        ql[i] = -t1 - surf.uref * gammod[i] + (-math.sqrt(surf.c) * surf.uref * a0 + math.sqrt(surf.x[i]) * udash) / den
+    return qu, ql
+
+
+def writeStamp(dirname, t, surf, curfield):
+    """writeStamp(dirname, t, surf::TwoDSurf, curfield), postprocess.jl:34-113"""
+    root = "Step Files"
+    os.makedirs(root, exist_ok=True)
+    d = os.path.join(root, dirname)
+    if os.path.isdir(d):
+        shutil.rmtree(d)
+    os.mkdir(d)
+    k = surf.kinem
+    with open(os.path.join(d, "timeKinem"), "w") as f:
+        f.write("#time \talpha (deg) \th/c \tu/uref \t\n")
+        _writedlm(f, [[t, k.alpha, k.h, k.u]])
+    with open(os.path.join(d, "FourierCoeffs"), "w") as f:
+        f.write("#Fourier coeffs (0-n) \td/dt (Fourier coeffs) \n")
+        m = np.zeros((surf.naterm + 1, 2))
+        m[:, 0] = np.concatenate([[surf.a0[0]], surf.aterm])
+        m[:, 1] = np.concatenate([[surf.a0dot[0]], surf.adot])
+        _writedlm(f, m)
+    for name, v in (("tev", curfield.tev), ("lev", curfield.lev), ("boundv", surf.bv)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write("#strength \tx-position \tz-position  \n")
+            if len(v):
+                _writedlm(f, np.stack([v.s, v.x, v.z], axis=1))
+    with open(os.path.join(d, "delcp_edgevel"), "w") as f:
+        f.write("#x \tdelcp \tdelcp_inner \tdelcp_outer \tqu \tql  \n")
+        vels = [float(curfield.u[0]), float(curfield.w[0])]
+        delcp, delcp_in, delcp_out = calc_delcp(surf, vels)
+        qu, ql = calc_edgeVel(surf, vels)
+        _writedlm(f, np.stack([surf.x, delcp, delcp_in, delcp_out, qu, ql], axis=1))

@@ -152,6 +152,11 @@ def _opts(driver, dt, nsteps, delvort, solve_mode):
     return o
 
 
+def _round_sig(t, nround):
+    """directory name "$(round(t, sigdigits=nround))" of solvers.jl:249"""
+    return repr(float(f"{t:.{nround}g}"))
+
+
 def _write_results_summary(mat):
     """solvers.jl:261-264"""
     with open("resultsSummary", "w") as f:
@@ -190,8 +195,7 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
             if stop in write_steps:
                 h.download()
                 from .postprocess import writeStamp
-                writeStamp(f"{float(np.format_float_positional(table[stop - 1, 0], precision=nround, unique=False, fractional=False, trim='k')):g}",
-                           table[stop - 1, 0], surf, curfield)
+                writeStamp(_round_sig(table[stop - 1, 0], nround), table[stop - 1, 0], surf, curfield)
         h.download()
         if two_dof:
             h.get_2dof(kinem)
