@@ -33,6 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 13.0
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_induce_sym<8,3> launch at N = 1e6 from the
+# `ncu --set full` capture summarised in profiles/r01_sym_R8_N1e6_ncu_full.txt (4.42 + 3.90 GB: the
+# per-CTA partial planes' read-modify-write; 0.2 % of DRAM bandwidth -- the kernel is FP64-bound)
+NCU_TRAFFIC_SYM8_N1E6 = 8.3155e9
 NBV = 69                        # ndiv - 1 bound vortices (typedefs.jl:68)
 
 
@@ -343,7 +347,8 @@ def main():
                 "how": "unsflow_wake_upload (host arrays) + unsflow_wake_step + unsflow_wake_download per step"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": ach_per_gpu, "peak": tf.value, "unit": "TFLOP/s",
-                     "frac": ach_per_gpu / tf.value, "traffic": None,
+                     "frac": ach_per_gpu / tf.value,
+                     "traffic": NCU_TRAFFIC_SYM8_N1E6 if (world == 1 and n == 1_000_000 and args.variant == 0) else None,
                      "kernel": "k_induce_* (all-pairs Vatistas induction)",
                      "peak_source": f"measured in this run: DFMA-chain microbenchmark (unsflow_fp64_peak), ~{mhz.value:.0f} MHz "
                                     "equivalent; MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
