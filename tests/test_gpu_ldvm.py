@@ -238,3 +238,41 @@ def test_write_stamps_from_device_snapshots(gpu_lib, uf, tmp_path, monkeypatch):
     dc = np.loadtxt(os.path.join("Step Files", "1.8", "delcp_edgevel"))
     assert dc.shape == (70, 6) and np.all(np.isfinite(dc))
     assert os.path.exists("resultsSummary")
+
+
+def test_cambered_nondefault_discretisation(gpu_lib, uf, oracle):
+    """non-default ndiv/naterm, chord and reference speed, and a cambered surface (cam,
+    cam_slope != 0 exercise the extra terms of update_downwash calcs.jl:51 and update_boundpos
+    :455-456); pitching + plunging with a non-zero external velocity field"""
+    kin = uf.KinemDef(uf.SinDef(4 * math.pi / 180, 12 * math.pi / 180, 0.5, 0.3), uf.CosDef(0.0, 0.15, 0.5, 0.0), uf.ConstDef(1.0))
+    surf = uf.TwoDSurf("FlatPlate", 0.3, kin, [0.14], c=2.0, uref=1.5, ndiv=48, naterm=24, initpos=(0.2, -0.1))
+    xc = surf.x / surf.c
+    surf.cam[:] = 0.04 * surf.c * 4 * xc * (1 - xc)              # parabolic camber line
+    surf.cam_slope[:] = 0.04 * 4 * (1 - 2 * xc)
+    k = surf.kinem                                              # rebuild bound points with camber (typedefs.jl:156-159)
+    surf.bnd_x[:] = -((surf.c - surf.pvt * surf.c) + ((surf.pvt * surf.c - surf.x) * math.cos(k.alpha))) + surf.cam * math.sin(k.alpha) + 0.2
+    surf.bnd_z[:] = k.h + ((surf.pvt * surf.c - surf.x) * math.sin(k.alpha)) + surf.cam * math.cos(k.alpha) - 0.1
+    fld = uf.TwoDFlowField(uf.SinDef(0.0, 0.05, 0.8, 0.0), uf.CosDef(0.0, 0.03, 0.8, 0.0))
+    n, dtstar = 110, 0.012
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    assert len(fld.lev) > 3
+    assert np.max(np.abs(mat - omat)) <= HTOL
+    _cmp_state(surf, fld, sim, tol=1e-7)
+    assert abs(fld.u[0] - 0.05 * math.sin(2 * 0.8 * mat[-1, 0])) < 1e-14
+
+
+def test_external_vortices_nonuniform_core(gpu_lib, uf, oracle):
+    """curfield.extv with its own core radii: the EXTV slab and the general (per-source vc^4)
+    kernel variant inside the stepper; extv convect with the flow but never shed or merge"""
+    surf, fld, _, dtstar = c1r_surf(uf, lespcrit=0.15)
+    rng = np.random.default_rng(11)
+    ne = 37
+    fld.extv = uf.VortList.from_arrays(0.5 + 2.0 * rng.random(ne), 0.4 * (rng.random(ne) - 0.5), 0.05 * (rng.random(ne) - 0.5),
+                                       0.02 * (0.5 + rng.random(ne)))
+    n = 100
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    assert len(fld.extv) == ne and len(fld.tev) == n
+    assert np.max(np.abs(mat - omat)) <= HTOL
+    _cmp_state(surf, fld, sim, tol=1e-7)
