@@ -67,7 +67,7 @@ def test_partition_covers_work_exactly_once_world2():
 
 
 def _ntiles(n):
-    tb = 2048 if n >= 400000 else 1024      # pair-tile width rule of the library (induce.cu)
+    tb = 2048 if n >= 150000 else 1024      # pair-tile width rule of the library (induce.cu)
     nb = (n + tb - 1) // tb
     return nb * (nb + 1) // 2
 

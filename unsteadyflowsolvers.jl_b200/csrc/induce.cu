@@ -68,10 +68,10 @@ size_t sym_smem_bytes(int R) { return sizeof(double) * (size_t)(2 * 3 + 2) * kTh
 
 int sym_rows_per_thread(long long n) {
     // env UNSFLOW_SYM_R in {1,2,4,8} forces a tile size (experiments); default: 2048-wide tiles
-    // (R = 8, 1 CTA/SM) once there are enough tiles per CTA, else 1024-wide (R = 4, 2 CTAs/SM)
+    // (R = 8, 1 CTA/SM) once there are >= ~18 tiles per CTA (N >= 150k), else 1024-wide (R = 4, 2 CTAs/SM)
     static int forced = [] { const char *e = getenv("UNSFLOW_SYM_R"); int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0; }();
     if (forced) return forced;
-    return n >= 400000 ? 8 : 4;
+    return n >= 150000 ? 8 : 4;
 }
 
 template <int R, int O>

@@ -235,7 +235,15 @@ __device__ void step_solve(const LdvmDev &d) {
             wind[i] = d.wind[i];
         } else {
             double su = 0.0, sw = 0.0;
-            for (int k = 0; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + i]; sw += d.p2w[(long long)k * d.p2stride + i]; }
+            int k = 0;
+            for (; k + 8 <= d.S2; k += 8) {
+                double bu[8], bw[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { bu[q] = d.p2u[(long long)(k + q) * d.p2stride + i]; bw[q] = d.p2w[(long long)(k + q) * d.p2stride + i]; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) { su += bu[q]; sw += bw[q]; }
+            }
+            for (; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + i]; sw += d.p2w[(long long)k * d.p2stride + i]; }
             uind[i] = su * kInvTwoPi;
             wind[i] = sw * kInvTwoPi;
         }
@@ -290,12 +298,12 @@ __device__ void step_solve(const LdvmDev &d) {
             dw[i] = downwash_at(d, kin, fs, i, uind[i], wind[i], sa, ca);
         }
         __syncthreads();
-        {
-            const int nint = (twodof ? na : 3) + 1;     // update_a2a3adot :2-12 / update_atermdot :14-24
-            for (int n = warp; n < nint; n += nwarps) {
-                const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-                if (lane == 0) aterm[n] = v;
-            }
+        // all A_n integrals of this downwash at once: A0..A3 feed update_a2a3adot (:2-12) /
+        // update_atermdot (:14-24); when no LEV is shed they are also the final coefficients
+        // (update_a2toan :66-72 recomputes the same numbers), so phase H is skipped then
+        for (int n = warp; n <= na; n += nwarps) {
+            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+            if (lane == 0) aterm[n] = v;
         }
         __syncthreads();
         if (tid == 0) {
@@ -380,12 +388,14 @@ __device__ void step_solve(const LdvmDev &d) {
             __syncthreads();
         }
         // ---- H: all Fourier coefficients from the final downwash (update_a0anda1 :57-63,
-        //         update_a2toan :66-72) --------------------------------------------------------
-        for (int n = warp; n <= na; n += nwarps) {
-            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-            if (lane == 0) aterm[n] = v;
+        //         update_a2toan :66-72); only the LEV branch changed the downwash since phase F ---
+        if (lev_shed) {
+            for (int n = warp; n <= na; n += nwarps) {
+                const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+                if (lane == 0) aterm[n] = v;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
         for (int n = tid + 1; n <= na; n += blockDim.x) d.aterm[n - 1] = aterm[n] = 2. * aterm[n] / urefpi;
         __syncthreads();
