@@ -175,6 +175,15 @@ int unsflow_ldvm_counts(unsflow_ldvm *h, int64_t *ntev, int64_t *nlev, int64_t *
 /* Download the full state into caller-owned arrays (pointers may be NULL to skip);
  * surf->bv.n / field->*.n must hold the array capacities and are set to the counts. */
 int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *surf, unsflow_field *field);
+/* Multi-surface ldvm(surf::Vector{TwoDSurf}, curfield, ...)  solvers.jl:270-445 (driver must be
+ * UNSFLOW_DRIVER_LDVM; 1 <= nsurf <= 4; all surfaces share ndiv, naterm and the theta grid).
+ * `surfs` is an array of nsurf unsflow_surf.  The kinematics table of
+ * unsflow_ldvm_set_kinematics then has nrows x nsurf x 9 entries (row-major; t, U_ext, W_ext are
+ * read from surface 0's row) and unsflow_ldvm_run returns nsteps x (1 + 7 nsurf) columns
+ * [t, (alpha, h, u, a0, cl, cd, cm) per surface] (solvers.jl:427-432), column-major. */
+int unsflow_ldvm_multi_create(unsflow_ldvm **out, int32_t nsurf, const unsflow_surf *surfs,
+                              const unsflow_field *field, const unsflow_opts *opts);
+int unsflow_ldvm_multi_get_state(unsflow_ldvm *h, int32_t nsurf, unsflow_surf *surfs, unsflow_field *field);
 /* CUDA-event milliseconds of the last unsflow_ldvm_run and number of kernel launches in it */
 int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches);
 int unsflow_ldvm_destroy(unsflow_ldvm *h);

@@ -237,4 +237,66 @@ lautat(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Flo
        writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
     run_driver(3, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround, solve_mode = solve_mode)
 
+# ---- multi-surface ldvm(surf::Vector{TwoDSurf}, ...)  replaces solvers.jl:270-445 -------------------
+function csurf(surf::TwoDSurf, bv::SoA)
+    k = surf.kinem
+    CSurf(surf.ndiv, surf.naterm, surf.c, surf.uref, surf.pvt, surf.lespcrit[1], surf.levflag[1], 0,
+        (k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot), surf.a0[1], surf.a0dot[1], surf.a0prev[1],
+        pointer(surf.theta), pointer(surf.x), pointer(surf.cam), pointer(surf.cam_slope), pointer(surf.bnd_x), pointer(surf.bnd_z),
+        pointer(surf.uind), pointer(surf.wind), pointer(surf.downwash), pointer(surf.aterm), pointer(surf.adot), pointer(surf.aprev),
+        cvorts(bv))
+end
+
+function ldvm(surf::Vector{TwoDSurf}, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0,
+              writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0)
+    startflag == 0 || throw("invalid start flag, should be 0 or 1")
+    nsurf = length(surf)
+    dt = dtstar * minimum(map(q -> q.c / q.uref, surf))                     # solvers.jl:289
+    # table: 9 x nsurf x nsteps column-major == nsteps x nsurf x 9 row-major for C
+    tab = zeros(9, nsurf, nsteps)
+    for (is, sf) in enumerate(surf)
+        tab[:, is, :] = kinematics_table(sf, curfield, nsteps, dt, 0.0)
+    end
+    tev = SoA(curfield.tev); lev = SoA(curfield.lev); extv = SoA(curfield.extv); bvs = [SoA(sf.bv) for sf in surf]
+    kind, lim, dist, tol = typeof(delvort) == delSpalart ? (1, delvort.limit, delvort.dist, delvort.tol) : (0, 0, 0.0, 0.0)
+    opts = Ref(COpts(0, solve_mode, kind, -1, lim, dist, tol, dt, nsteps))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mat = Matrix{Float64}(undef, nsteps, 1 + 7 * nsurf)
+    GC.@preserve surf tev lev extv bvs tab mat begin
+        cs = [csurf(surf[i], bvs[i]) for i = 1:nsurf]
+        cf = Ref(CField(curfield.u[1], curfield.w[1], cvorts(tev), cvorts(lev), cvorts(extv)))
+        check(ccall((:unsflow_ldvm_multi_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Int32, Ptr{CSurf}, Ptr{CField}, Ptr{COpts}), h, nsurf, cs, cf, opts))
+        try
+            check(ccall((:unsflow_ldvm_set_kinematics, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], nsteps, tab))
+            check(ccall((:unsflow_ldvm_run, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], nsteps, mat))
+            nt = Ref{Int64}(0); nl = Ref{Int64}(0); ne = Ref{Int64}(0)
+            check(ccall((:unsflow_ldvm_counts, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), h[], nt, nl, ne))
+            tev = SoA(nt[]); lev = SoA(nl[]); extv = SoA(ne[])
+            cs = [csurf(surf[i], bvs[i]) for i = 1:nsurf]
+            cf = Ref(CField(0.0, 0.0, cvorts(tev), cvorts(lev), cvorts(extv)))
+            GC.@preserve tev lev extv begin
+                check(ccall((:unsflow_ldvm_multi_get_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{CSurf}, Ptr{CField}), h[], nsurf, cs, cf))
+            end
+            for i = 1:nsurf
+                sf = surf[i]; c = cs[i]; k = sf.kinem
+                sf.levflag[1] = c.levflag
+                k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = c.kinem
+                sf.a0[1] = c.a0; sf.a0dot[1] = c.a0dot; sf.a0prev[1] = c.a0prev
+                for j = 1:sf.ndiv-1
+                    sf.bv[j].s = bvs[i].s[j]; sf.bv[j].x = bvs[i].x[j]; sf.bv[j].z = bvs[i].z[j]
+                end
+            end
+            curfield.u[1] = cf[].u; curfield.w[1] = cf[].w
+            unpack!(curfield.tev, tev, nt[]); unpack!(curfield.lev, lev, nl[]); unpack!(curfield.extv, extv, ne[])
+        finally
+            ccall((:unsflow_ldvm_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
+        end
+    end
+    f = open("resultsSummary", "w")                                         # solvers.jl:438-441
+    println(f, "#time \t", "alpha(deg) \t", "h/c \t", "u/uref \t", "A0 \t", "Cl \t", "Cd \t", "Cm ")
+    DelimitedFiles.writedlm(f, mat)
+    close(f)
+    mat, surf, curfield
+end
+
 end # module

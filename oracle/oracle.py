@@ -241,3 +241,59 @@ class Sim:
 import sys as _sys
 _sys.path.insert(0, os.path.dirname(_HERE))
 from synth import s_wake, splitmix_uniform  # noqa: E402,F401
+
+
+class MultiSim:
+    """Oracle state of the multi-surface ldvm(surf::Vector{TwoDSurf}), solvers.jl:270-445."""
+
+    def __init__(self, surfs, curfield=None):
+        self.ns, self.nd, self.na = len(surfs), surfs[0].ndiv, surfs[0].naterm
+        assert all(s.ndiv == self.nd and s.naterm == self.na for s in surfs)
+        L = lib()
+        L.o_msim_create.restype = C.c_void_p
+        L.o_msim_count.restype = C.c_long
+        L.o_msim_nfev.restype = C.c_long
+        self.h = C.c_void_p(L.o_msim_create(C.c_int(self.ns), C.c_int(self.nd), C.c_int(self.na)))
+        for i, s in enumerate(surfs):
+            p = pack_surf(s)
+            L.o_msim_set_surf(self.h, C.c_int(i), _p(p))
+        if curfield is not None:
+            for fam, v in enumerate((curfield.tev, curfield.lev, curfield.extv)):
+                n = len(v)
+                a = _f(np.stack([v.x, v.z, v.s, v.vc, v.vx, v.vz])) if n else np.zeros((6, 1))
+                L.o_msim_set_vorts(self.h, C.c_int(fam), C.c_long(n), _p(a))
+            L.o_msim_set_field_uw(self.h, C.c_double(float(curfield.u[0])), C.c_double(float(curfield.w[0])))
+
+    def close(self):
+        if self.h:
+            lib().o_msim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, tables, dt, solver_mode=0, delvort=(0, 0, 0.0, 0.0)):
+        """tables: nsteps x nsurf x 9"""
+        tables = _f(tables)
+        n = tables.shape[0]
+        mat = np.zeros((n, 1 + 7 * self.ns))
+        rc = lib().o_msim_run(self.h, C.c_long(n), C.c_double(dt), _p(tables), C.c_int(solver_mode), C.c_int(delvort[0]),
+                              C.c_long(int(delvort[1])), C.c_double(delvort[2]), C.c_double(delvort[3]), _p(mat))
+        assert rc == 0
+        return mat
+
+    def get_surf(self, i):
+        n = lib().o_surf_pack_len(C.c_int(self.nd), C.c_int(self.na))
+        p = np.zeros(n)
+        lib().o_msim_get_surf(self.h, C.c_int(i), _p(p))
+        return unpack_surf(p, self.nd, self.na)
+
+    def get_vorts(self, fam):
+        n = lib().o_msim_count(self.h, C.c_int(fam))
+        v = np.zeros((6, max(n, 1)))
+        lib().o_msim_get_vorts(self.h, C.c_int(fam), _p(v))
+        v = v.reshape(-1)[: 6 * n].reshape(6, n) if n else np.zeros((6, 0))
+        return dict(zip(("x", "z", "s", "vc", "vx", "vz"), v))

@@ -571,23 +571,37 @@ static void kelvinkutta_functor(o_sim *m, const double v_iter[2], double val[2])
  *      x - eps*e_last, and the reference drivers then use that stale surf state after only
  *      overwriting the strengths with soln.zero (solvers.jl:200,217).
  * ---------------------------------------------------------------------------------------- */
-typedef void (*o_fun)(o_sim *, const double *, double *);
+#define O_NMAX 8
+typedef void (*o_fun)(void *, const double *, double *);
 
-static void fun1(o_sim *m, const double *x, double *r) { r[0] = kelvin_functor(m, x[0]); }
-static void fun2(o_sim *m, const double *x, double *r) { kelvinkutta_functor(m, x, r); }
+static void fun1(void *m, const double *x, double *r) { r[0] = kelvin_functor((o_sim *)m, x[0]); }
+static void fun2(void *m, const double *x, double *r) { kelvinkutta_functor((o_sim *)m, x, r); }
 
 static void solve_lin(int n, const double *J /*row-major*/, const double *rhs, double *p) {
-    if (n == 1) { p[0] = rhs[0] / J[0]; return; }
-    double det = J[0] * J[3] - J[1] * J[2];
-    p[0] = (rhs[0] * J[3] - J[1] * rhs[1]) / det;
-    p[1] = (J[0] * rhs[1] - rhs[0] * J[2]) / det;
+    /* Gaussian elimination with partial pivoting, n <= O_NMAX */
+    double A[O_NMAX][O_NMAX + 1];
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i][j] = J[i * n + j]; A[i][n] = rhs[i]; }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+        if (piv != c) for (int j = 0; j <= n; j++) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+        for (int r = c + 1; r < n; r++) {
+            const double f = A[r][c] / A[c][c];
+            for (int j = c; j <= n; j++) A[r][j] -= f * A[c][j];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double v = A[i][n];
+        for (int j = i + 1; j < n; j++) v -= A[i][j] * p[j];
+        p[i] = v / A[i][i];
+    }
 }
 
-static void solve_exact(o_sim *m, o_fun fn, int n, double *x) {
+static void solve_exact(void *m, o_fun fn, int n, double *x) {
     /* probe step 1e-3: small enough not to trip the sign switch of the LESP condition
      * (typedefs.jl:340), large enough that the difference quotient of an affine function is
      * exact to ~1e-13; the loop then polishes the root to rounding. */
-    double r0[2], r1[2], J[4], p[2], xt[2];
+    double r0[O_NMAX], r1[O_NMAX], J[O_NMAX * O_NMAX], p[O_NMAX], xt[O_NMAX];
     for (int it = 0; it < 12; it++) {
         fn(m, x, r0);
         for (int j = 0; j < n; j++) {
@@ -597,7 +611,8 @@ static void solve_exact(o_sim *m, o_fun fn, int n, double *x) {
             fn(m, xt, r1);
             for (int i = 0; i < n; i++) J[i * n + j] = (r1[i] - r0[i]) / hstep;
         }
-        double rhs[2] = { -r0[0], -r0[1] };
+        double rhs[O_NMAX];
+        for (int i = 0; i < n; i++) rhs[i] = -r0[i];
         solve_lin(n, J, rhs, p);
         double chg = 0;
         for (int k = 0; k < n; k++) { chg += fabs(p[k]) / (fabs(x[k]) + 1e-300); x[k] += p[k]; }
@@ -606,10 +621,10 @@ static void solve_exact(o_sim *m, o_fun fn, int n, double *x) {
     fn(m, x, r0);   /* leave the functor's side effects at the root */
 }
 
-static void fd_jacobian(o_sim *m, o_fun fn, int n, const double *x, double *J) {
+static void fd_jacobian(void *m, o_fun fn, int n, const double *x, double *J) {
     /* FiniteDiff central differences: column j uses x+eps*e_j first, then x-eps*e_j */
     const double cbrt_eps = cbrt(2.220446049250313e-16);
-    double xt[2], fp[2], fm[2];
+    double xt[O_NMAX], fp[O_NMAX], fm[O_NMAX];
     for (int j = 0; j < n; j++) {
         double e = cbrt_eps * fmax(1.0, fabs(x[j]));
         for (int k = 0; k < n; k++) xt[k] = x[k];
@@ -627,32 +642,33 @@ static double wnorm(int n, const double *d, const double *v) {
 
 /* Powell dogleg step inside NLsolve's trust_region (scaled by d) */
 static void dogleg(int n, const double *r, const double *d, const double *J, double delta, double *p) {
-    double pi_[2], rhs[2] = { -r[0], -r[1] };
+    double pi_[O_NMAX], rhs[O_NMAX];
+    for (int i = 0; i < n; i++) rhs[i] = -r[i];
     solve_lin(n, J, rhs, pi_);                      /* Gauss-Newton step */
     if (wnorm(n, d, pi_) <= delta) { for (int i = 0; i < n; i++) p[i] = pi_[i]; return; }
-    double g[2] = { 0, 0 };                         /* g = J' r  scaled by 1/d^2 */
+    double g[O_NMAX] = { 0 };                       /* g = J' r  scaled by 1/d^2 */
     for (int j = 0; j < n; j++) {
         for (int i = 0; i < n; i++) g[j] += J[i * n + j] * r[i];
         g[j] /= d[j] * d[j];
     }
-    double Jg[2] = { 0, 0 };
+    double Jg[O_NMAX] = { 0 };
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Jg[i] += J[i * n + j] * g[j];
     double gn = wnorm(n, d, g);
     double Jgn2 = 0; for (int i = 0; i < n; i++) Jgn2 += Jg[i] * Jg[i];
-    double pc[2];
+    double pc[O_NMAX];
     for (int i = 0; i < n; i++) pc[i] = -(gn * gn / Jgn2) * g[i];   /* Cauchy point */
     double pcn = wnorm(n, d, pc);
     if (pcn >= delta) { for (int i = 0; i < n; i++) p[i] = pc[i] * (delta / pcn); return; }
-    double df[2]; for (int i = 0; i < n; i++) df[i] = pi_[i] - pc[i];
+    double df[O_NMAX]; for (int i = 0; i < n; i++) df[i] = pi_[i] - pc[i];
     double b = 0; for (int i = 0; i < n; i++) b += 2 * pc[i] * df[i] * d[i] * d[i];
     double a = wnorm(n, d, df); a = a * a;
     double tau = (-b + sqrt(b * b - 4 * a * (pcn * pcn - delta * delta))) / (2 * a);
     for (int i = 0; i < n; i++) p[i] = pc[i] + tau * df[i];
 }
 
-static void o_nlsolve_tr(o_sim *m, o_fun fn, int n, double *x) {
+static void o_nlsolve_tr(void *m, o_fun fn, int n, double *x) {
     const double ftol = 1e-8, eta = 1e-4;
-    double r[2], rn[2], J[4], d[2], p[2], rp[2];
+    double r[O_NMAX], rn[O_NMAX], J[O_NMAX * O_NMAX], d[O_NMAX], p[O_NMAX], rp[O_NMAX];
     fn(m, x, r);                       /* value_jacobian!!: value first, then FD probes */
     fd_jacobian(m, fn, n, x, J);
     double fmaxv = 0; for (int i = 0; i < n; i++) fmaxv = fmax(fmaxv, fabs(r[i]));
@@ -693,7 +709,7 @@ static void o_nlsolve_tr(o_sim *m, o_fun fn, int n, double *x) {
     }
 }
 
-static void root_solve(o_sim *m, int mode, o_fun fn, int n, double *x) {
+static void root_solve(void *m, int mode, o_fun fn, int n, double *x) {
     if (mode == 1) o_nlsolve_tr(m, fn, n, x);
     else solve_exact(m, fn, n, x);
 }
@@ -1034,4 +1050,291 @@ void o_kinem_eval(int kind, const double *p, double t, double *val, double *der)
         case 6: *val = (t >= p[1] && t <= p[1] + p[2]) ? p[0] : 0.; *der = 0; break;
         default: *val = 0; *der = 0;
     }
+}
+
+/* ==========================================================================================
+ * Multi-surface LDVM: ldvm(surf::Vector{TwoDSurf}, ...), src/lowOrder2D/solvers.jl:270-445
+ * (SURVEY 8f rank 3).  Restated literally, including the way the Mult functors only ever feed
+ * a surface's OWN newly shed vortices back into its induced velocities (typedefs.jl:279-287).
+ * ======================================================================================== */
+typedef struct {
+    int nsurf;
+    o_surf *s;
+    o_field f;
+    double t;
+    long nfev;
+    int shed[O_NMAX];   /* shed_ind (0-based surface indices) */
+    int nshed;
+} o_msim;
+
+/* place_tev(surf::Vector{TwoDSurf}, field, dt), calcs.jl:389-406 */
+static void place_tev_multi(o_msim *m, double dt) {
+    const int ns = m->nsurf;
+    const long ntev = m->f.tev.n;
+    for (int i = 0; i < ns; i++) {
+        o_surf *s = &m->s[i];
+        const int nd = s->ndiv;
+        double xloc, zloc;
+        if (ntev < ns) {
+            xloc = s->bnd_x[nd - 1] + 0.5 * s->u * dt;
+            zloc = s->bnd_z[nd - 1];
+        } else {
+            const o_vort *q = &m->f.tev.v[ntev - ns + i];
+            xloc = s->bnd_x[nd - 1] + (1. / 3.) * (q->x - s->bnd_x[nd - 1]);
+            zloc = s->bnd_z[nd - 1] + (1. / 3.) * (q->z - s->bnd_z[nd - 1]);
+        }
+        o_vort v = { xloc, zloc, 0., 0.02 * s->c, 0., 0. };
+        vec_push(&m->f.tev, v);
+    }
+}
+
+static int in_shed(const o_msim *m, int i) {
+    for (int k = 0; k < m->nshed; k++) if (m->shed[k] == i) return 1;
+    return 0;
+}
+
+/* place_lev(surf::Vector{TwoDSurf}, field, dt, shed_ind), calcs.jl:428-450 */
+static void place_lev_multi(o_msim *m, double dt) {
+    const int ns = m->nsurf;
+    const long nlev = m->f.lev.n;
+    for (int i = 0; i < ns; i++) {
+        o_surf *s = &m->s[i];
+        if (in_shed(m, i)) {
+            double xloc, zloc;
+            if (s->levflag == 0) {
+                double le_vel_x = s->u - s->alphadot * sin(s->alpha) * s->pvt * s->c + s->uind[0];
+                double le_vel_z = -s->alphadot * cos(s->alpha) * s->pvt * s->c - s->hdot + s->wind[0];
+                xloc = s->bnd_x[0] + 0.5 * le_vel_x * dt;
+                zloc = s->bnd_z[0] + 0.5 * le_vel_z * dt;
+            } else {
+                const o_vort *q = &m->f.lev.v[nlev - ns + i];
+                xloc = s->bnd_x[0] + (1. / 3.) * (q->x - s->bnd_x[0]);
+                zloc = s->bnd_z[0] + (1. / 3.) * (q->z - s->bnd_z[0]);
+            }
+            o_vort v = { xloc, zloc, 0., 0.02 * s->c, 0., 0. };
+            vec_push(&m->f.lev, v);
+        } else {
+            o_vort v = { 0., 0., 0., 0., 0., 0. };      /* placeholder, calcs.jl:446 */
+            vec_push(&m->f.lev, v);
+        }
+    }
+}
+
+/* [tev_list; (lev_list;) bv_list] of the Mult functors for surface i, typedefs.jl:270-279, :364-375 */
+static long mult_sources(const o_msim *m, int i, int with_lev, o_vort *out) {
+    const int ns = m->nsurf;
+    long k = 0;
+    for (int j = 0; j < ns; j++) out[k++] = m->f.tev.v[m->f.tev.n - ns + j];
+    if (with_lev)
+        for (int q = 0; q < m->nshed; q++) out[k++] = m->f.lev.v[m->f.lev.n - ns + m->shed[q]];
+    for (int j = 0; j < ns; j++)
+        if (j != i)
+            for (int b = 0; b < m->s[j].ndiv - 1; b++) out[k++] = m->s[j].bv[b];
+    return k;
+}
+
+static double kelvin_val(const o_surf *s) {
+    return s->uref * s->c * O_PI * (s->a0 + s->aterm[0] / 2.) - s->uref * s->c * O_PI * (s->a0prev + s->aprev[0] / 2.);
+}
+
+/* shared body of KelvinConditionMult (typedefs.jl:261-305) and KelvinKuttaMult (:356-420) */
+static void mult_functor(o_msim *m, const double *v_iter, double *val, int with_lev) {
+    const int ns = m->nsurf;
+    long cap = 2 * ns;
+    for (int j = 0; j < ns; j++) cap += m->s[j].ndiv;
+    o_vort *src = (o_vort *)malloc((size_t)cap * sizeof(o_vort));
+    int levcount = 0;
+    for (int i = 0; i < ns; i++) {
+        o_surf *s = &m->s[i];
+        const int nd = s->ndiv;
+        double uprev[nd], wprev[nd], unow[nd], wnow[nd];
+        long n = mult_sources(m, i, with_lev, src);
+        ind_vel_aos(src, n, s->bnd_x, s->bnd_z, nd, uprev, wprev);
+        m->f.tev.v[m->f.tev.n - ns + i].s = v_iter[i];
+        if (with_lev && in_shed(m, i)) {
+            levcount += 1;
+            m->f.lev.v[m->f.lev.n - ns + i].s = v_iter[ns + levcount - 1];
+        }
+        n = mult_sources(m, i, with_lev, src);
+        ind_vel_aos(src, n, s->bnd_x, s->bnd_z, nd, unow, wnow);
+        for (int b = 0; b < nd; b++) {
+            s->uind[b] = s->uind[b] - uprev[b] + unow[b];
+            s->wind[b] = s->wind[b] - wprev[b] + wnow[b];
+        }
+        update_downwash(s, m->f.u, m->f.w);
+    }
+    levcount = 0;
+    for (int i = 0; i < ns; i++) {
+        o_surf *s = &m->s[i];
+        update_a0anda1(s);
+        update_a2toan(s);
+        update_bv(s);
+        const double tevs = m->f.tev.v[m->f.tev.n - ns + i].s;
+        if (with_lev && in_shed(m, i)) {
+            val[i] = kelvin_val(s) + tevs + m->f.lev.v[m->f.lev.n - ns + i].s;
+            levcount += 1;
+            const double lesp_cond = (s->a0 > 0) ? s->lespcrit : -s->lespcrit;
+            val[levcount - 1 + ns] = s->a0 - lesp_cond;
+        } else {
+            val[i] = kelvin_val(s) + tevs;
+        }
+    }
+    m->nfev++;
+    free(src);
+}
+static void mfun1(void *m, const double *x, double *r) { mult_functor((o_msim *)m, x, r, 0); }
+static void mfun2(void *m, const double *x, double *r) { mult_functor((o_msim *)m, x, r, 1); }
+
+/* wakeroll(surf::Vector{TwoDSurf}, curfield, dt), calcs.jl:296-372 */
+static void wakeroll_multi(o_msim *m, double dt) {
+    o_field *f = &m->f;
+    long ntev = f->tev.n, nlev = f->lev.n, nextv = f->extv.n, n = ntev + nlev + nextv;
+    o_vort *all = (o_vort *)malloc((size_t)(n > 0 ? n : 1) * sizeof(o_vort));
+    memcpy(all, f->tev.v, (size_t)ntev * sizeof(o_vort));
+    memcpy(all + ntev, f->lev.v, (size_t)nlev * sizeof(o_vort));
+    memcpy(all + ntev + nlev, f->extv.v, (size_t)nextv * sizeof(o_vort));
+    for (long i = 0; i < n; i++) { all[i].vx = 0; all[i].vz = 0; }
+    mutual_ind_aos(all, n);
+    double *tx = (double *)malloc((size_t)(n > 0 ? n : 1) * 6 * sizeof(double));
+    double *tz = tx + n, *ut = tz + n, *wt = ut + n, *us = wt + n, *ws = us + n;
+    for (long i = 0; i < n; i++) { tx[i] = all[i].x; tz[i] = all[i].z; us[i] = 0; ws[i] = 0; }
+    for (int is = 0; is < m->nsurf; is++) {                              /* :325-329 */
+        ind_vel_aos(m->s[is].bv, m->s[is].ndiv - 1, tx, tz, n, ut, wt);
+        for (long i = 0; i < n; i++) { us[i] += ut[i]; ws[i] += wt[i]; }
+    }
+    for (long i = 0; i < n; i++) { all[i].vx += us[i]; all[i].vz += ws[i]; }
+    for (long i = 0; i < n; i++) { all[i].vx += f->u; all[i].vz += f->w; }
+    for (long i = 0; i < n; i++) { all[i].x += dt * all[i].vx; all[i].z += dt * all[i].vz; }
+    memcpy(f->tev.v, all, (size_t)ntev * sizeof(o_vort));
+    memcpy(f->lev.v, all + ntev, (size_t)nlev * sizeof(o_vort));
+    memcpy(f->extv.v, all + ntev + nlev, (size_t)nextv * sizeof(o_vort));
+    free(tx);
+    free(all);
+}
+
+/* one step of ldvm(surf::Vector{TwoDSurf}), solvers.jl:311-434.
+ * kin: nsurf rows of 9 [t, alpha, h, alphadot, hdot, u, udot, U, W]; matrow: 1 + 7*nsurf */
+static void step_ldvm_multi(o_msim *m, double dt, const double *kin, int mode,
+                            int dkind, long dlimit, double ddist, double dtol, double *matrow) {
+    const int ns = m->nsurf;
+    o_field *f = &m->f;
+    m->t = kin[0]; f->u = kin[7]; f->w = kin[8];                         /* :313-316 */
+    for (int is = 0; is < ns; is++) {                                    /* :318-324 */
+        o_surf *s = &m->s[is];
+        const double *r = kin + 9 * is;
+        s->alpha = r[1]; s->h = r[2]; s->alphadot = r[3]; s->hdot = r[4]; s->u = r[5]; s->udot = r[6];
+        update_boundpos(s, dt);
+    }
+    place_tev_multi(m, dt);                                              /* :327 */
+    for (int is = 0; is < ns; is++) {                                    /* :329-338 */
+        o_surf *s = &m->s[is];
+        update_indbound(s, f);
+        for (int js = 0; js < ns; js++) {
+            if (is == js) continue;
+            const int nd = s->ndiv;
+            double u[nd], w[nd];
+            ind_vel_aos(m->s[js].bv, m->s[js].ndiv - 1, s->bnd_x, s->bnd_z, nd, u, w);   /* add_indbound_b, calcs.jl:40-46 */
+            for (int b = 0; b < nd; b++) { s->uind[b] += u[b]; s->wind[b] += w[b]; }
+        }
+    }
+    double x[O_NMAX];
+    for (int i = 0; i < ns; i++) x[i] = -0.01;                           /* :343 */
+    root_solve(m, mode, mfun1, ns, x);
+    m->nshed = 0;
+    for (int i = 0; i < ns; i++) {                                       /* :345-362 */
+        f->tev.v[f->tev.n - ns + i].s = x[i];
+        update_a2a3adot(&m->s[i], dt);
+        if (fabs(m->s[i].a0) > m->s[i].lespcrit) m->shed[m->nshed++] = i;
+    }
+    if (m->nshed > 0) {                                                  /* :365-390 */
+        place_lev_multi(m, dt);
+        for (int i = 0; i < ns + m->nshed; i++) x[i] = -0.01;            /* :372 */
+        root_solve(m, mode, mfun2, ns + m->nshed, x);
+        /* strengths: the functor has already stored the iterate in the vortices; the driver's
+         * own assignment block (:374-390) re-stores soln.zero for the index patterns it handles */
+        int lc = 0;
+        for (int i = 0; i < ns; i++) {
+            f->tev.v[f->tev.n - ns + i].s = x[i];
+            if (in_shed(m, i)) { f->lev.v[f->lev.n - ns + i].s = x[ns + lc]; lc++; m->s[i].levflag = 1; }
+            else m->s[i].levflag = 0;
+        }
+    } else {
+        for (int i = 0; i < ns; i++) m->s[i].levflag = 0;                /* :392-394 */
+    }
+    for (int i = 0; i < ns; i++) {                                       /* :397-403 */
+        o_surf *s = &m->s[i];
+        s->a0prev = s->a0;
+        for (int ia = 0; ia < 3; ia++) s->aprev[ia] = s->aterm[ia];
+    }
+    double mx = 0, mz = 0;                                               /* :406-408 */
+    for (int i = 0; i < ns; i++) {
+        const int mid = (int)nearbyint(m->s[i].ndiv / 2.0) - 1;
+        mx += m->s[i].bnd_x[mid]; mz += m->s[i].bnd_z[mid];
+    }
+    control_vort_count(dkind, dlimit, ddist, dtol, mx / ns, mz / ns, f);
+    wakeroll_multi(m, dt);                                               /* :411 */
+    matrow[0] = m->t;
+    for (int i = 0; i < ns; i++) {                                       /* :414-432 */
+        double cl, cd, cm, cn;
+        calc_forces(&m->s[i], f->u, f->w, &cl, &cd, &cm, &cn);
+        double *r = matrow + 1 + 7 * i;
+        r[0] = m->s[i].alpha; r[1] = m->s[i].h; r[2] = m->s[i].u; r[3] = m->s[i].a0; r[4] = cl; r[5] = cd; r[6] = cm;
+    }
+}
+
+void *o_msim_create(int nsurf, int ndiv, int naterm) {
+    o_msim *m = (o_msim *)calloc(1, sizeof(o_msim));
+    m->nsurf = nsurf;
+    m->s = (o_surf *)calloc((size_t)nsurf, sizeof(o_surf));
+    for (int i = 0; i < nsurf; i++) {
+        o_sim *tmp = (o_sim *)o_sim_create(ndiv, naterm);
+        m->s[i] = tmp->s;
+        free(tmp);
+    }
+    return m;
+}
+void o_msim_destroy(void *h) {
+    o_msim *m = (o_msim *)h;
+    for (int i = 0; i < m->nsurf; i++) {
+        o_surf *s = &m->s[i];
+        free(s->theta); free(s->x); free(s->cam); free(s->cam_slope); free(s->bnd_x); free(s->bnd_z);
+        free(s->uind); free(s->wind); free(s->downwash); free(s->aterm); free(s->adot); free(s->aprev); free(s->bv);
+    }
+    free(m->s); free(m->f.tev.v); free(m->f.lev.v); free(m->f.extv.v); free(m);
+}
+/* reuse the single-surface pack/unpack through a temporary o_sim view of surface i */
+void o_msim_set_surf(void *h, int i, const double *p) {
+    o_msim *m = (o_msim *)h; o_sim v; memset(&v, 0, sizeof(v)); v.s = m->s[i];
+    o_sim_set_surf(&v, p); m->s[i] = v.s;
+}
+void o_msim_get_surf(void *h, int i, double *p) {
+    o_msim *m = (o_msim *)h; o_sim v; memset(&v, 0, sizeof(v)); v.s = m->s[i];
+    o_sim_get_surf(&v, p);
+}
+static o_vec *mfamily(o_msim *m, int fam) { return fam == 0 ? &m->f.tev : fam == 1 ? &m->f.lev : &m->f.extv; }
+void o_msim_set_vorts(void *h, int fam, long n, const double *v) {
+    o_vec *a = mfamily((o_msim *)h, fam);
+    a->n = 0;
+    for (long i = 0; i < n; i++) { o_vort q = { v[i], v[n + i], v[2 * n + i], v[3 * n + i], v[4 * n + i], v[5 * n + i] }; vec_push(a, q); }
+}
+long o_msim_count(void *h, int fam) { return mfamily((o_msim *)h, fam)->n; }
+void o_msim_get_vorts(void *h, int fam, double *v) {
+    o_vec *a = mfamily((o_msim *)h, fam);
+    long n = a->n;
+    for (long i = 0; i < n; i++) {
+        v[i] = a->v[i].x; v[n + i] = a->v[i].z; v[2 * n + i] = a->v[i].s;
+        v[3 * n + i] = a->v[i].vc; v[4 * n + i] = a->v[i].vx; v[5 * n + i] = a->v[i].vz;
+    }
+}
+void o_msim_set_field_uw(void *h, double u, double w) { ((o_msim *)h)->f.u = u; ((o_msim *)h)->f.w = w; }
+long o_msim_nfev(void *h) { return ((o_msim *)h)->nfev; }
+/* kin: nsteps x nsurf x 9 row-major; mat: nsteps x (1 + 7 nsurf) row-major */
+int o_msim_run(void *h, long nsteps, double dt, const double *kin, int solver_mode,
+               int dkind, long dlimit, double ddist, double dtol, double *mat) {
+    o_msim *m = (o_msim *)h;
+    const int ns = m->nsurf, nc = 1 + 7 * ns;
+    if (ns > O_NMAX / 2) return 1;
+    for (long is = 0; is < nsteps; is++)
+        step_ldvm_multi(m, dt, kin + (size_t)is * ns * 9, solver_mode, dkind, dlimit, ddist, dtol, mat + (size_t)is * nc);
+    return 0;
 }

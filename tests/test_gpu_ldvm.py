@@ -276,3 +276,43 @@ def test_external_vortices_nonuniform_core(gpu_lib, uf, oracle):
     assert len(fld.extv) == ne and len(fld.tev) == n
     assert np.max(np.abs(mat - omat)) <= HTOL
     _cmp_state(surf, fld, sim, tol=1e-7)
+
+
+def _tandem(uf, lesps=(0.12, 0.2)):
+    def mk(x0, phase, lesp):
+        kin = uf.KinemDef(uf.SinDef(5 * math.pi / 180, 15 * math.pi / 180, 0.6, phase), uf.ConstDef(0.0), uf.ConstDef(1.0))
+        return uf.TwoDSurf("FlatPlate", 0.25, kin, [lesp], initpos=(x0, 0.0))
+    return [mk(0.0, 0.0, lesps[0]), mk(1.5, 1.0, lesps[1])]
+
+
+def test_multi_surface_tandem_ldvm(gpu_lib, uf, oracle):
+    """ldvm(surf::Vector{TwoDSurf}) solvers.jl:270-445: two flat plates in tandem, LEV shedding
+    on one or both (placeholder LEVs, calcs.jl:446), against the multi-surface oracle"""
+    surfs, fld = _tandem(uf), uf.TwoDFlowField()
+    n, dtstar = 100, 0.012
+    tabs = np.stack([uf.kinematics_table(s, fld, n, dtstar) for s in surfs], axis=1)
+    sim = oracle.MultiSim(surfs, fld)
+    omat = sim.run(tabs, dtstar)
+    mat, surfs, fld = uf.ldvm(surfs, fld, n, dtstar, write_summary=False)
+    assert mat.shape == (n, 15)
+    assert np.max(np.abs(mat - omat)) <= HTOL
+    olev = sim.get_vorts(1)
+    assert len(fld.tev) == 2 * n and len(fld.lev) == len(olev["x"]) and len(fld.lev) > 20
+    assert np.sum(fld.lev.vc == 0) == np.sum(olev["vc"] == 0) > 0          # placeholders
+    for fam, v in enumerate((fld.tev, fld.lev)):
+        o = sim.get_vorts(fam)
+        for k in ("x", "z", "s"):
+            assert np.max(np.abs(getattr(v, k) - o[k])) <= 1e-7, (fam, k)
+    for q, surf in enumerate(surfs):
+        so = sim.get_surf(q)
+        assert np.max(np.abs(surf.aterm - so["aterm"])) < 1e-8 and abs(surf.a0[0] - so["a0"]) < 1e-9
+        assert np.max(np.abs(surf.bv.s - so["bv_s"])) < 1e-8 and surf.levflag[0] == so["levflag"]
+        assert np.max(np.abs(surf.uind - so["uind"])) < 1e-8
+
+
+def test_multi_surface_one_surface_equals_single(gpu_lib, uf):
+    a, fa = _tandem(uf)[:1], uf.TwoDFlowField()
+    b, fb = _tandem(uf)[0], uf.TwoDFlowField()
+    m1, _, _ = uf.ldvm(a, fa, 40, 0.012, write_summary=False)
+    m2, _, _ = uf.ldvm(b, fb, 40, 0.012, write_summary=False)
+    assert m1.shape == (40, 8) and np.max(np.abs(m1 - m2)) <= 1e-12

@@ -138,3 +138,24 @@ def test_kinematics_table_matches_oracle_callables(oracle, uf):
             if kind != 5:   # analytic derivative vs central difference
                 h = 1e-6
                 assert abs((d(t + h) - d(t - h)) / (2 * h) - d.deriv(t)) < 1e-7
+
+
+def test_multi_surface_oracle_consistency(oracle, uf):
+    """multi-surface restatement (solvers.jl:270-445): one surface == the single-surface driver;
+    two surfaces shed placeholder LEVs (calcs.jl:446) without NaNs; each surface keeps its own
+    Kelvin invariant contribution finite"""
+    def mk(x0, phase, lesp):
+        kin = uf.KinemDef(uf.SinDef(5 * math.pi / 180, 15 * math.pi / 180, 0.6, phase), uf.ConstDef(0.0), uf.ConstDef(1.0))
+        return uf.TwoDSurf("FlatPlate", 0.25, kin, [lesp], initpos=(x0, 0.0))
+    fld, dt = uf.TwoDFlowField(), 0.012
+    tab1 = uf.kinematics_table(mk(0.0, 0.0, 0.12), fld, 30, dt)
+    m1 = oracle.MultiSim([mk(0.0, 0.0, 0.12)], fld).run(tab1[:, None, :], dt)
+    ms = oracle.Sim(mk(0.0, 0.0, 0.12), fld).run(oracle.DRIVER_LDVM, tab1, dt)
+    assert np.max(np.abs(m1 - ms)) < 1e-12
+    surfs = [mk(0.0, 0.0, 0.12), mk(1.5, 1.0, 0.2)]
+    tabs = np.stack([uf.kinematics_table(s, fld, 120, dt) for s in surfs], axis=1)
+    sim = oracle.MultiSim(surfs, fld)
+    mat = sim.run(tabs, dt)
+    lev = sim.get_vorts(1)
+    assert np.all(np.isfinite(mat)) and np.sum(lev["vc"] == 0) > 0 and np.sum(lev["vc"] > 0) > 0
+    assert len(sim.get_vorts(0)["x"]) == 240

@@ -91,6 +91,8 @@ def lib():
         "unsflow_wake_timing": [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(i64)],
         "unsflow_wake_destroy": [vp],
         "unsflow_ldvm_create": [C.POINTER(vp), C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts)],
+        "unsflow_ldvm_multi_create": [C.POINTER(vp), C.c_int32, C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts)],
+        "unsflow_ldvm_multi_get_state": [vp, C.c_int32, C.POINTER(Surf), C.POINTER(Field)],
         "unsflow_ldvm_set_kinematics": [vp, i64, d],
         "unsflow_ldvm_set_2dof": [vp, d, d],
         "unsflow_ldvm_get_2dof": [vp, d],

@@ -49,8 +49,21 @@ struct StepState {
     double sp[11];       // TwoDOFPar
 };
 
+// per-surface scalars of the multi-surface driver (ldvm(surf::Vector{TwoDSurf}), solvers.jl:270-445)
+struct SurfState {
+    double c, uref, pvt, lespcrit, vc_new, vc4_new;
+    double kin[6];
+    double a0, a0dot, a0prev;
+    double cl, cd, cm;
+    int levflag;
+    int pad_;
+};
+constexpr int kMaxSurf = 4;
+
 struct LdvmDev {
     StepState *st;
+    SurfState *ms;       // [nsurf] (multi-surface driver only)
+    int nsurf;
     int ndiv, naterm, driver, solve_mode, del_kind;
     long long del_limit;
     double del_dist, del_tol;
@@ -581,6 +594,333 @@ __device__ void step_solve(const LdvmDev &d) {
 }
 
 
+
+// =============================================================================================
+// Multi-surface step: ldvm(surf::Vector{TwoDSurf}, ...) solvers.jl:311-434.
+// Surface arrays are laid out [array][surface][ndiv]; surface q uses offset q*ndiv (q*naterm).
+// The reference's Mult functors feed back only a surface's OWN newly shed vortices
+// (typedefs.jl:279-287, :375-388), so every surface solves an independent 1x1 (Kelvin) or 2x2
+// (Kelvin-Kutta) affine system; cross-surface influence enters through update_indbound and
+// add_indbound_b (calcs.jl:40-46) with the other surfaces' bound vortices of the previous step.
+// =============================================================================================
+__device__ void mstep_head(const LdvmDev &d) {
+    StepState *s = d.st;
+    const int tid = threadIdx.x, nd = d.ndiv, ns = d.nsurf;
+    __shared__ double sk[kMaxSurf][6];
+    if (tid == 0) {
+        const long long row = s->step < d.kin_rows ? s->step : d.kin_rows - 1;
+        const double *r0 = d.kin + 9 * ns * row;
+        s->t = r0[0]; s->fs[0] = r0[7]; s->fs[1] = r0[8];            // solvers.jl:313-316
+        for (int q = 0; q < ns; q++) {
+            const double *r = r0 + 9 * q;
+            SurfState &m = d.ms[q];
+            m.kin[0] = r[1]; m.kin[1] = r[2]; m.kin[2] = r[3]; m.kin[3] = r[4]; m.kin[4] = r[5]; m.kin[5] = r[6];
+            for (int k = 0; k < 6; k++) sk[q][k] = m.kin[k];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < ns * nd; t += blockDim.x) {                 // update_boundpos, calcs.jl:453-459
+        const int q = t / nd;
+        const SurfState &m = d.ms[q];
+        const double alpha = sk[q][0], alphadot = sk[q][2], hdot = sk[q][3], u = sk[q][4];
+        double sa, ca;
+        sincos(alpha, &sa, &ca);
+        d.bnd_x[t] = d.bnd_x[t] + d.dt * ((m.pvt * m.c - d.x[t]) * sa * alphadot - u + d.cam[t] * ca * alphadot);
+        d.bnd_z[t] = d.bnd_z[t] + d.dt * (hdot + (m.pvt * m.c - d.x[t]) * ca * alphadot - d.cam[t] * sa * alphadot);
+    }
+    __syncthreads();
+    if (tid == 0) {                                                    // place_tev multi, calcs.jl:389-406
+        const long long b = s->wake.begin[0], e = s->wake.end[0];
+        const long long ntev = e - b;
+        for (int q = 0; q < ns; q++) {
+            const SurfState &m = d.ms[q];
+            const double bx = d.bnd_x[q * nd + nd - 1], bz = d.bnd_z[q * nd + nd - 1];
+            double xloc, zloc;
+            if (ntev < ns) { xloc = bx + 0.5 * sk[q][4] * d.dt; zloc = bz; }
+            else { xloc = bx + (1. / 3.) * (d.wx[e - ns + q] - bx); zloc = bz + (1. / 3.) * (d.wz[e - ns + q] - bz); }
+            const long long k = e + q;
+            d.wx[k] = xloc; d.wz[k] = zloc; d.wg[k] = 0.0; d.wvc4[k] = m.vc4_new; d.wvc[k] = m.vc_new; d.wvx[k] = 0.0; d.wvz[k] = 0.0;
+        }
+        s->wake.end[0] = e + ns;
+    }
+}
+
+// downwash of surface q at its bound point i (global index t = q*nd + i), calcs.jl:49-54
+__device__ __forceinline__ double mdownwash_at(const LdvmDev &d, const SurfState &m, const double *fs, int t, double ui, double wi,
+                                               double sa, double ca) {
+    const double alphadot = m.kin[2], hdot = m.kin[3], u = m.kin[4];
+    return -(u + fs[0]) * sa - ui * sa + (hdot - fs[1]) * ca - wi * ca - alphadot * (d.x[t] - m.pvt * m.c)
+           + d.cam_slope[t] * (ui * ca + (u + fs[0]) * ca + (hdot - fs[1]) * sa - wi * sa);
+}
+
+__device__ void mstep_solve(const LdvmDev &d) {
+    StepState *s = d.st;
+    const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm, ns = d.nsurf;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
+    __shared__ double uT[kNdMax], wT[kNdMax], uL[kNdMax], wL[kNdMax], gam[kNdMax];
+    __shared__ double aterm[kNaMax + 1], dth[kNdMax], sc[32], fs[2];
+    __shared__ double gts[kMaxSurf], a0s[kMaxSurf];
+    __shared__ int shed[kMaxSurf], nshed;
+    __shared__ SurfState ms[kMaxSurf];
+    const double eps_fd = 6.0554544523933395e-06;
+    if (tid < 2) fs[tid] = s->fs[tid];
+    if (tid < ns) ms[tid] = d.ms[tid];
+    for (int i = tid; i < nd; i += blockDim.x) dth[i] = i > 0 ? d.theta[i] - d.theta[i - 1] : 0.0;
+    __syncthreads();
+    const long long te = s->wake.end[0];          // the ns TEVs shed this step are te-ns .. te-1
+    const long long bv0 = s->wake.begin[3];
+    const int nb = nd - 1;
+
+    // ---------------- pass 1: per surface, update_indbound + add_indbound_b + 1x1 Kelvin ----------
+    for (int q = 0; q < ns; q++) {
+        const SurfState &m = ms[q];
+        const double urefpi = m.uref * kPi, kfac = m.uref * m.c * kPi;
+        double sa, ca;
+        sincos(m.kin[0], &sa, &ca);
+        const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
+        for (int i = tid; i < nd; i += blockDim.x) {
+            const int t = q * nd + i;
+            double su = 0.0, sw = 0.0;
+            for (int k = 0; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + t]; sw += d.p2w[(long long)k * d.p2stride + t]; }
+            double u = su * kInvTwoPi, w = sw * kInvTwoPi;
+            // add_indbound_b (calcs.jl:40-46): bound vortices of the other surfaces (previous step)
+            for (int j = 0; j < ns; j++) {
+                if (j == q) continue;
+                double uj = 0.0, wj = 0.0;
+                for (int b = 0; b < nb; b++) {
+                    const long long k = bv0 + (long long)j * nb + b;
+                    const double xd = d.wx[k] - d.bnd_x[t], zd = d.wz[k] - d.bnd_z[t];
+                    const double dsq = xd * xd + zd * zd;
+                    const double den = kTwoPi * sqrt(d.wvc4[k] + dsq * dsq);
+                    uj = uj - d.wg[k] * zd / den;
+                    wj = wj + d.wg[k] * xd / den;
+                }
+                u += uj; w += wj;
+            }
+            uind[i] = u; wind[i] = w;
+            unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
+            dw[i] = mdownwash_at(d, m, fs, t, u, w, sa, ca);
+            dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
+        }
+        __syncthreads();
+        for (int k = warp; k < 4; k += nwarps) {
+            const double v = warp_trapz_cos((k & 2) ? dw1 : dw, dth, d.costab + (k & 1) * nd, nd);
+            if (lane == 0) sc[k] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
+            const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
+            const double g = -(K0 - Kp) / (K1 + 1.0);
+            sc[8] = g;
+            // NLsolve emulation: only the LAST unknown is one probe away from the root
+            sc[9] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE && q == ns - 1) ? g - eps_fd * fmax(1.0, fabs(g)) : g;
+            gts[q] = g;
+        }
+        __syncthreads();
+        const double ga = sc[9];
+        for (int i = tid; i < nd; i += blockDim.x) {
+            const int t = q * nd + i;
+            uind[i] += ga * uT[i]; wind[i] += ga * wT[i];
+            dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+            d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
+        }
+        __syncthreads();
+        for (int n = warp; n <= na; n += nwarps) {
+            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+            if (lane == 0) aterm[n] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double a0 = -aterm[0] / urefpi;
+            a0s[q] = a0;
+            ms[q].a0 = a0;
+            ms[q].a0dot = (a0 - m.a0prev) / d.dt;                 // update_a2a3adot, calcs.jl:7
+        }
+        for (int n = tid + 1; n <= na; n += blockDim.x) {
+            const double an = 2. * aterm[n] / urefpi;
+            d.aterm[q * na + n - 1] = an;                          // functor: update_a0anda1 + update_a2toan
+            if (n <= 3) d.adot[q * na + n - 1] = (an - d.aprev[q * na + n - 1]) / d.dt;   // calcs.jl:8-10
+        }
+        __syncthreads();
+    }
+    // ---------------- LESP test and place_lev (solvers.jl:354-368, calcs.jl:428-450) ---------------
+    if (tid == 0) {
+        int c = 0;
+        for (int q = 0; q < ns; q++) { shed[q] = fabs(a0s[q]) > ms[q].lespcrit ? 1 : 0; c += shed[q]; }
+        nshed = c;
+        if (c > 0) {
+            const long long le = s->wake.end[1];
+            for (int q = 0; q < ns; q++) {
+                const long long k = le + q;
+                if (shed[q]) {
+                    const SurfState &m = ms[q];
+                    double sa, ca;
+                    sincos(m.kin[0], &sa, &ca);
+                    const double bx = d.bnd_x[q * nd], bz = d.bnd_z[q * nd];
+                    double xl, zl;
+                    if (m.levflag == 0) {
+                        const double vx = m.kin[4] - m.kin[2] * sa * m.pvt * m.c + d.uind[q * nd];
+                        const double vz = -m.kin[2] * ca * m.pvt * m.c - m.kin[3] + d.wind[q * nd];
+                        xl = bx + 0.5 * vx * d.dt; zl = bz + 0.5 * vz * d.dt;
+                    } else {
+                        xl = bx + (1. / 3.) * (d.wx[le - ns + q] - bx); zl = bz + (1. / 3.) * (d.wz[le - ns + q] - bz);
+                    }
+                    d.wx[k] = xl; d.wz[k] = zl; d.wg[k] = 0.0; d.wvc4[k] = m.vc4_new; d.wvc[k] = m.vc_new;
+                } else {
+                    // placeholder TwoDVort(0,0,0,0,0,0) (calcs.jl:446): strength 0 contributes nothing;
+                    // vc4 is kept > 0 on the device so that two coincident placeholders cannot make 0*Inf
+                    d.wx[k] = 0.0; d.wz[k] = 0.0; d.wg[k] = 0.0; d.wvc4[k] = 1.0; d.wvc[k] = 0.0;
+                }
+                d.wvx[k] = 0.0; d.wvz[k] = 0.0;
+            }
+            s->wake.end[1] = le + ns;
+        }
+    }
+    __syncthreads();
+    const long long le = s->wake.end[1];
+    // ---------------- pass 2: Kelvin-Kutta 2x2 for shedding surfaces, bv, forces -------------------
+    for (int q = 0; q < ns; q++) {
+        const SurfState &m = ms[q];
+        const double urefpi = m.uref * kPi, kfac = m.uref * m.c * kPi;
+        double sa, ca;
+        sincos(m.kin[0], &sa, &ca);
+        double gt = gts[q], gl = 0.0;
+        for (int i = tid; i < nd; i += blockDim.x) { const int t = q * nd + i; uind[i] = d.uind[t]; wind[i] = d.wind[t]; dw[i] = d.downwash[t]; }
+        __syncthreads();
+        if (nshed > 0 && shed[q]) {
+            const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
+            const double xl = d.wx[le - ns + q], zl = d.wz[le - ns + q];
+            for (int i = tid; i < nd; i += blockDim.x) {
+                const int t = q * nd + i;
+                unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
+                unit_influence(xl, zl, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uL[i], &wL[i]);
+                uind[i] -= gt * uT[i]; wind[i] -= gt * wT[i];           // functor subtracts the STORED strength
+                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+                dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
+                dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[t] * (uL[i] * ca - wL[i] * sa);
+            }
+            __syncthreads();
+            for (int k = warp; k < 6; k += nwarps) {
+                const double v = warp_trapz_cos(k < 2 ? dw : (k < 4 ? dw1 : dw2), dth, d.costab + (k & 1) * nd, nd);
+                if (lane == 0) sc[k] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
+                const double a02 = -sc[4] / urefpi, a12 = 2. * sc[5] / urefpi;
+                const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), K2 = kfac * (a02 + a12 / 2.);
+                const double Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
+                const double lesp_cond = (a0s[q] > 0) ? m.lespcrit : -m.lespcrit;
+                const double m11 = K1 + 1., m12 = K2 + 1., m21 = a01, m22 = a02, r1 = Kp - K0, r2 = lesp_cond - a00;
+                const double det = m11 * m22 - m12 * m21;
+                const double g1 = (r1 * m22 - m12 * r2) / det, g2 = (m11 * r2 - r1 * m21) / det;
+                sc[8] = g1; sc[14] = g2;
+                // last unknown of KelvinKuttaMult = LEV strength of the last shedding surface
+                int lastshed = -1;
+                for (int j = 0; j < ns; j++) if (shed[j]) lastshed = j;
+                sc[15] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE && q == lastshed) ? g2 - eps_fd * fmax(1.0, fabs(g2)) : g2;
+            }
+            __syncthreads();
+            gt = sc[8]; gl = sc[14];
+            const double gla = sc[15];
+            for (int i = tid; i < nd; i += blockDim.x) {
+                const int t = q * nd + i;
+                uind[i] += gt * uT[i] + gla * uL[i]; wind[i] += gt * wT[i] + gla * wL[i];
+                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+                d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
+            }
+            __syncthreads();
+        }
+        // final Fourier coefficients of this surface from its final downwash
+        for (int n = warp; n <= na; n += nwarps) {
+            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
+            if (lane == 0) aterm[n] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double a0 = -aterm[0] / urefpi;
+            ms[q].a0 = a0; ms[q].a0prev = a0;                           // solvers.jl:399
+            ms[q].levflag = (nshed > 0 && shed[q]) ? 1 : 0;             // :377-394
+            d.wg[te - ns + q] = gt;
+            if (nshed > 0 && shed[q]) d.wg[le - ns + q] = gl;
+            sc[10] = a0;
+        }
+        for (int n = tid + 1; n <= na; n += blockDim.x) {
+            const double an = 2. * aterm[n] / urefpi;
+            aterm[n] = an;
+            d.aterm[q * na + n - 1] = an;
+            if (n <= 3) d.aprev[q * na + n - 1] = an;                   // :400-402
+        }
+        __syncthreads();
+        const double a0 = sc[10];
+        for (int ib = tid; ib < nd; ib += blockDim.x) {                 // update_bv, calcs.jl:204-219
+            double g = (a0 * (1 + d.costab[nd + ib]));
+            const double sth = d.sintab[nd + ib];
+#pragma unroll 7
+            for (int ia = 1; ia <= na; ia++) g = g + aterm[ia] * d.sintab[ia * nd + ib] * sth;
+            gam[ib] = g * m.uref * m.c;
+        }
+        __syncthreads();
+        for (int ib = tid + 1; ib < nd; ib += blockDim.x) {
+            const long long k = bv0 + (long long)q * nb + ib - 1;
+            d.wg[k] = (gam[ib] + gam[ib - 1]) * (d.theta[1] - d.theta[0]) / 2.;
+            d.wx[k] = (d.bnd_x[q * nd + ib] + d.bnd_x[q * nd + ib - 1]) / 2.;
+            d.wz[k] = (d.bnd_z[q * nd + ib] + d.bnd_z[q * nd + ib - 1]) / 2.;
+        }
+        if (warp == 1 % nwarps) {                                       // calc_forces, postprocess.jl:1-32
+            const double hdot = m.kin[3], u = m.kin[4];
+            const double a1 = aterm[1], a2 = aterm[2], a0dot = ms[q].a0dot;
+            const double ad1 = d.adot[q * na], ad2 = d.adot[q * na + 1], ad3 = d.adot[q * na + 2];
+            const double ufac = (u + fs[0]) * ca / m.uref + (hdot - fs[1]) * sa / m.uref;
+            const double cnc = 2 * kPi * ufac * (a0 + a1 / 2.);
+            const double cnnc = 2 * kPi * (3 * m.c * a0dot / (4 * m.uref) + m.c * ad1 / (4 * m.uref) + m.c * ad2 / (8 * m.uref));
+            const double cs = 2 * kPi * a0 * a0;
+            double nonl = 0, nonl_m = 0;
+            for (int ib = lane; ib < nb; ib += 32) {
+                const double gb = (gam[ib + 1] + gam[ib]) * (d.theta[1] - d.theta[0]) / 2.;
+                const double v = (uind[ib] * ca - wind[ib] * sa);
+                nonl = nonl + v * gb;
+                nonl_m = nonl_m + v * d.x[q * nd + ib] * gb;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { nonl += __shfl_xor_sync(0xffffffffu, nonl, o); nonl_m += __shfl_xor_sync(0xffffffffu, nonl_m, o); }
+            nonl = nonl * 2. / (m.uref * m.uref * m.c);
+            nonl_m = nonl_m * 2. / (m.uref * m.uref * m.c * m.c);
+            const double cn = cnc + cnnc + nonl;
+            const double cl = cn * ca + cs * sa, cd = cn * sa - cs * ca;
+            const double cm = cn * m.pvt - 2 * kPi * (ufac * (a0 / 4. + a1 / 4. - a2 / 8.)
+                              + (m.c / m.uref) * (7. * a0dot / 16. + 3. * ad1 / 16. + ad2 / 16. - ad3 / 64.)) - nonl_m;
+            if (lane == 0) {
+                ms[q].cl = cl; ms[q].cd = cd; ms[q].cm = cm;
+                double *r = d.mat + (1 + 7 * ns) * s->mat_row + 1 + 7 * q;
+                r[0] = m.kin[0]; r[1] = m.kin[1]; r[2] = m.kin[4]; r[3] = a0; r[4] = cl; r[5] = cd; r[6] = cm;   // solvers.jl:427-432
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < ns) d.ms[tid] = ms[tid];
+    if (tid == 0) {
+        if (d.del_kind == UNSFLOW_DEL_SPALART) {                        // solvers.jl:406-408
+            double lx = 0, lz = 0;
+            const int mid = (int)nearbyint(nd / 2.0) - 1;
+            for (int q = 0; q < ns; q++) { lx += d.bnd_x[q * nd + mid]; lz += d.bnd_z[q * nd + mid]; }
+            lx /= ns; lz /= ns;
+            if (s->wake.end[0] - s->wake.begin[0] > d.del_limit) {
+                dev_spalart(d, &s->wake.begin[0], s->wake.end[0], lx, lz);
+                if (s->wake.end[1] - s->wake.begin[1] > d.del_limit) dev_spalart(d, &s->wake.begin[1], s->wake.end[1], lx, lz);
+            }
+        }
+        d.mat[(1 + 7 * ns) * s->mat_row] = s->t;
+        s->mat_row += 1;
+        s->step += 1;
+    }
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_mstep_head(const LdvmDev d) { mstep_head(d); }
+__global__ void __launch_bounds__(kSolveThreads) k_mstep_solve(const LdvmDev d) { mstep_solve(d); }
+
 __global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) { step_head(d); }
 __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) { step_solve(d); }
 
@@ -732,6 +1072,8 @@ static thread_local float g_batch_ms = 0.f;   // CUDA-event time of the last k_e
 struct unsflow_ldvm {
     unsflow_opts opts{};
     int ndiv = 0, naterm = 0;
+    int nsurf = 1, mat_cols = 8;
+    DevBuf<SurfState> ms;
     int64_t cap_t = 0, cap_l = 0, cap_e = 0, bvpad = 0, tot = 0;
     int64_t off_t = 0, off_l = 0, off_e = 0, off_b = 0;
     int64_t ntev0 = 0, nlev0 = 0, nextv = 0;
@@ -789,10 +1131,19 @@ int unsflow_ldvm_destroy(unsflow_ldvm *h) {
     return 0;
 }
 
-int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow_field *fl, const unsflow_opts *op) {
+static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *sfs, const unsflow_field *fl, const unsflow_opts *op) {
     UF_CHECK(out != nullptr, "unsflow_ldvm_create: null handle pointer");
     *out = nullptr;
-    UF_CHECK(sf && fl && op, "unsflow_ldvm_create: null argument");
+    UF_CHECK(sfs && fl && op, "unsflow_ldvm_create: null argument");
+    UF_CHECK(nsurf >= 1 && nsurf <= kMaxSurf, "unsflow_ldvm_create: nsurf=%d outside [1,%d]", nsurf, kMaxSurf);
+    const unsflow_surf *sf = &sfs[0];
+    for (int q = 1; q < nsurf; q++) {
+        UF_CHECK(sfs[q].ndiv == sf->ndiv && sfs[q].naterm == sf->naterm, "unsflow_ldvm_create: all surfaces must share ndiv and naterm");
+        UF_CHECK(sfs[q].theta && sfs[q].x && sfs[q].cam && sfs[q].cam_slope && sfs[q].bnd_x && sfs[q].bnd_z && sfs[q].uind && sfs[q].wind && sfs[q].downwash && sfs[q].aterm && sfs[q].adot && sfs[q].aprev, "unsflow_ldvm_create: null surf array");
+        UF_CHECK(sfs[q].bv.n == sf->ndiv - 1, "unsflow_ldvm_create: surf.bv must hold ndiv-1 vortices");
+        for (int i = 0; i < sf->ndiv; i++) UF_CHECK(sfs[q].theta[i] == sf->theta[i], "unsflow_ldvm_create: all surfaces must share the theta grid");
+    }
+    UF_CHECK(nsurf == 1 || op->driver == UNSFLOW_DRIVER_LDVM, "unsflow_ldvm_create: several surfaces are supported by the ldvm driver only");
     UF_CHECK(sf->ndiv >= 3 && sf->ndiv <= kNdMax, "unsflow_ldvm_create: ndiv=%d outside [3,%d]", sf->ndiv, kNdMax);
     UF_CHECK(sf->naterm >= 3 && sf->naterm <= kNaMax, "unsflow_ldvm_create: naterm=%d outside [3,%d]", sf->naterm, kNaMax);
     UF_CHECK(op->driver >= 0 && op->driver <= 3, "unsflow_ldvm_create: bad driver %d", op->driver);
@@ -810,35 +1161,41 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     auto fail = [&](int rc) { unsflow_ldvm_destroy(h); return rc; };
     h->opts = *op;
     const int nd = h->ndiv = sf->ndiv, na = h->naterm = sf->naterm;
+    const int ns = h->nsurf = nsurf;
+    h->mat_cols = nsurf == 1 ? 8 : 1 + 7 * nsurf;
     h->ntev0 = fl->tev.n; h->nlev0 = fl->lev.n; h->nextv = fl->extv.n;
     // slabs start on pair-tile boundaries (kSymTB is a multiple of the direct kernel's kTS)
-    h->cap_t = round_up(h->ntev0 + op->max_steps + 1, kSymTB);
-    h->cap_l = round_up(h->nlev0 + op->max_steps + 1, kSymTB);
+    h->cap_t = round_up(h->ntev0 + ns * op->max_steps + ns, kSymTB);
+    h->cap_l = round_up(h->nlev0 + ns * op->max_steps + ns, kSymTB);
     h->cap_e = round_up(std::max<int64_t>(h->nextv, 1), kSymTB);
-    h->bvpad = round_up(nd - 1, kSymTB);
+    h->bvpad = round_up(ns * (nd - 1), kSymTB);
     h->off_t = 0; h->off_l = h->cap_t; h->off_e = h->off_l + h->cap_l; h->off_b = h->off_e + h->cap_e;
     h->tot = h->off_b + h->bvpad;
     h->mat_cap = std::max<int64_t>(op->max_steps, 1);
-    h->ndivpad = round_up(nd, 8);
+    h->ndivpad = round_up(ns * nd, 8);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(2); }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evc);
     if (cudaMallocHost((void **)&h->pinned, sizeof(StepState)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(2); }
     const int64_t tot = h->tot;
     h->S2max = 256;
     h->S1max = (int)std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)2e9 / (16 * tot)));
-    if (h->st.alloc(1) || h->surf.alloc(9 * nd + 3 * na) || h->tabs.alloc(2 * (na + 1) * nd) || h->wake.alloc(7 * tot) ||
-        h->mat.alloc(8 * h->mat_cap) || h->p2.alloc(2 * (int64_t)h->S2max * h->ndivpad) ||
+    if (h->st.alloc(1) || h->ms.alloc(ns) || h->surf.alloc(ns * (9 * nd + 3 * na)) || h->tabs.alloc(2 * (na + 1) * nd) || h->wake.alloc(7 * tot) ||
+        h->mat.alloc(h->mat_cols * h->mat_cap) || h->p2.alloc(2 * (int64_t)h->S2max * h->ndivpad) ||
         h->p1.alloc(2 * (int64_t)h->S1max * tot))
         return fail(2);
     if (h->wake.zero(h->stream) || h->mat.zero(h->stream)) return fail(2);
 
     // ---- host staging -------------------------------------------------------------------------
-    std::vector<double> hs((size_t)(9 * nd + 3 * na));
-    const double *sarr[9] = {sf->theta, sf->x, sf->cam, sf->cam_slope, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
-    for (int k = 0; k < 9; k++) memcpy(&hs[(size_t)k * nd], sarr[k], sizeof(double) * nd);
-    memcpy(&hs[(size_t)9 * nd], sf->aterm, sizeof(double) * na);
-    memcpy(&hs[(size_t)9 * nd + na], sf->adot, sizeof(double) * na);
-    memcpy(&hs[(size_t)9 * nd + 2 * na], sf->aprev, sizeof(double) * na);
+    // surface arrays laid out [array][surface][ndiv] (+ [array][surface][naterm])
+    std::vector<double> hs((size_t)ns * (9 * nd + 3 * na));
+    for (int q = 0; q < ns; q++) {
+        const unsflow_surf *sq = &sfs[q];
+        const double *sarr[9] = {sq->theta, sq->x, sq->cam, sq->cam_slope, sq->bnd_x, sq->bnd_z, sq->uind, sq->wind, sq->downwash};
+        for (int k = 0; k < 9; k++) memcpy(&hs[((size_t)k * ns + q) * nd], sarr[k], sizeof(double) * nd);
+        memcpy(&hs[(size_t)9 * ns * nd + ((size_t)0 * ns + q) * na], sq->aterm, sizeof(double) * na);
+        memcpy(&hs[(size_t)9 * ns * nd + ((size_t)1 * ns + q) * na], sq->adot, sizeof(double) * na);
+        memcpy(&hs[(size_t)9 * ns * nd + ((size_t)2 * ns + q) * na], sq->aprev, sizeof(double) * na);
+    }
     std::vector<double> ht((size_t)(2 * (na + 1) * nd));
     for (int n = 0; n <= na; n++)
         for (int i = 0; i < nd; i++) {
@@ -861,7 +1218,9 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
         }
         return 0;
     };
-    if (put(fl->tev, h->off_t) || put(fl->lev, h->off_l) || put(fl->extv, h->off_e) || put(sf->bv, h->off_b)) return fail(1);
+    if (put(fl->tev, h->off_t) || put(fl->lev, h->off_l) || put(fl->extv, h->off_e)) return fail(1);
+    for (int q = 0; q < ns; q++)
+        if (put(sfs[q].bv, h->off_b + (int64_t)q * (nd - 1))) return fail(1);
     h->uniform = uni;
     h->vc4u = vc_new * vc_new * vc_new * vc_new;
 
@@ -870,8 +1229,8 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     s0.wake.begin[0] = h->off_t; s0.wake.end[0] = h->off_t + h->ntev0;
     s0.wake.begin[1] = h->off_l; s0.wake.end[1] = h->off_l + h->nlev0;
     s0.wake.begin[2] = h->off_e; s0.wake.end[2] = h->off_e + h->nextv;
-    s0.wake.begin[3] = h->off_b; s0.wake.end[3] = h->off_b + nd - 1;
-    s0.bnd.begin[0] = 0; s0.bnd.end[0] = nd;
+    s0.wake.begin[3] = h->off_b; s0.wake.end[3] = h->off_b + (int64_t)ns * (nd - 1);
+    s0.bnd.begin[0] = 0; s0.bnd.end[0] = (int64_t)ns * nd;
     s0.levflag = sf->levflag;
     for (int k = 0; k < 6; k++) s0.kin[k] = sf->kinem[k];
     s0.fs[0] = fl->u; s0.fs[1] = fl->w;
@@ -879,8 +1238,21 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     *h->pinned = s0;
     h->known_step = 0; h->known_ntev_end = h->ntev0; h->known_nlev_end = h->nlev0;
 
+    std::vector<SurfState> hms((size_t)ns);
+    for (int q = 0; q < ns; q++) {
+        SurfState &m = hms[q];
+        memset(&m, 0, sizeof(m));
+        const unsflow_surf *sq = &sfs[q];
+        m.c = sq->c; m.uref = sq->uref; m.pvt = sq->pvt; m.lespcrit = sq->lespcrit;
+        m.vc_new = 0.02 * sq->c; m.vc4_new = m.vc_new * m.vc_new * m.vc_new * m.vc_new;
+        for (int k = 0; k < 6; k++) m.kin[k] = sq->kinem[k];
+        m.a0 = sq->a0; m.a0dot = sq->a0dot; m.a0prev = sq->a0prev; m.levflag = sq->levflag;
+        if (q > 0 && m.vc_new != vc_new) uni = false;
+    }
+    h->uniform = uni;
     cudaStream_t st = h->stream;
-    if (cudaMemcpyAsync(h->st.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+    if (cudaMemcpyAsync(h->ms.p, hms.data(), sizeof(SurfState) * ns, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(h->st.p, &s0, sizeof(s0), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(h->surf.p, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(h->tabs.p, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(h->wake.p, hw.data(), sizeof(double) * hw.size(), cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -896,9 +1268,11 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     d.c = sf->c; d.uref = sf->uref; d.pvt = sf->pvt; d.lespcrit = sf->lespcrit; d.dt = op->dt;
     d.vc_new = vc_new; d.vc4_new = h->vc4u;
     double *sp = h->surf.p;
-    d.theta = sp; d.x = sp + nd; d.cam = sp + 2 * nd; d.cam_slope = sp + 3 * nd; d.bnd_x = sp + 4 * nd; d.bnd_z = sp + 5 * nd;
-    d.uind = sp + 6 * nd; d.wind = sp + 7 * nd; d.downwash = sp + 8 * nd;
-    d.aterm = sp + 9 * nd; d.adot = sp + 9 * nd + na; d.aprev = sp + 9 * nd + 2 * na;
+    const int64_t snd = (int64_t)ns * nd, sna = (int64_t)ns * na;
+    d.ms = h->ms.p; d.nsurf = ns;
+    d.theta = sp; d.x = sp + snd; d.cam = sp + 2 * snd; d.cam_slope = sp + 3 * snd; d.bnd_x = sp + 4 * snd; d.bnd_z = sp + 5 * snd;
+    d.uind = sp + 6 * snd; d.wind = sp + 7 * snd; d.downwash = sp + 8 * snd;
+    d.aterm = sp + 9 * snd; d.adot = sp + 9 * snd + sna; d.aprev = sp + 9 * snd + 2 * sna;
     d.costab = h->tabs.p; d.sintab = h->tabs.p + (int64_t)(na + 1) * nd;
     double *wp = h->wake.p;
     d.wx = wp; d.wz = wp + tot; d.wg = wp + 2 * tot; d.wvc4 = wp + 3 * tot; d.wvc = wp + 4 * tot; d.wvx = wp + 5 * tot; d.wvz = wp + 6 * tot;
@@ -909,12 +1283,21 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflo
     return 0;
 }
 
+int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow_field *fl, const unsflow_opts *op) {
+    return ldvm_create_impl(out, 1, sf, fl, op);
+}
+
+int unsflow_ldvm_multi_create(unsflow_ldvm **out, int32_t nsurf, const unsflow_surf *surfs, const unsflow_field *fl,
+                              const unsflow_opts *op) {
+    return ldvm_create_impl(out, nsurf, surfs, fl, op);
+}
+
 int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *table) {
     UF_CHECK(h != nullptr, "unsflow_ldvm_set_kinematics: null handle");
     UF_CHECK(nrows > 0 && table != nullptr, "unsflow_ldvm_set_kinematics: empty table");
     UF_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->kin.alloc(9 * nrows)) return 2;
-    UF_CUDA(cudaMemcpyAsync(h->kin.p, table, sizeof(double) * 9 * nrows, cudaMemcpyHostToDevice, h->stream));
+    if (h->kin.alloc(9 * nrows * h->nsurf)) return 2;
+    UF_CUDA(cudaMemcpyAsync(h->kin.p, table, sizeof(double) * 9 * nrows * h->nsurf, cudaMemcpyHostToDevice, h->stream));
     // rows are consumed from the start of the new table
     StepState *zero_step = h->pinned;
     (void)zero_step;
@@ -945,7 +1328,7 @@ int unsflow_ldvm_get_2dof(unsflow_ldvm *h, double *k22) {
 
 // upper bounds of the live end offsets at `ahead` steps from now (known counts + steps since)
 static void step_bounds(const unsflow_ldvm *h, int64_t ahead, int64_t *ntev_ub, int64_t *nlev_ub) {
-    const int64_t since = h->steps_done - h->known_step + ahead;
+    const int64_t since = (h->steps_done - h->known_step + ahead) * h->nsurf;
     *ntev_ub = std::min(h->cap_t, h->known_ntev_end + since);
     *nlev_ub = std::min(h->cap_l, h->known_nlev_end + since);
 }
@@ -954,11 +1337,13 @@ static void step_bounds(const unsflow_ldvm *h, int64_t ahead, int64_t *ntev_ub, 
 static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaStream_t st) {
     const int driver = h->opts.driver, smc = sm_count(), order = rsqrt_order();
     const int64_t tot = h->tot, nwake_ub = ntev_ub + nlev_ub + h->nextv;
-    k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+    const bool multi = h->nsurf > 1;
+    if (multi) k_mstep_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+    else k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;
     if (driver != UNSFLOW_DRIVER_LAUTAT) {
         // bound-point sweep (update_indbound, calcs.jl:35-38): targets = bound points
-        InducePlan p2 = plan_induce(h->ndiv, 1, nwake_ub, 3, smc, h->S2max);
+        InducePlan p2 = plan_induce((long long)h->ndiv * h->nsurf, 1, nwake_ub, 3, smc, h->S2max);
         InduceArgs a;
         a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
         a.tx = h->dev.bnd_x; a.tz = h->dev.bnd_z;
@@ -969,11 +1354,12 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         h->dev.S2 = p2.S;
         h->launches++;
     }
-    k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+    if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+    else k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;
     // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
     const bool sym = h->uniform && nwake_ub >= sym_threshold();
-    InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + h->ndiv - 1, 4, smc, h->S1max);
+    InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + (long long)h->nsurf * (h->ndiv - 1), 4, smc, h->S1max);
     InduceArgs a;
     a.sx = h->dev.wx; a.sz = h->dev.wz; a.sg = h->dev.wg; a.svc4 = h->dev.wvc4;
     a.tx = h->dev.wx; a.tz = h->dev.wz;
@@ -1090,12 +1476,13 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
     const int64_t tot = h->tot;
     (void)tot;
     // mat: device row-major [nsteps][8] -> caller column-major nsteps x 8
-    std::vector<double> hm((size_t)(8 * nsteps));
-    UF_CUDA(cudaMemcpyAsync(hm.data(), h->mat.p, sizeof(double) * 8 * nsteps, cudaMemcpyDeviceToHost, st));
+    const int mc = h->mat_cols;
+    std::vector<double> hm((size_t)(mc * nsteps));
+    UF_CUDA(cudaMemcpyAsync(hm.data(), h->mat.p, sizeof(double) * mc * nsteps, cudaMemcpyDeviceToHost, st));
     UF_CUDA(cudaStreamSynchronize(st));
     h->readback_pending = false;
     for (int64_t i = 0; i < nsteps; i++)
-        for (int j = 0; j < 8; j++) mat_out[i + j * nsteps] = hm[(size_t)(8 * i + j)];
+        for (int j = 0; j < mc; j++) mat_out[i + j * nsteps] = hm[(size_t)(mc * i + j)];
     UF_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     // exact counts are known now
     StepState s;
@@ -1116,30 +1503,16 @@ int unsflow_ldvm_counts(unsflow_ldvm *h, int64_t *ntev, int64_t *nlev, int64_t *
     return 0;
 }
 
-int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *sf, unsflow_field *fl) {
+static int ldvm_get_state_impl(unsflow_ldvm *h, int nsurf, unsflow_surf *sfs, unsflow_field *fl) {
     UF_CHECK(h != nullptr, "unsflow_ldvm_get_state: null handle");
+    UF_CHECK(sfs == nullptr || nsurf == h->nsurf, "unsflow_ldvm_get_state: handle has %d surface(s), caller passed %d", h->nsurf, nsurf);
     StepState s;
     if (int rc = ldvm_sync_counts(h, &s)) return rc;
     cudaStream_t st = h->stream;
-    const int nd = h->ndiv, na = h->naterm;
+    const int nd = h->ndiv, na = h->naterm, ns = h->nsurf;
     const int64_t tot = h->tot;
-    if (sf) {
-        UF_CHECK(sf->ndiv == nd && sf->naterm == na, "unsflow_ldvm_get_state: surf dimensions differ from the handle's");
-        std::vector<double> hs((size_t)(9 * nd + 3 * na));
-        UF_CUDA(cudaMemcpyAsync(hs.data(), h->surf.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, st));
-        UF_CUDA(cudaStreamSynchronize(st));
-        double *sarr[9] = {nullptr, nullptr, nullptr, nullptr, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
-        for (int k = 4; k < 9; k++) if (sarr[k]) memcpy(sarr[k], &hs[(size_t)k * nd], sizeof(double) * nd);
-        if (sf->aterm) memcpy(sf->aterm, &hs[(size_t)9 * nd], sizeof(double) * na);
-        if (sf->adot) memcpy(sf->adot, &hs[(size_t)9 * nd + na], sizeof(double) * na);
-        if (sf->aprev) memcpy(sf->aprev, &hs[(size_t)9 * nd + 2 * na], sizeof(double) * na);
-        sf->levflag = s.levflag;
-        for (int k = 0; k < 6; k++) sf->kinem[k] = s.kin[k];
-        sf->a0 = s.a0; sf->a0dot = s.a0dot; sf->a0prev = s.a0prev;
-    }
-    auto get = [&](unsflow_vorts *v, int reg) -> int {
+    auto get = [&](unsflow_vorts *v, int64_t b, int64_t n) -> int {
         if (!v) return 0;
-        const int64_t b = s.wake.begin[reg], n = s.wake.end[reg] - b;
         UF_CHECK(v->n >= n, "unsflow_ldvm_get_state: vortex array capacity %lld < count %lld", (long long)v->n, (long long)n);
         double *dst[6] = {v->x, v->z, v->s, v->vc, v->vx, v->vz};
         const int slab[6] = {0, 1, 2, 4, 5, 6};
@@ -1149,15 +1522,47 @@ int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *sf, unsflow_field *fl)
         v->n = n;
         return 0;
     };
-    if (sf) if (int rc = get(&sf->bv, 3)) return rc;
+    if (sfs) {
+        std::vector<double> hs((size_t)ns * (9 * nd + 3 * na));
+        std::vector<SurfState> hms((size_t)ns);
+        UF_CUDA(cudaMemcpyAsync(hs.data(), h->surf.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, st));
+        UF_CUDA(cudaMemcpyAsync(hms.data(), h->ms.p, sizeof(SurfState) * ns, cudaMemcpyDeviceToHost, st));
+        UF_CUDA(cudaStreamSynchronize(st));
+        for (int q = 0; q < ns; q++) {
+            unsflow_surf *sf = &sfs[q];
+            UF_CHECK(sf->ndiv == nd && sf->naterm == na, "unsflow_ldvm_get_state: surf dimensions differ from the handle's");
+            double *sarr[9] = {nullptr, nullptr, nullptr, nullptr, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
+            for (int k = 4; k < 9; k++) if (sarr[k]) memcpy(sarr[k], &hs[((size_t)k * ns + q) * nd], sizeof(double) * nd);
+            if (sf->aterm) memcpy(sf->aterm, &hs[(size_t)9 * ns * nd + ((size_t)0 * ns + q) * na], sizeof(double) * na);
+            if (sf->adot) memcpy(sf->adot, &hs[(size_t)9 * ns * nd + ((size_t)1 * ns + q) * na], sizeof(double) * na);
+            if (sf->aprev) memcpy(sf->aprev, &hs[(size_t)9 * ns * nd + ((size_t)2 * ns + q) * na], sizeof(double) * na);
+            if (ns == 1) {
+                sf->levflag = s.levflag;
+                for (int k = 0; k < 6; k++) sf->kinem[k] = s.kin[k];
+                sf->a0 = s.a0; sf->a0dot = s.a0dot; sf->a0prev = s.a0prev;
+            } else {
+                sf->levflag = hms[q].levflag;
+                for (int k = 0; k < 6; k++) sf->kinem[k] = hms[q].kin[k];
+                sf->a0 = hms[q].a0; sf->a0dot = hms[q].a0dot; sf->a0prev = hms[q].a0prev;
+            }
+            if (int rc = get(&sf->bv, s.wake.begin[3] + (int64_t)q * (nd - 1), nd - 1)) return rc;
+        }
+    }
     if (fl) {
-        if (int rc = get(&fl->tev, 0)) return rc;
-        if (int rc = get(&fl->lev, 1)) return rc;
-        if (int rc = get(&fl->extv, 2)) return rc;
+        for (int r = 0; r < 3; r++) {
+            unsflow_vorts *v = r == 0 ? &fl->tev : (r == 1 ? &fl->lev : &fl->extv);
+            if (int rc = get(v, s.wake.begin[r], s.wake.end[r] - s.wake.begin[r])) return rc;
+        }
         fl->u = s.fs[0]; fl->w = s.fs[1];
     }
     UF_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *sf, unsflow_field *fl) { return ldvm_get_state_impl(h, 1, sf, fl); }
+
+int unsflow_ldvm_multi_get_state(unsflow_ldvm *h, int32_t nsurf, unsflow_surf *surfs, unsflow_field *fl) {
+    return ldvm_get_state_impl(h, nsurf, surfs, fl);
 }
 
 int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {

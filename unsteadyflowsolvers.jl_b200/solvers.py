@@ -76,9 +76,15 @@ class LdvmHandle:
         self._h = C.c_void_p()
         self._keep = []
         self.surf, self.curfield = surf, curfield
-        s = surf_struct(surf, self._keep)
+        self.surfs = list(surf) if isinstance(surf, (list, tuple)) else [surf]
+        self.multi = isinstance(surf, (list, tuple))
         f = field_struct(curfield, self._keep)
-        cabi.check(cabi.lib().unsflow_ldvm_create(C.byref(self._h), C.byref(s), C.byref(f), C.byref(opts)))
+        if self.multi:   # ldvm(surf::Vector{TwoDSurf}, ...), solvers.jl:270
+            arr = (cabi.Surf * len(self.surfs))(*[surf_struct(q, self._keep) for q in self.surfs])
+            cabi.check(cabi.lib().unsflow_ldvm_multi_create(C.byref(self._h), len(self.surfs), arr, C.byref(f), C.byref(opts)))
+        else:
+            s = surf_struct(surf, self._keep)
+            cabi.check(cabi.lib().unsflow_ldvm_create(C.byref(self._h), C.byref(s), C.byref(f), C.byref(opts)))
 
     def close(self):
         if self._h:
@@ -105,7 +111,7 @@ class LdvmHandle:
         kinem.from_array(b)
 
     def run(self, nsteps):
-        mat = np.zeros((nsteps, 8), order="F")
+        mat = np.zeros((nsteps, 1 + 7 * len(self.surfs) if self.multi else 8), order="F")
         cabi.check(cabi.lib().unsflow_ldvm_run(self._h, nsteps, mat.ctypes.data_as(cabi.c_double_p)))
         return mat
 
@@ -121,21 +127,27 @@ class LdvmHandle:
 
     def download(self):
         """unsflow_ldvm_get_state -> mutate surf and curfield in place, like the reference."""
-        surf, fld = self.surf, self.curfield
+        fld = self.curfield
         nt, nl, ne = self.counts()
         keep = []
         for v, n in ((fld.tev, nt), (fld.lev, nl), (fld.extv, ne)):
             v.resize(n)
-        s = surf_struct(surf, keep)
-        f = field_struct(fld, keep)
-        cabi.check(cabi.lib().unsflow_ldvm_get_state(self._h, C.byref(s), C.byref(f)))
-        surf.levflag[0] = s.levflag
-        k = surf.kinem
-        k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = list(s.kinem)
-        surf.a0[0], surf.a0dot[0], surf.a0prev[0] = s.a0, s.a0dot, s.a0prev
+        structs = [surf_struct(q, keep) for q in self.surfs]     # keep: one bv entry per surface, in order
+        f = field_struct(fld, keep)                               # then tev, lev, extv
+        if self.multi:
+            arr = (cabi.Surf * len(structs))(*structs)
+            cabi.check(cabi.lib().unsflow_ldvm_multi_get_state(self._h, len(structs), arr, C.byref(f)))
+            structs = list(arr)
+        else:
+            cabi.check(cabi.lib().unsflow_ldvm_get_state(self._h, C.byref(structs[0]), C.byref(f)))
+        for surf, s in zip(self.surfs, structs):
+            surf.levflag[0] = s.levflag
+            k = surf.kinem
+            k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = list(s.kinem)
+            surf.a0[0], surf.a0dot[0], surf.a0prev[0] = s.a0, s.a0dot, s.a0prev
         fld.u[0], fld.w[0] = f.u, f.w
-        # _vorts_struct made copies: copy back (keep order: bv, tev, lev, extv)
-        for v, arrs in zip((surf.bv, fld.tev, fld.lev, fld.extv), keep):
+        # _vorts_struct made copies: copy back (keep order: bv per surface, tev, lev, extv)
+        for v, arrs in zip([q.bv for q in self.surfs] + [fld.tev, fld.lev, fld.extv], keep):
             v.assign(*arrs)
 
 
@@ -174,9 +186,16 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
                                   "(solvers.jl:150-155) and not supported")
     else:
         raise ValueError("invalid start flag, should be 0 or 1")  # solvers.jl:157
-    dt = dtstar * surf.c / surf.uref  # solvers.jl:161
+    multi = isinstance(surf, (list, tuple))
     two_dof = driver == cabi.DRIVER_LDVM2DOF
-    table = kinematics_table(surf, curfield, nsteps, dt, t, external=(driver != cabi.DRIVER_LAUTAT), two_dof=two_dof)
+    if multi:
+        if driver != cabi.DRIVER_LDVM:
+            raise TypeError("a Vector{TwoDSurf} is accepted by ldvm only (solvers.jl:270)")
+        dt = dtstar * min(q.c / q.uref for q in surf)  # solvers.jl:289
+        table = np.ascontiguousarray(np.stack([kinematics_table(q, curfield, nsteps, dt, t) for q in surf], axis=1))
+    else:
+        dt = dtstar * surf.c / surf.uref  # solvers.jl:161
+        table = kinematics_table(surf, curfield, nsteps, dt, t, external=(driver != cabi.DRIVER_LAUTAT), two_dof=two_dof)
     h = LdvmHandle(surf, curfield, _opts(driver, dt, nsteps, delvort, solve_mode))
     try:
         if two_dof:
@@ -195,7 +214,10 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
             if stop in write_steps:
                 h.download()
                 from .postprocess import writeStamp
-                writeStamp(_round_sig(table[stop - 1, 0], nround), table[stop - 1, 0], surf, curfield)
+                tstamp = float(table[stop - 1].reshape(-1)[0])
+                if multi:
+                    raise NotImplementedError("writeStamp for several surfaces (postprocess.jl:115-182) is not mirrored")
+                writeStamp(_round_sig(tstamp, nround), tstamp, surf, curfield)
         h.download()
         if two_dof:
             h.get_2dof(kinem)
@@ -203,6 +225,9 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
     finally:
         h.close()
     mat = np.vstack(mats) if mats else np.zeros((0, 8))
+    if multi and write_summary:
+        _write_results_summary(mat)
+        write_summary = False
     if write_summary:
         _write_results_summary(mat)
     return mat, surf, curfield
@@ -211,7 +236,9 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
 def ldvm(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
          maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
     """ldvm(surf::TwoDSurf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort;
-    maxwrite, nround) -> (mat, surf, curfield), solvers.jl:144-268"""
+    maxwrite, nround) -> (mat, surf, curfield), solvers.jl:144-268.  Passing a list of TwoDSurf
+    selects the multi-surface method ldvm(surf::Vector{TwoDSurf}, ...) of solvers.jl:270-445
+    (mat then has 1 + 7*nsurf columns)."""
     return _run(cabi.DRIVER_LDVM, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
                 delvort or delNone(), maxwrite, nround, solve_mode, write_summary=write_summary)
 
