@@ -60,3 +60,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the reference CPU path = oracle port on the host cores) prints
+    exactly one JSON line on stdout with the contract keys; tiny sample so it takes < 2 s"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "20000",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 1e7 and d["unit"] == "interactions/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
