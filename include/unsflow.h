@@ -205,6 +205,9 @@ int unsflow_ldvm_batch_timing(float *ms_kernel);
 /* DFMA-chain microbenchmark: measured FP64 (non-tensor) peak of the current device, TFLOP/s
  * (2 flop per DFMA).  This is the roofline denominator for the induction kernels. */
 int unsflow_fp64_peak(double *tflops, double *sm_mhz_est);
+/* bound-point sweep (update_indbound, calcs.jl:35-38) micro-benchmark on synthetic device-resident
+ * sources: best-of-reps milliseconds of the dedicated sweep kernel and of the generic kernel */
+int unsflow_bench_sweep(int64_t n, int ndiv, int reps, float *ms_sweep, float *ms_generic);
 /* relative error statistics of the rsqrt seed / refined value over a log-spaced q sweep */
 int unsflow_rsqrt_probe(int64_t nsamples, double qmin, double qmax, double *max_rel_seed,
                         double *max_rel_newton, double *max_rel_cubic);

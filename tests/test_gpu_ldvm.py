@@ -167,7 +167,7 @@ def test_chunked_runs_equal_one_run(gpu_lib, uf):
 
 
 def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
-    """with >= 65536 free vortices the stepper switches to the symmetric pair-tile kernel;
+    """with >= 36864 free vortices the stepper switches to the symmetric pair-tile kernel;
     it must agree with the (oracle-validated) direct kernel on the same state.  Run in two
     subprocesses because the switch threshold is read once per process."""
     import subprocess, sys, textwrap
@@ -186,7 +186,7 @@ def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
     """)
     import tempfile
     outs = []
-    for thr in ("65536", "100000000"):
+    for thr in ("36864", "100000000"):
         f = tempfile.mktemp(suffix=".npz")
         env = dict(os.environ, UNSFLOW_SYM_THRESHOLD=thr)
         subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))

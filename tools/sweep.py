@@ -35,3 +35,14 @@ for n in (1000, 3000, 10000, 30000, 100000, 300000, 1000000):
         rate = float(n) * (n + nbv) * steps / (ms.value * 1e-3)
         print(f"| {n} | {name} | {ms.value / steps:.3f} | {rate:.3e} | {13 * rate / 1e12:.2f} | {13 * rate / 1e12 / tf.value:.3f} |", flush=True)
         L.unsflow_wake_destroy(h)
+
+# ---- bound-point sweep (update_indbound): 70 targets x N sources, device-resident ---------------
+print()
+print("| N sources | kernel | ms | sources/s | HBM GB/s (24 B/source) | alg. TFLOP/s | of measured FP64 peak |")
+print("|---|---|---|---|---|---|---|")
+for n in (10000, 100000, 1000000, 4000000):
+    a, b = C.c_float(), C.c_float()
+    cabi.check(L.unsflow_bench_sweep(n, 70, 5, C.byref(a), C.byref(b)))
+    for name, ms in (("k_sweep", a.value), ("generic direct", b.value)):
+        rate = n / (ms * 1e-3)
+        print(f"| {n} | {name} | {ms:.4f} | {rate:.3e} | {24 * rate / 1e9:.1f} | {13 * 70 * rate / 1e12:.2f} | {13 * 70 * rate / 1e12 / tf.value:.3f} |", flush=True)

@@ -1,6 +1,7 @@
 // api.cu -- C-ABI plumbing, stateless host-buffer entry points and measurement helpers.
 #include "../../include/unsflow.h"
 #include "induce_sym.cuh"
+#include "sweep.cuh"
 #include "runtime.h"
 #include <cstdarg>
 #include <cstdlib>
@@ -127,10 +128,13 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     for (int k = 0; k < ng; k++) ns += g[k].n;
     InducePlan plan = plan_induce(nt, 1, ns, ng, sm_count(), 64);
     // large uniform-core mutual induction: symmetric pair-tile kernel (induce_sym.cuh)
-    const bool sym = self_targets && uni && g[0].n >= 65536;
+    const bool sym = self_targets && uni && g[0].n >= 36864;
     const int symR = sym_rows_per_thread(g[0].n);
     const int ctas = sym ? sym_ctas(symR) : 0;
     if (sym) { plan.S = ctas; }
+    // few targets against many sources (update_indbound): dedicated sweep kernel
+    const bool sweep = !sym && !self_targets && nt <= 256 && ns >= 2048 && sweep_supported((int)nt);
+    if (sweep) plan.S = (int)std::max<int64_t>(1, std::min<int64_t>((ns + kTS - 1) / kTS + ng, 256));
     if (d_part.alloc(sym ? (int64_t)ctas * 2 * tot : 2 * (int64_t)plan.S * ntp)) return 2;
     if (d_out.alloc(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
 
@@ -149,6 +153,8 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
         sa.reg = d_reg.p; sa.nreg = 1; sa.bv_reg = ng > 1 ? 1 : -1;
         sa.vc4 = a.vc4_uniform; sa.P = d_part.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
         if (int rc = launch_induce_sym(sa, symR, rsqrt_order(), st)) return rc;
+    } else if (sweep) {
+        if (int rc = launch_sweep(a, (int)nt, plan.S, uni, st)) return rc;
     } else {
         if (int rc = launch_induce_direct(a, plan, uni, rsqrt_order(), st)) return rc;
     }
@@ -331,6 +337,61 @@ int unsflow_fp64_peak(double *tflops, double *sm_mhz_est) {
     cudaEventDestroy(e1);
     *tflops = best;
     if (sm_mhz_est) *sm_mhz_est = mhz;
+    return 0;
+}
+
+// bound-point sweep micro-benchmark: ndiv targets x n synthetic sources resident in HBM; times the
+// dedicated k_sweep and the generic one-target-per-thread kernel (CUDA events, best of reps)
+__global__ void k_fill_sweep(double *x, double *z, double *g, long long n, long long npad) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += (long long)gridDim.x * blockDim.x) {
+        const bool ok = i < n;
+        x[i] = ok ? 0.5 + 0.015 * (double)i : 0.0;
+        z[i] = ok ? 0.3 * sin(0.37 * (double)i) : 0.0;
+        g[i] = ok ? 0.01 * cos(0.11 * (double)i) : 0.0;
+    }
+}
+
+int unsflow_bench_sweep(int64_t n, int ndiv, int reps, float *ms_sweep, float *ms_generic) {
+    UF_CHECK(n > 0 && ndiv >= 1 && ndiv <= 256 && reps >= 1 && ms_sweep && ms_generic, "unsflow_bench_sweep: bad arguments");
+    if (int rc = require_device()) return rc;
+    const int64_t npad = round_up(n, kSymTB), ndp = round_up(ndiv, 8);
+    DevBuf<double> src, tgt, part;
+    DevBuf<Regions> reg;
+    const int S = (int)std::max<int64_t>(1, std::min<int64_t>((n + kTS - 1) / kTS + 1, 592));
+    InducePlan plan = plan_induce(ndiv, 1, n, 1, sm_count(), 592);
+    const int Smax = std::max(S, plan.S);
+    if (src.alloc(3 * npad) || tgt.alloc(2 * ndp) || part.alloc(2 * (int64_t)Smax * ndp) || reg.alloc(2)) return 2;
+    k_fill_sweep<<<sm_count() * 4, 256>>>(src.p, src.p + npad, src.p + 2 * npad, n, npad);
+    std::vector<double> ht((size_t)(2 * ndp), 0.0);
+    for (int i = 0; i < ndiv; i++) { ht[i] = -1.0 + (double)i / ndiv; ht[ndp + i] = 0.02 * i / ndiv; }
+    UF_CUDA(cudaMemcpy(tgt.p, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice));
+    Regions hr[2];
+    memset(hr, 0, sizeof(hr));
+    hr[0].end[0] = n; hr[1].end[0] = ndiv;
+    UF_CUDA(cudaMemcpy(reg.p, hr, sizeof(hr), cudaMemcpyHostToDevice));
+    InduceArgs a;
+    a.sx = src.p; a.sz = src.p + npad; a.sg = src.p + 2 * npad; a.svc4 = nullptr;
+    a.tx = tgt.p; a.tz = tgt.p + ndp; a.sreg = reg.p; a.treg = reg.p + 1; a.nsreg = 1; a.ntreg = 1;
+    a.vc4_uniform = 1.6e-7; a.pu = part.p; a.pw = part.p + (int64_t)Smax * ndp; a.tstride = ndp;
+    cudaEvent_t e0, e1;
+    UF_CUDA(cudaEventCreate(&e0));
+    UF_CUDA(cudaEventCreate(&e1));
+    float best[2] = {1e30f, 1e30f};
+    for (int which = 0; which < 2; which++)
+        for (int r = 0; r < reps + 2; r++) {
+            UF_CUDA(cudaEventRecord(e0));
+            if (which == 0) { if (int rc = launch_sweep(a, ndiv, S, true, 0)) return rc; }
+            else { if (int rc = launch_induce_direct(a, plan, true, 3, 0)) return rc; }
+            UF_CUDA(cudaEventRecord(e1));
+            UF_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            UF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (r >= 2) best[which] = std::min(best[which], ms);
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_sweep = best[0];
+    *ms_generic = best[1];
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // induce.cu -- launch plumbing for the induction kernels (see induce.cuh).
 #define UNSFLOW_INDUCE_KERNELS
 #include "induce_sym.cuh"
+#include "sweep.cuh"
 #include "runtime.h"
 #include <algorithm>
 #include <cstdlib>
@@ -52,6 +53,23 @@ int launch_induce_direct(const InduceArgs &a, const InducePlan &p, bool uniform,
             default: set_error("launch_induce_direct: unsupported R=%d", p.R); return 1;
         }
     }
+    UF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sweep_supported(int ndiv) { return ndiv >= 1 && ndiv <= 256; }
+
+template <int RT>
+static void launch_sweep_rt(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
+    if (uniform) k_sweep<RT, true><<<S, kThreads, 0, st>>>(a, ndiv);
+    else k_sweep<RT, false><<<S, kThreads, 0, st>>>(a, ndiv);
+}
+
+int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
+    if (!sweep_supported(ndiv)) { set_error("launch_sweep: ndiv=%d not supported", ndiv); return 1; }
+    if (ndiv <= 9 * kSweepTG) launch_sweep_rt<9>(a, ndiv, S, uniform, st);
+    else if (ndiv <= 16 * kSweepTG) launch_sweep_rt<16>(a, ndiv, S, uniform, st);
+    else launch_sweep_rt<32>(a, ndiv, S, uniform, st);
     UF_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@
 // head (popfirst! of the Spalart merge = zero the strength and advance the head).
 #include "../../include/unsflow.h"
 #include "induce_sym.cuh"
+#include "sweep.cuh"
 #include "runtime.h"
 #include <algorithm>
 #include <cmath>
@@ -29,7 +30,7 @@ constexpr int kNaMax = 128;    // max naterm
 constexpr int kSolveThreads = 256;
 // free vortices from which the pair-tile kernel wins (env UNSFLOW_SYM_THRESHOLD overrides, for tests)
 static int64_t sym_threshold() {
-    static int64_t v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? (int64_t)atoll(e) : (int64_t)65536; }();
+    static int64_t v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? (int64_t)atoll(e) : (int64_t)36864; }();
     return v;
 }
 
@@ -1350,7 +1351,14 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         a.sreg = &h->st.p->wake; a.treg = &h->st.p->bnd; a.nsreg = 3; a.ntreg = 1;
         a.vc4_uniform = h->vc4u;
         a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
-        if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
+        if (!multi && sweep_supported(h->ndiv)) {
+            // dedicated few-targets kernel (sweep.cuh): one partial plane per block
+            const long long tsrc = (nwake_ub + kTS - 1) / kTS + 3;
+            p2.S = (int)std::max<long long>(1, std::min<long long>(tsrc, h->S2max));
+            if (int rc = launch_sweep(a, h->ndiv, p2.S, h->uniform, st)) return rc;
+        } else {
+            if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
+        }
         h->dev.S2 = p2.S;
         h->launches++;
     }

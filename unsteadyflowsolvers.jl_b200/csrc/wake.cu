@@ -130,7 +130,7 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     const int64_t my_t = std::max<int64_t>(0, std::min(n, (rank + 1) * w->slice) - rank * w->slice);
     w->plan = plan_induce(my_t, 1, n + nbv, 2, sm_count(), 64);
     if (w->part.alloc(2 * (int64_t)w->plan.S * w->npad)) return fail(2);
-    w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= 65536);
+    w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= 36864);
     w->symR = sym_rows_per_thread(n);
     w->ctas = sym_ctas(w->symR);
     if (w->want_sym && w->planes.alloc((int64_t)w->ctas * 2 * w->tot)) return fail(2);
