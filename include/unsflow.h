@@ -162,6 +162,12 @@ int unsflow_ldvm_create(unsflow_ldvm **out, const unsflow_surf *surf, const unsf
  * t = t + dt (solvers.jl:180).  Rows are consumed one per step.  For ldvm2DOF only the
  * columns t, U_ext, W_ext are read (alpha/h come from the structural solve on device). */
 int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *table);
+/* Multi-GPU stepping (one process per GPU, call once before the first run with the same state on
+ * every rank): the pair tiles of the wake roll-up are split over ranks and the partial velocities
+ * are summed with an NCCL all-reduce each step; the O(ndiv) kernels and the bound sweep are
+ * replicated bit-identically, so every rank returns the same mat and state.  nccl_unique_id:
+ * 128 bytes from unsflow_nccl_unique_id() of rank 0.  Needs a uniform core radius. */
+int unsflow_ldvm_set_parallel(unsflow_ldvm *h, int rank, int nranks, const void *nccl_unique_id);
 /* TwoDOFPar (typedefs.jl:178-190, 11 doubles in field order) and KinemPar2DOF
  * (typedefs.jl:193-220, 22 doubles in field order) for ldvm2DOF */
 int unsflow_ldvm_set_2dof(unsflow_ldvm *h, const double *strpar11, const double *kinem22);

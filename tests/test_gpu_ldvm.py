@@ -316,3 +316,18 @@ def test_multi_surface_one_surface_equals_single(gpu_lib, uf):
     m1, _, _ = uf.ldvm(a, fa, 40, 0.012, write_summary=False)
     m2, _, _ = uf.ldvm(b, fb, 40, 0.012, write_summary=False)
     assert m1.shape == (40, 8) and np.max(np.abs(m1 - m2)) <= 1e-12
+
+
+def test_multi_gpu_stepper_lockstep(gpu_lib, uf):
+    """needs >= 2 GPUs on the box (skipped otherwise; run by hand with gpurun --gpus 2, log in
+    profiles/): roll-up pair tiles split over ranks + NCCL all-reduce, replicas bit-identical"""
+    import subprocess, sys
+    if uf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(__file__))
+    env = dict(os.environ, MG_WAKE="60000", MG_STEPS="4")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "ldvm_multigpu_check.py")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bit-identical across ranks True" in out.stdout

@@ -94,6 +94,7 @@ def lib():
         "unsflow_ldvm_multi_create": [C.POINTER(vp), C.c_int32, C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts)],
         "unsflow_ldvm_multi_get_state": [vp, C.c_int32, C.POINTER(Surf), C.POINTER(Field)],
         "unsflow_ldvm_set_kinematics": [vp, i64, d],
+        "unsflow_ldvm_set_parallel": [vp, C.c_int, C.c_int, vp],
         "unsflow_ldvm_set_2dof": [vp, d, d],
         "unsflow_ldvm_get_2dof": [vp, d],
         "unsflow_ldvm_run": [vp, i64, d],

@@ -16,6 +16,7 @@
 #include "../../include/unsflow.h"
 #include "induce_sym.cuh"
 #include "sweep.cuh"
+#include "nccl_dl.h"
 #include "runtime.h"
 #include <algorithm>
 #include <cmath>
@@ -1105,6 +1106,10 @@ struct unsflow_ldvm {
     int64_t readback_step = 0;
     int64_t launches = 0;
     float last_ms = 0;
+    // multi-GPU: pair tiles of the roll-up split over ranks, everything else replicated bit-identically
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    DevBuf<double> vsum;      // [2][tot] raw plane sums exchanged by all-reduce
     // CUDA-graph cache for the launch-bound regime
     cudaGraphExec_t gexec = nullptr;
     int64_t gkey_t = -1, gkey_l = -1;
@@ -1122,6 +1127,7 @@ extern "C" {
 int unsflow_ldvm_destroy(unsflow_ldvm *h) {
     if (!h) return 0;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1312,6 +1318,24 @@ int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *ta
     return 0;
 }
 
+int unsflow_ldvm_set_parallel(unsflow_ldvm *h, int rank, int nranks, const void *nccl_unique_id) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_set_parallel: null handle");
+    UF_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "unsflow_ldvm_set_parallel: bad rank %d / %d", rank, nranks);
+    UF_CHECK(h->steps_done == 0 && h->comm == nullptr, "unsflow_ldvm_set_parallel: call once, before the first run");
+    if (nranks == 1) return 0;
+    UF_CHECK(nccl_unique_id != nullptr, "unsflow_ldvm_set_parallel: nccl_unique_id required");
+    UF_CHECK(h->uniform, "unsflow_ldvm_set_parallel: the multi-GPU roll-up needs a uniform core radius");
+    const NcclApi *nc = nccl_api();
+    if (!nc) return 4;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    if (nc->CommInitRank(&h->comm, nranks, id, rank) != ncclSuccess) { set_error("ncclCommInitRank failed"); return 4; }
+    if (h->vsum.alloc(2 * h->tot) || h->vsum.zero(h->stream)) return 2;
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    h->rank = rank; h->nranks = nranks;
+    return 0;
+}
+
 int unsflow_ldvm_set_2dof(unsflow_ldvm *h, const double *sp11, const double *k22) {
     UF_CHECK(h && sp11 && k22, "unsflow_ldvm_set_2dof: null argument");
     UF_CUDA(cudaMemcpyAsync(h->st.p->sp, sp11, sizeof(double) * 11, cudaMemcpyHostToDevice, h->stream));
@@ -1389,7 +1413,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         SymArgs sa;
         sa.x = h->dev.wx; sa.z = h->dev.wz; sa.g = h->dev.wg;
         sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
-        sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = 0; sa.nranks = 1;
+        sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = h->rank; sa.nranks = h->nranks;
         if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
     } else {
         if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
@@ -1401,6 +1425,33 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     f.treg = &h->st.p->wake; f.ntreg = 3;
     f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
     f.fs = h->st.p->fs; f.dt = h->opts.dt;
+    if (sym && h->nranks > 1) {
+        // every rank holds the partial velocities of ITS share of the pair tiles for all vortices:
+        // plain plane sums -> NCCL all-reduce over the live slab ranges -> 1/2pi, free stream, convection.
+        // The all-reduce returns identical bits on every rank, so the replicated state stays in lockstep.
+        FinishArgs fr = f;
+        fr.raw = 1; fr.vx = h->vsum.p; fr.vz = h->vsum.p + tot;
+        if (int rc = launch_induce_finish(fr, nwake_ub, st)) return rc;
+        const NcclApi *nc = nccl_api();
+        if (!nc) return 4;
+        const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
+        const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
+        if (nc->GroupStart() != ncclSuccess) { set_error("ncclGroupStart failed"); return 4; }
+        for (int r = 0; r < 3; r++) {
+            const int64_t cnt = std::min(hi[r], tot) - lo[r];
+            if (cnt <= 0) continue;
+            for (int c = 0; c < 2; c++) {
+                double *p = h->vsum.p + c * tot + lo[r];
+                if (nc->AllReduce(p, p, (size_t)cnt, ncclDouble, ncclSum, h->comm, st) != ncclSuccess) { set_error("ncclAllReduce failed"); return 4; }
+            }
+        }
+        if (nc->GroupEnd() != ncclSuccess) { set_error("ncclGroupEnd failed"); return 4; }
+        FinishArgs f2 = f;
+        f2.pu = h->vsum.p; f2.pw = h->vsum.p + tot; f2.tstride = 0; f2.S = 1;
+        if (int rc = launch_induce_finish(f2, nwake_ub, st)) return rc;
+        h->launches += 3;
+        return 0;
+    }
     if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
     h->launches += 2;
     return 0;
@@ -1473,7 +1524,17 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
             h->steps_done++;
             is++;
         }
-        if (!h->readback_pending && h->steps_done - h->readback_step >= 64) {
+        if (h->nranks > 1) {
+            // grid sizes must be identical on all ranks (they fix the grouping of partial sums, hence the
+            // bits): no timing-dependent read-back; a synchronous one at fixed step counts instead
+            if (h->steps_done - h->readback_step >= 256) {
+                StepState sx;
+                if (int rc = ldvm_sync_counts(h, &sx)) return rc;
+                h->known_step = h->readback_step = h->steps_done;
+                h->known_ntev_end = sx.wake.end[0] - h->off_t;
+                h->known_nlev_end = sx.wake.end[1] - h->off_l;
+            }
+        } else if (!h->readback_pending && h->steps_done - h->readback_step >= 64) {
             UF_CUDA(cudaMemcpyAsync(h->pinned, h->st.p, sizeof(StepState), cudaMemcpyDeviceToHost, st));
             UF_CUDA(cudaEventRecord(h->evc, st));
             h->readback_pending = true;

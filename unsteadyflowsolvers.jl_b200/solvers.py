@@ -101,6 +101,10 @@ class LdvmHandle:
         t = cabi.f64(table)
         cabi.check(cabi.lib().unsflow_ldvm_set_kinematics(self._h, t.shape[0], cabi.dptr(t)))
 
+    def set_parallel(self, rank, nranks, nccl_unique_id):
+        """unsflow_ldvm_set_parallel: split the roll-up pair tiles over `nranks` GPUs (one process each)"""
+        cabi.check(cabi.lib().unsflow_ldvm_set_parallel(self._h, rank, nranks, nccl_unique_id))
+
     def set_2dof(self, strpar: TwoDOFPar, kinem: KinemPar2DOF):
         a, b = strpar.as_array(), kinem.as_array()
         cabi.check(cabi.lib().unsflow_ldvm_set_2dof(self._h, cabi.dptr(a), cabi.dptr(b)))
