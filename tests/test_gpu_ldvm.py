@@ -331,3 +331,22 @@ def test_multi_gpu_stepper_lockstep(gpu_lib, uf):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "bit-identical across ranks True" in out.stdout
+
+
+def test_nlsolve_mode_other_drivers(gpu_lib, uf, oracle):
+    """UNSFLOW_SOLVE_NLSOLVE (stale finite-difference probe state) on ldvm2DOF and
+    on the multi-surface driver, against the oracle's full trust-region emulation"""
+    cabi = uf._cabi
+    surf, fld, strpar, kin0 = c5_2dof(uf)
+    n = 60
+    k_or = copy.deepcopy(kin0)
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM2DOF, n, 0.015,
+                            twodof=(strpar, k_or), solver_mode=1)
+    mat, surf, fld = uf.ldvm2DOF(surf, fld, strpar, kin0, n, 0.015, solve_mode=cabi.SOLVE_NLSOLVE, write_summary=False)
+    assert np.max(np.abs(mat - omat)) <= 1e-7
+    surfs, fld = _tandem(uf), uf.TwoDFlowField()
+    tabs = np.stack([uf.kinematics_table(s, fld, n, 0.012) for s in surfs], axis=1)
+    omat = oracle.MultiSim(surfs, fld).run(tabs, 0.012, solver_mode=1)
+    mat, surfs, fld = uf.ldvm(surfs, fld, n, 0.012, solve_mode=cabi.SOLVE_NLSOLVE, write_summary=False)
+    assert len(fld.lev) > 0
+    assert np.max(np.abs(mat - omat)) <= 1e-7

@@ -835,6 +835,39 @@ __device__ void mstep_solve(const LdvmDev &d) {
             }
             __syncthreads();
         }
+        if (nshed > 0 && !shed[q]) {
+            // KelvinKuttaMult re-solves the TEV of a non-shedding surface too (typedefs.jl:413-417):
+            // same 1x1 system on the base left by the first solve (identical root unless that base
+            // carries the stale probe offset of the NLsolve emulation)
+            const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
+            for (int i = tid; i < nd; i += blockDim.x) {
+                const int t = q * nd + i;
+                unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
+                uind[i] -= gt * uT[i]; wind[i] -= gt * wT[i];
+                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+                dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
+            }
+            __syncthreads();
+            for (int k = warp; k < 4; k += nwarps) {
+                const double v = warp_trapz_cos((k & 2) ? dw1 : dw, dth, d.costab + (k & 1) * nd, nd);
+                if (lane == 0) sc[k] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
+                const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
+                sc[8] = -(K0 - Kp) / (K1 + 1.0);
+            }
+            __syncthreads();
+            gt = sc[8];
+            for (int i = tid; i < nd; i += blockDim.x) {
+                const int t = q * nd + i;
+                uind[i] += gt * uT[i]; wind[i] += gt * wT[i];
+                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+                d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
+            }
+            __syncthreads();
+        }
         // final Fourier coefficients of this surface from its final downwash
         for (int n = warp; n <= na; n += nwarps) {
             const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
