@@ -190,6 +190,21 @@ int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *surf, unsflow_field *f
 int unsflow_ldvm_multi_create(unsflow_ldvm **out, int32_t nsurf, const unsflow_surf *surfs,
                               const unsflow_field *field, const unsflow_opts *opts);
 int unsflow_ldvm_multi_get_state(unsflow_ldvm *h, int32_t nsurf, unsflow_surf *surfs, unsflow_field *field);
+/* LVE(surf, curfield, nsteps, dtstar, ...)  src/lowOrder2D/LVE.jl:6-302 (lumped-vortex-element panel
+ * solver).  `surf` supplies the panel geometry (x, cam), pvt, lespcrit, initial kinem; ifr_field is
+ * the (normally empty) inertial-frame wake; ifr_xend, ifr_camend = x[end], cam[end] and ifr_u0,
+ * ifr_hdot0 = kinem.u, kinem.hdot of the reference's auxiliary IFR_surf (LVE.jl:17); rho = surf.rho;
+ * lev_stop = LEV_Stop; opts.dt = dtstar (LVE does not rescale it), opts.max_steps = nsteps + 1.
+ * unsflow_ldvm_set_kinematics takes (nsteps + 2) x 9 rows [t, alpha, h, alphadot, hdot, u, udot, X0, Z0]
+ * (X0 = -kindef.u(t) t, Z0 = kindef.h(t), calcs.jl:654-656); one unsflow_ldvm_run step = one loop
+ * iteration i = 0..nsteps, each returning a row of NINE columns [t, alpha(deg), h, u, a0, cl, cd, cm, lev]
+ * (lev = 1 when an LEV was ejected in that iteration; zeros in the load columns for i = 0, where the
+ * reference records nothing, LVE.jl:203).  The wake returned by
+ * unsflow_ldvm_get_state is IFR_field; bv holds the inertial-frame bound vortices (IFR_surf.bv). */
+int unsflow_lve_create(unsflow_ldvm **out, const unsflow_surf *surf, const unsflow_field *ifr_field,
+                       const unsflow_opts *opts, double rho, double lev_stop, double ifr_xend,
+                       double ifr_camend, double ifr_u0, double ifr_hdot0);
+int unsflow_lve_get_circ(unsflow_ldvm *h, double *circ_ndiv, double *gamma_crit);
 /* CUDA-event milliseconds of the last unsflow_ldvm_run and number of kernel launches in it */
 int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches);
 int unsflow_ldvm_destroy(unsflow_ldvm *h);

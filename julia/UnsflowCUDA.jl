@@ -299,4 +299,69 @@ function ldvm(surf::Vector{TwoDSurf}, curfield::TwoDFlowField, nsteps::Int64 = 5
     mat, surf, curfield
 end
 
+# ---- LVE(surf, curfield, nsteps, dtstar, ...)  replaces the time loop of LVE.jl:6-302 ---------------
+# (plotting / animation outputs are not produced: frames = 0, anim and wflag must be false)
+function LVE(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, frameCnt = 20, view = "square",
+             LEV_Stop = 1000, anim = false, animStep = 30, wflag = false, writeInterval = 50)
+    (anim || wflag) && error("UnsflowCUDA.LVE: anim / wflag are host-side plotting, use UnsteadyFlowSolvers.LVE")
+    IFR_surf = TwoDSurf(surf.coord_file, surf.pvt, surf.kindef, surf.lespcrit; ndiv = surf.ndiv, camberType = "linear")  # LVE.jl:17
+    IFR_field = TwoDFlowField()
+    ds = sqrt.((surf.x[1:end-1] - surf.x[2:end]).^2 + (surf.cam[1:end-1] - surf.cam[2:end]).^2)                          # :29-41
+    cam_slope = asind.((surf.cam[2:end] - surf.cam[1:end-1]) ./ ds)
+    vor_loc = hcat(surf.x[1:end-1] + .25 .* ds .* cosd.(cam_slope), surf.cam[1:end-1] + .25 .* ds .* sind.(cam_slope))
+    UFS.refresh_vortex(surf, vor_loc)                                                                                    # :55
+    # (nsteps + 2) rows [t, alpha, h, alphadot, hdot, u, udot, X0, Z0]: iterations i = 0..nsteps and t + dtstar of the last
+    tab = zeros(9, nsteps + 2); s = deepcopy(surf); t = -dtstar
+    for i = 1:nsteps+2
+        t += dtstar
+        UFS.update_kinem(s, t); k = s.kinem
+        tab[:, i] = [t, s.kindef.alpha(t), k.h, k.alphadot, k.hdot, k.u, k.udot, -s.kindef.u(t) * t, s.kindef.h(t)]
+    end
+    bv = SoA(surf.bv); e = SoA(0)
+    opts = Ref(COpts(0, 0, 0, -1, 0, 0.0, 0.0, dtstar, nsteps + 1))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    m9 = Matrix{Float64}(undef, nsteps + 1, 9)
+    circ = zeros(surf.ndiv); gcrit = Ref{Cdouble}(0.0)
+    tev = SoA(0); lev = SoA(0)
+    GC.@preserve surf bv e tab m9 circ begin
+        cs = Ref(csurf(surf, bv)); cf = Ref(CField(0.0, 0.0, cvorts(e), cvorts(e), cvorts(e)))
+        check(ccall((:unsflow_lve_create, LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Ptr{CSurf}, Ptr{CField}, Ptr{COpts}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble),
+            h, cs, cf, opts, surf.rho, LEV_Stop, IFR_surf.x[end], IFR_surf.cam[end], IFR_surf.kinem.u, IFR_surf.kinem.hdot))
+        try
+            check(ccall((:unsflow_ldvm_set_kinematics, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], nsteps + 2, tab))
+            check(ccall((:unsflow_ldvm_run, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), h[], nsteps + 1, m9))
+            nt = Ref{Int64}(0); nl = Ref{Int64}(0); ne = Ref{Int64}(0)
+            check(ccall((:unsflow_ldvm_counts, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), h[], nt, nl, ne))
+            tev = SoA(nt[]); lev = SoA(nl[]); ibv = SoA(surf.ndiv - 1)
+            bx = copy(surf.bnd_x); bz = copy(surf.bnd_z)
+            GC.@preserve tev lev ibv begin
+                cs2 = Ref(csurf(surf, ibv)); cf2 = Ref(CField(0.0, 0.0, cvorts(tev), cvorts(lev), cvorts(e)))
+                check(ccall((:unsflow_ldvm_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{CSurf}, Ptr{CField}), h[], cs2, cf2))
+                k = surf.kinem; c2 = cs2[]
+                k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = c2.kinem
+                surf.levflag[1] = c2.levflag; surf.a0[1] = c2.a0
+            end
+            surf.bnd_x[:] = bx; surf.bnd_z[:] = bz                       # LVE never touches surf.bnd_x/z
+            check(ccall((:unsflow_lve_get_circ, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], circ, gcrit))
+            unpack!(IFR_field.tev, tev, nt[]); unpack!(IFR_field.lev, lev, nl[])
+        finally
+            ccall((:unsflow_ldvm_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
+        end
+    end
+    for j = 1:surf.ndiv-1
+        surf.bv[j].s = circ[j]                                              # LVE.jl:156
+    end
+    # curfield = body-frame twin of IFR_field at t + dtstar (LVE.jl:238-242)
+    resize!(curfield.tev, 0); resize!(curfield.lev, 0)
+    for q in IFR_field.tev; push!(curfield.tev, TwoDVort(0, 0, q.s, 0.02 * surf.c, 0., 0.)); end
+    for q in IFR_field.lev; push!(curfield.lev, TwoDVort(0, 0, q.s, 0.02 * surf.c, 0., 0.)); end
+    UFS.vor_BFR(surf, tab[1, end], IFR_field, curfield)
+    mat = m9[2:end, 1:8]
+    TEVhist = hcat(tab[1, 1:nsteps+1], map(q -> q.s, IFR_field.tev)[1:nsteps+1])
+    shed = findall(m9[:, 9] .> 0.5)
+    LEVhist = hcat(tab[1, shed], map(q -> q.s, IFR_field.lev)[1:length(shed)])
+    return 0, IFR_field, mat, TEVhist, LEVhist
+end
+
 end # module

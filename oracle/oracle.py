@@ -297,3 +297,48 @@ class MultiSim:
         lib().o_msim_get_vorts(self.h, C.c_int(fam), _p(v))
         v = v.reshape(-1)[: 6 * n].reshape(6, n) if n else np.zeros((6, 0))
         return dict(zip(("x", "z", "s", "vc", "vx", "vz"), v))
+
+
+class LveSim:
+    """Oracle state of LVE (src/lowOrder2D/LVE.jl:6-302)."""
+
+    def __init__(self, surf, ifr_surf, lev_stop=1000.0):
+        L = lib()
+        L.o_lve_create.restype = C.c_void_p
+        L.o_lve_count.restype = C.c_long
+        self.nd = surf.ndiv
+        p = pack_surf(surf)
+        self.h = C.c_void_p(L.o_lve_create(C.c_int(surf.ndiv), C.c_int(surf.naterm), _p(p), C.c_double(surf.rho), C.c_double(lev_stop),
+                                           C.c_double(float(ifr_surf.x[-1])), C.c_double(float(ifr_surf.cam[-1])),
+                                           C.c_double(ifr_surf.kinem.u), C.c_double(ifr_surf.kinem.hdot)))
+
+    def close(self):
+        if self.h:
+            lib().o_lve_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, table, nsteps, dtstar):
+        table = _f(table)
+        assert table.shape == (nsteps + 2, 9)
+        mat = np.zeros((nsteps, 8))
+        assert lib().o_lve_run(self.h, C.c_long(nsteps), C.c_double(dtstar), _p(table), _p(mat)) == 0
+        return mat
+
+    def get_vorts(self, which):
+        n = lib().o_lve_count(self.h, C.c_int(which))
+        v = np.zeros((6, max(n, 1)))
+        lib().o_lve_get_vorts(self.h, C.c_int(which), _p(v))
+        v = v.reshape(-1)[: 6 * n].reshape(6, n) if n else np.zeros((6, 0))
+        return dict(zip(("x", "z", "s", "vc", "vx", "vz"), v))
+
+    def get_circ(self):
+        c = np.zeros(self.nd)
+        g = C.c_double(0)
+        lib().o_lve_get_circ(self.h, _p(c), C.byref(g))
+        return c, g.value

@@ -1338,3 +1338,291 @@ int o_msim_run(void *h, long nsteps, double dt, const double *kin, int solver_mo
         step_ldvm_multi(m, dt, kin + (size_t)is * ns * 9, solver_mode, dkind, dlimit, ddist, dtol, mat + (size_t)is * nc);
     return 0;
 }
+
+/* ==========================================================================================
+ * LVE -- lumped-vortex-element panel solver, src/lowOrder2D/LVE.jl:6-302 with its helpers
+ * src/lowOrder2D/calcs.jl:652-836.  Restated without the plotting /
+ * animation / global-variable scaffolding.  Two wakes are kept like the reference: IFR_field
+ * (inertial frame, convected by wakeroll) and curfield (body frame, positions refreshed by
+ * vor_BFR for the NEXT time level).
+ * kin table per iteration (nsteps+1 rows x 9): [t, alpha, h, alphadot, hdot, u, udot, X0, Z0]
+ * with alpha = kindef.alpha(t) (= kinem.alpha), X0 = -kindef.u(t)*t, Z0 = kindef.h(t)
+ * (calcs.jl:654-656), and one extra row for t + dtstar of the last iteration (vor_BFR).
+ * ======================================================================================== */
+typedef struct {
+    o_surf s;            /* body-frame surf (bv positions = vor_loc) */
+    o_vort *ifr_bv;      /* IFR_surf.bv */
+    o_field ifr, cur;    /* IFR_field, curfield */
+    int nd;
+    double *ds, *cam_slope_deg, *nx, *nz, *taux, *tauz, *vorx, *vorz, *colx, *colz;
+    double *prevCirc, *circChange, *circ, *RHS, *relx, *relz, *dp;
+    double gamma_crit, rho, lev_stop, t_start, te_x, te_cam, le_x, le_cam, ifr_u0, ifr_hdot0;
+} o_lve;
+
+/* IFR / BFR, calcs.jl:652-676 (alpha, X0, Z0 supplied from the table) */
+static void lve_ifr(double pvt, double al, double X0, double Z0, double x, double z, double *X, double *Z) {
+    *X = (x - pvt) * cos(al) + z * sin(al) + X0 + pvt;
+    *Z = -(x - pvt) * sin(al) + z * cos(al) + Z0;
+}
+static void lve_bfr(double pvt, double al, double X0, double Z0, double X, double Z, double *x, double *z) {
+    *x = (X - X0 - pvt) * cos(al) - (Z - Z0) * sin(al) + pvt;
+    *z = (X - X0 - pvt) * sin(al) + (Z - Z0) * cos(al);
+}
+
+/* dense solve a\RHS (Julia: LU with partial pivoting), n <= 256 */
+static void dense_solve(int n, const double *a /*row-major n x n*/, const double *b, double *x) {
+    double *A = (double *)malloc((size_t)n * (n + 1) * sizeof(double));
+    for (int i = 0; i < n; i++) { memcpy(A + (size_t)i * (n + 1), a + (size_t)i * n, (size_t)n * sizeof(double)); A[(size_t)i * (n + 1) + n] = b[i]; }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(A[(size_t)r * (n + 1) + c]) > fabs(A[(size_t)piv * (n + 1) + c])) piv = r;
+        if (piv != c) for (int j = 0; j <= n; j++) { double t = A[(size_t)c * (n + 1) + j]; A[(size_t)c * (n + 1) + j] = A[(size_t)piv * (n + 1) + j]; A[(size_t)piv * (n + 1) + j] = t; }
+        for (int r = c + 1; r < n; r++) {
+            const double f = A[(size_t)r * (n + 1) + c] / A[(size_t)c * (n + 1) + c];
+            for (int j = c; j <= n; j++) A[(size_t)r * (n + 1) + j] -= f * A[(size_t)c * (n + 1) + j];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double v = A[(size_t)i * (n + 1) + n];
+        for (int j = i + 1; j < n; j++) v -= A[(size_t)i * (n + 1) + j] * x[j];
+        x[i] = v / A[(size_t)i * (n + 1) + i];
+    }
+    free(A);
+}
+
+/* influence_coeff, calcs.jl:756-787 (+ the LEV modification of mod_influence_coeff :789-836) */
+static void lve_influence(const o_lve *L, double x_w, double z_w, double *a) {
+    const int nd = L->nd;
+    const double vc = L->s.bv[0].vc;
+    memset(a, 0, (size_t)nd * nd * sizeof(double));
+    for (int j = 0; j < nd; j++) a[(size_t)(nd - 1) * nd + j] = 1.;
+    for (int i = 0; i < nd - 1; i++)
+        for (int j = 0; j < nd; j++) {
+            const double t_x = L->colx[i], t_z = L->colz[i];
+            double u, w;
+            if (j < nd - 1) {
+                const double xdist = L->s.bv[j].x - t_x, zdist = L->s.bv[j].z - t_z;
+                const double distsq = xdist * xdist + zdist * zdist;
+                u = -zdist / (2 * O_PI * distsq);
+                w = xdist / (2 * O_PI * distsq);
+            } else {
+                const double xdist = x_w - t_x, zdist = z_w - t_z;
+                const double distsq = xdist * xdist + zdist * zdist;
+                u = -zdist / (2 * O_PI * sqrt(vc * vc * vc * vc + distsq * distsq));
+                w = xdist / (2 * O_PI * sqrt(vc * vc * vc * vc + distsq * distsq));
+            }
+            a[(size_t)i * nd + j] = u * L->nx[i] + w * L->nz[i];
+        }
+}
+
+void *o_lve_create(int ndiv, int naterm, const double *surfpack, double rho, double lev_stop,
+                   double ifr_xend, double ifr_camend, double ifr_u0, double ifr_hdot0) {
+    o_lve *L = (o_lve *)calloc(1, sizeof(o_lve));
+    o_sim *tmp = (o_sim *)o_sim_create(ndiv, naterm);
+    o_sim_set_surf(tmp, surfpack);
+    L->s = tmp->s;
+    free(tmp);
+    const int nd = L->nd = ndiv, np = ndiv - 1;
+    o_surf *s = &L->s;
+    L->rho = rho; L->lev_stop = lev_stop; L->t_start = 0;
+    L->te_x = ifr_xend; L->te_cam = ifr_camend; L->ifr_u0 = ifr_u0; L->ifr_hdot0 = ifr_hdot0;
+    L->le_x = s->x[0]; L->le_cam = s->cam[0];
+    double **arr[] = { &L->ds, &L->cam_slope_deg, &L->nx, &L->nz, &L->taux, &L->tauz, &L->vorx, &L->vorz, &L->colx, &L->colz,
+                       &L->prevCirc, &L->circChange, &L->circ, &L->RHS, &L->relx, &L->relz, &L->dp };
+    for (size_t k = 0; k < sizeof(arr) / sizeof(arr[0]); k++) *arr[k] = (double *)calloc((size_t)nd, sizeof(double));
+    L->ifr_bv = (o_vort *)calloc((size_t)np, sizeof(o_vort));
+    const double d2r = O_PI / 180.0;
+    for (int j = 0; j < np; j++) {                                   /* LVE.jl:29-47 */
+        const double dx = s->x[j] - s->x[j + 1], dc = s->cam[j] - s->cam[j + 1];
+        L->ds[j] = sqrt(dx * dx + dc * dc);
+        L->cam_slope_deg[j] = asin((s->cam[j + 1] - s->cam[j]) / L->ds[j]) / d2r;     /* asind */
+        const double sd = sin(L->cam_slope_deg[j] * d2r), cd = cos(L->cam_slope_deg[j] * d2r);   /* sind / cosd */
+        L->nx[j] = -sd; L->nz[j] = cd; L->taux[j] = cd; L->tauz[j] = sd;
+        L->vorx[j] = s->x[j] + .25 * L->ds[j] * cd; L->vorz[j] = s->cam[j] + .25 * L->ds[j] * sd;
+        L->colx[j] = s->x[j] + .75 * L->ds[j] * cd; L->colz[j] = s->cam[j] + .75 * L->ds[j] * sd;
+        s->bv[j].x = L->vorx[j]; s->bv[j].z = L->vorz[j];             /* refresh_vortex :55 */
+        L->ifr_bv[j] = s->bv[j];
+    }
+    const double x = 1 - 2 * L->ds[0] / s->c;                         /* :50-52 */
+    L->gamma_crit = s->lespcrit / 1.13 * (s->u * s->c * (acos(x) + sin(acos(x))));
+    return L;
+}
+
+void o_lve_destroy(void *h) {
+    o_lve *L = (o_lve *)h;
+    o_surf *s = &L->s;
+    free(s->theta); free(s->x); free(s->cam); free(s->cam_slope); free(s->bnd_x); free(s->bnd_z);
+    free(s->uind); free(s->wind); free(s->downwash); free(s->aterm); free(s->adot); free(s->aprev); free(s->bv);
+    free(L->ds); free(L->cam_slope_deg); free(L->nx); free(L->nz); free(L->taux); free(L->tauz); free(L->vorx); free(L->vorz);
+    free(L->colx); free(L->colz); free(L->prevCirc); free(L->circChange); free(L->circ); free(L->RHS); free(L->relx); free(L->relz);
+    free(L->dp); free(L->ifr_bv);
+    free(L->ifr.tev.v); free(L->ifr.lev.v); free(L->ifr.extv.v); free(L->cur.tev.v); free(L->cur.lev.v); free(L->cur.extv.v);
+    free(L);
+}
+
+/* iterations i = 0..nsteps of LVE.jl:60-298; kin has nsteps+2 rows (last = t+dtstar of the final
+ * iteration); mat = nsteps x 8 row-major [t, alpha(deg), h, u, a0, cl, cd, cm] */
+int o_lve_run(void *h, long nsteps, double dtstar, const double *kin, double *mat) {
+    o_lve *L = (o_lve *)h;
+    o_surf *s = &L->s;
+    const int nd = L->nd, np = nd - 1;
+    double *a = (double *)malloc((size_t)nd * nd * sizeof(double));
+    double *a1 = (double *)malloc((size_t)nd * sizeof(double));
+    const double d2r = O_PI / 180.0;
+    for (long i = 0; i <= nsteps; i++) {
+        const double *r = kin + 9 * i, *rn = kin + 9 * (i + 1);
+        const double t = r[0], al = r[1], X0 = r[7], Z0 = r[8];
+        s->alpha = r[1]; s->h = r[2]; s->alphadot = r[3]; s->hdot = r[4]; s->u = r[5]; s->udot = r[6];   /* update_kinem :64 */
+        for (int j = 0; j < np; j++)                                                                   /* :67-68 */
+            lve_ifr(s->pvt, al, X0, Z0, L->vorx[j], L->vorz[j], &L->ifr_bv[j].x, &L->ifr_bv[j].z);
+        {   /* place_tev2(IFR_surf, IFR_field, dtstar, t), calcs.jl:688-709 */
+            double TE_x, TE_z, xloc, zloc;
+            lve_ifr(s->pvt, al, X0, Z0, L->te_x, L->te_cam, &TE_x, &TE_z);
+            if (L->ifr.tev.n == 0) { xloc = TE_x + 0.5 * L->ifr_u0 * dtstar; zloc = TE_z + 0.5 * L->ifr_hdot0 * dtstar; }
+            else {
+                const o_vort *q = &L->ifr.tev.v[L->ifr.tev.n - 1];
+                xloc = TE_x + (1. / 3.) * (q->x - TE_x); zloc = TE_z + (1. / 3.) * (q->z - TE_z);
+            }
+            o_vort v = { xloc, zloc, 0., 0.02 * s->c, 0., 0. };
+            vec_push(&L->ifr.tev, v);
+        }
+        double x_w, z_w;
+        { const o_vort *q = &L->ifr.tev.v[L->ifr.tev.n - 1]; lve_bfr(s->pvt, al, X0, Z0, q->x, q->z, &x_w, &z_w); }   /* :74 */
+        lve_influence(L, x_w, z_w, a);                                                                 /* :75 */
+        double sp = 0; for (int j = 0; j < np; j++) sp += L->prevCirc[j];
+        L->RHS[nd - 1] = sp;                                                                           /* :78 */
+        if (L->cur.tev.n > 0) {                                                                        /* :80-82 */
+            long n = L->cur.tev.n + L->cur.lev.n;
+            o_vort *all = (o_vort *)malloc((size_t)n * sizeof(o_vort));
+            memcpy(all, L->cur.tev.v, (size_t)L->cur.tev.n * sizeof(o_vort));
+            memcpy(all + L->cur.tev.n, L->cur.lev.v, (size_t)L->cur.lev.n * sizeof(o_vort));
+            ind_vel_aos(all, n, L->colx, L->colz, np, s->uind, s->wind);
+            free(all);
+        }
+        for (int j = 0; j < np; j++) {                                                                 /* :83-90 */
+            const double ux = cos(al) * s->u - sin(al) * (-s->hdot), uz = sin(al) * s->u + cos(al) * (-s->hdot);
+            L->relx[j] = ux + (-s->alphadot * L->colz[j]);
+            L->relz[j] = uz + s->alphadot * (L->colx[j] - s->pvt);
+            L->RHS[j] = -((L->relx[j] + s->uind[j]) * L->nx[j] + (L->relz[j] + s->wind[j]) * L->nz[j]);
+        }
+        dense_solve(nd, a, L->RHS, L->circ);                                                           /* :93 */
+        for (int j = 0; j < np; j++) {                                                                 /* :96-100 */
+            double g1 = 0, g2 = 0;
+            for (int k = 0; k < j; k++) { g1 += L->prevCirc[k]; g2 += L->circ[k]; }
+            L->circChange[j] = (g2 - g1) / dtstar;
+        }
+        const double xx = 1 - 2 * L->ds[0] / s->c;
+        if (fabs(L->circ[0]) > L->gamma_crit) {                                                        /* :104 */
+            double gamma_crit_use;
+            if (s->levflag == 0 && t < L->lev_stop) {                                                  /* :105-108 */
+                gamma_crit_use = fabs(L->circ[0]) / L->circ[0] * L->gamma_crit;
+                L->t_start = t;
+            } else {                                                                                   /* :109-115 */
+                const double m_slp = -s->lespcrit / (L->lev_stop - L->t_start);
+                const double c_slp = s->lespcrit - (m_slp * L->t_start);
+                const double LESP_crit_use = (m_slp * t) + c_slp;
+                gamma_crit_use = fabs(L->circ[0]) / L->circ[0] * LESP_crit_use / 1.13 * (s->u * s->c * (acos(xx) + sin(acos(xx))));
+            }
+            {   /* place_lev2(surf, IFR_field, dtstar, t), calcs.jl:712-730 */
+                double LE_x, LE_z, xloc, zloc;
+                lve_ifr(s->pvt, al, X0, Z0, L->le_x, L->le_cam, &LE_x, &LE_z);
+                const double le_vel_x = s->u - s->alphadot * sin(s->alpha) * s->pvt * s->c + s->uind[0];
+                const double le_vel_z = -s->alphadot * cos(s->alpha) * s->pvt * s->c - s->hdot + s->wind[0];
+                if (s->levflag == 0) { xloc = LE_x + 0.5 * le_vel_x * dtstar; zloc = LE_z + 0.5 * le_vel_z * dtstar; }
+                else {
+                    const o_vort *q = &L->ifr.lev.v[L->ifr.lev.n - 1];
+                    xloc = LE_x + (1. / 3.) * (q->x - LE_x); zloc = LE_z + (1. / 3.) * (q->z - LE_z);
+                }
+                o_vort v = { xloc, zloc, 0., 0.02 * s->c, 0., 0. };
+                vec_push(&L->ifr.lev, v);
+            }
+            s->levflag = 1;                                                                            /* :123 */
+            double x_lev, z_lev;
+            { const o_vort *q = &L->ifr.lev.v[L->ifr.lev.n - 1]; lve_bfr(s->pvt, al, X0, Z0, q->x, q->z, &x_lev, &z_lev); }
+            /* mod_influence_coeff, calcs.jl:789-836 */
+            lve_influence(L, x_w, z_w, a);
+            for (int ii = 0; ii < nd; ii++) a1[ii] = a[(size_t)ii * nd];
+            for (int ii = 0; ii < nd; ii++) for (int j = 0; j < nd - 1; j++) a[(size_t)ii * nd + j] = a[(size_t)ii * nd + j + 1];
+            {
+                const double vc = s->bv[0].vc;
+                for (int ii = 0; ii < np; ii++) {
+                    const double xdist = x_lev - L->colx[ii], zdist = z_lev - L->colz[ii];
+                    const double distsq = xdist * xdist + zdist * zdist;
+                    const double u = -zdist / (2 * O_PI * sqrt(vc * vc * vc * vc + distsq * distsq));
+                    const double w = xdist / (2 * O_PI * sqrt(vc * vc * vc * vc + distsq * distsq));
+                    a[(size_t)ii * nd + nd - 1] = u * L->nx[ii] + w * L->nz[ii];
+                }
+            }
+            for (int j = 0; j < np; j++)                                                               /* :134-137 */
+                L->RHS[j] = -((L->relx[j] + s->uind[j]) * L->nx[j] + (L->relz[j] + s->wind[j]) * L->nz[j]) - gamma_crit_use * a1[j];
+            L->RHS[nd - 1] -= gamma_crit_use;                                                          /* :138 */
+            dense_solve(nd, a, L->RHS, L->circ);                                                       /* :140 */
+            L->ifr.lev.v[L->ifr.lev.n - 1].s = L->circ[nd - 1];                                        /* :142 */
+            for (int j = nd - 1; j >= 1; j--) L->circ[j] = L->circ[j - 1];                             /* :144 */
+            L->circ[0] = gamma_crit_use;                                                               /* :145 */
+        } else {
+            s->levflag = 0;                                                                            /* :151 */
+        }
+        for (int j = 0; j < np; j++) { L->prevCirc[j] = L->circ[j]; s->bv[j].s = L->circ[j]; L->ifr_bv[j].s = L->circ[j]; }   /* :154-159 */
+        if (L->ifr.tev.n > 1) L->ifr.tev.v[L->ifr.tev.n - 1].s = L->circ[nd - 1];                      /* :160-162 */
+        if (i > 0) {                                                                                   /* :203-232 */
+            for (int j = 0; j < np; j++)
+                L->dp[j] = L->rho * (((L->relx[j] + s->uind[j]) * L->taux[j] + (L->relz[j] + s->wind[j]) * L->tauz[j]) * L->circ[j] / L->ds[j]
+                                     + L->circChange[j]);
+            double ndem = .5 * L->rho * s->u * s->u * s->c;
+            double cn = 0; for (int j = 0; j < np; j++) cn += L->dp[j] * L->ds[j];
+            cn /= ndem;
+            s->a0 = 1.13 * L->circ[0] / (s->u * s->c * (acos(xx) + sin(acos(xx))));
+            const double cs = 2 * O_PI * s->a0 * s->a0;
+            const double cl = cn * cos(al) + cs * sin(al), cd = cn * sin(al) - cs * cos(al);
+            ndem = ndem * s->c;
+            double m1 = 0, m2 = 0;
+            for (int j = 0; j < np; j++) {
+                m1 += L->dp[j] * L->ds[j] * cos(L->cam_slope_deg[j] * d2r) * (L->vorx[j] - s->pvt);
+                m2 += L->dp[j] * L->ds[j] * sin(L->cam_slope_deg[j] * d2r) * L->vorz[j];
+            }
+            const double cm = -m1 / ndem + m2 / ndem;
+            double *mr = mat + 8 * (i - 1);
+            mr[0] = t; mr[1] = s->alpha * 180 / O_PI; mr[2] = s->h; mr[3] = s->u; mr[4] = s->a0; mr[5] = cl; mr[6] = cd; mr[7] = cm;
+        }
+        {   /* wakeroll(IFR_surf, IFR_field, dtstar) :235 -- reuse the single-surface restatement */
+            o_surf tmp = *s;
+            tmp.bv = L->ifr_bv;
+            wakeroll(&tmp, &L->ifr, dtstar);
+        }
+        {   /* :238-242 */
+            o_vort v = { 0, 0, L->ifr.tev.v[L->ifr.tev.n - 1].s, 0.02 * s->c, 0., 0. };
+            vec_push(&L->cur.tev, v);
+            if (L->ifr.lev.n > 0 && s->levflag == 1) {
+                o_vort w = { 0, 0, L->ifr.lev.v[L->ifr.lev.n - 1].s, 0.02 * s->c, 0., 0. };
+                vec_push(&L->cur.lev, w);
+            }
+            /* vor_BFR(surf, t+dtstar, IFR_field, curfield), calcs.jl:732-754 */
+            for (long k = 0; k < L->ifr.tev.n; k++)
+                lve_bfr(s->pvt, rn[1], rn[7], rn[8], L->ifr.tev.v[k].x, L->ifr.tev.v[k].z, &L->cur.tev.v[k].x, &L->cur.tev.v[k].z);
+            for (long k = 0; k < L->ifr.lev.n; k++)
+                lve_bfr(s->pvt, rn[1], rn[7], rn[8], L->ifr.lev.v[k].x, L->ifr.lev.v[k].z, &L->cur.lev.v[k].x, &L->cur.lev.v[k].z);
+        }
+    }
+    free(a); free(a1);
+    return 0;
+}
+
+long o_lve_count(void *h, int which) {   /* 0 ifr.tev, 1 ifr.lev, 2 cur.tev, 3 cur.lev */
+    o_lve *L = (o_lve *)h;
+    return which == 0 ? L->ifr.tev.n : which == 1 ? L->ifr.lev.n : which == 2 ? L->cur.tev.n : L->cur.lev.n;
+}
+void o_lve_get_vorts(void *h, int which, double *v) {
+    o_lve *L = (o_lve *)h;
+    o_vec *a = which == 0 ? &L->ifr.tev : which == 1 ? &L->ifr.lev : which == 2 ? &L->cur.tev : &L->cur.lev;
+    long n = a->n;
+    for (long i = 0; i < n; i++) {
+        v[i] = a->v[i].x; v[n + i] = a->v[i].z; v[2 * n + i] = a->v[i].s;
+        v[3 * n + i] = a->v[i].vc; v[4 * n + i] = a->v[i].vx; v[5 * n + i] = a->v[i].vz;
+    }
+}
+void o_lve_get_circ(void *h, double *circ_nd, double *gamma_crit) {
+    o_lve *L = (o_lve *)h;
+    memcpy(circ_nd, L->circ, (size_t)L->nd * sizeof(double));
+    *gamma_crit = L->gamma_crit;
+}

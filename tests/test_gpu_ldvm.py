@@ -350,3 +350,30 @@ def test_nlsolve_mode_other_drivers(gpu_lib, uf, oracle):
     mat, surfs, fld = uf.ldvm(surfs, fld, n, 0.012, solve_mode=cabi.SOLVE_NLSOLVE, write_summary=False)
     assert len(fld.lev) > 0
     assert np.max(np.abs(mat - omat)) <= 1e-7
+
+
+def test_lve_panel_solver(gpu_lib, uf, oracle):
+    """LVE (src/lowOrder2D/LVE.jl): Eldredge ramp with LEV ejection and a steady 5-degree plate,
+    against the LVE oracle; inertial-frame wake, body-frame curfield, panel circulations"""
+    for kin, lesp, n in ((uf.KinemDef(uf.EldUpDef(25 * math.pi / 180, 0.2, 0.8), uf.ConstDef(0.0), uf.ConstDef(1.0)), 0.2, 150),
+                         (uf.KinemDef(uf.ConstDef(5 * math.pi / 180), uf.ConstDef(0.0), uf.ConstDef(1.0)), 10.0, 120)):
+        surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [lesp], rho=1.0)
+        ifr = uf.TwoDSurf("FlatPlate", 0.25, kin, [lesp], ndiv=surf.ndiv, camberType="linear")
+        tab = uf.lve_table(surf, n, 0.015)
+        sim = oracle.LveSim(copy.deepcopy(surf), ifr)
+        omat = sim.run(tab, n, 0.015)
+        cur = uf.TwoDFlowField()
+        frames, ifr_field, mat, tevhist, levhist = uf.LVE(surf, cur, n, 0.015)
+        assert mat.shape == (n, 8)
+        assert np.max(np.abs(mat - omat)) <= HTOL, float(np.max(np.abs(mat - omat)))
+        for which, v in ((0, ifr_field.tev), (1, ifr_field.lev), (2, cur.tev), (3, cur.lev)):
+            o = sim.get_vorts(which)
+            assert len(v) == len(o["x"])
+            if len(v):
+                for k in ("x", "z", "s"):
+                    assert np.max(np.abs(getattr(v, k) - o[k])) <= 1e-8, (which, k)
+        ocirc, og = sim.get_circ()
+        assert np.max(np.abs(surf.bv.s - ocirc[:-1])) <= 1e-9
+        assert tevhist.shape == (n + 1, 2) and levhist.shape[0] == len(ifr_field.lev)
+        if lesp < 1:
+            assert len(ifr_field.lev) > 10

@@ -159,3 +159,33 @@ def test_multi_surface_oracle_consistency(oracle, uf):
     lev = sim.get_vorts(1)
     assert np.all(np.isfinite(mat)) and np.sum(lev["vc"] == 0) > 0 and np.sum(lev["vc"] > 0) > 0
     assert len(sim.get_vorts(0)["x"]) == 240
+
+
+def test_lve_oracle_consistency(oracle, uf):
+    """LVE restatement (LVE.jl:6-302): the steady 5-degree plate approaches the same Wagner value as
+    ldvm (Cl(t*=7) ~ 0.50); Kelvin's theorem (last row of the influence matrix, calcs.jl:759)
+    keeps  sum(bound) + sum(wake)  constant -- not zero, because the reference never stores the
+    strength of the FIRST shed TEV (`if length(IFR_field.tev) > 1`, LVE.jl:160)"""
+    def total(sim):
+        circ, _ = sim.get_circ()
+        return circ[:-1].sum() + sim.get_vorts(0)["s"].sum() + sim.get_vorts(1)["s"].sum()
+
+    kin = uf.KinemDef(uf.ConstDef(5 * math.pi / 180), uf.ConstDef(0.0), uf.ConstDef(1.0))
+    surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [10.0], rho=1.0)
+    ifr = uf.TwoDSurf("FlatPlate", 0.25, kin, [10.0], ndiv=70, camberType="linear")
+    tab = uf.lve_table(surf, 468, 0.015)
+    sim = oracle.LveSim(surf, ifr)
+    mat = sim.run(tab, 468, 0.015)
+    assert abs(mat[-1, 5] - 0.5065) < 2e-3 and abs(mat[-1, 1] - 5.0) < 1e-12
+    short = oracle.LveSim(surf, ifr)
+    short.run(np.vstack([tab[:51], tab[51:52]]), 50, 0.015)
+    assert abs(total(sim) - total(short)) < 1e-12 and abs(total(sim)) > 1e-3
+    assert sim.get_vorts(0)["s"][0] == 0.0
+    kin = uf.KinemDef(uf.EldUpDef(25 * math.pi / 180, 0.2, 0.8), uf.ConstDef(0.0), uf.ConstDef(1.0))
+    surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [0.2], rho=1.0)
+    ifr = uf.TwoDSurf("FlatPlate", 0.25, kin, [0.2], ndiv=70, camberType="linear")
+    sim = oracle.LveSim(surf, ifr)
+    mat = sim.run(uf.lve_table(surf, 200, 0.015), 200, 0.015)
+    circ, gcrit = sim.get_circ()
+    assert np.all(np.isfinite(mat)) and len(sim.get_vorts(1)["x"]) > 20
+    assert abs(abs(circ[0]) - gcrit) < 2e-4        # leading panel clipped near gamma_crit while shedding

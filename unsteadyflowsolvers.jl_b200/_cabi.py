@@ -93,6 +93,9 @@ def lib():
         "unsflow_ldvm_create": [C.POINTER(vp), C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts)],
         "unsflow_ldvm_multi_create": [C.POINTER(vp), C.c_int32, C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts)],
         "unsflow_ldvm_multi_get_state": [vp, C.c_int32, C.POINTER(Surf), C.POINTER(Field)],
+        "unsflow_lve_create": [C.POINTER(vp), C.POINTER(Surf), C.POINTER(Field), C.POINTER(Opts), C.c_double, C.c_double, C.c_double,
+                               C.c_double, C.c_double, C.c_double],
+        "unsflow_lve_get_circ": [vp, d, d],
         "unsflow_ldvm_set_kinematics": [vp, i64, d],
         "unsflow_ldvm_set_parallel": [vp, C.c_int, C.c_int, vp],
         "unsflow_ldvm_set_2dof": [vp, d, d],

@@ -62,9 +62,12 @@ struct SurfState {
 };
 constexpr int kMaxSurf = 4;
 
+struct LveState;
 struct LdvmDev {
     StepState *st;
     SurfState *ms;       // [nsurf] (multi-surface driver only)
+    LveState *lve;       // LVE driver only
+    double *lvea;        // LVE panel arrays [kLveArrays][ndiv]
     int nsurf;
     int ndiv, naterm, driver, solve_mode, del_kind;
     long long del_limit;
@@ -956,6 +959,277 @@ __device__ void mstep_solve(const LdvmDev &d) {
 __global__ void __launch_bounds__(kSolveThreads) k_mstep_head(const LdvmDev d) { mstep_head(d); }
 __global__ void __launch_bounds__(kSolveThreads) k_mstep_solve(const LdvmDev d) { mstep_solve(d); }
 
+
+// =============================================================================================
+// LVE -- lumped-vortex-element panel solver: src/lowOrder2D/LVE.jl:6-302 with
+// the helpers of calcs.jl:652-836.  The wake lives in the INERTIAL frame on the device (the
+// reference's IFR_field); its body-frame twin (curfield, refreshed by vor_BFR every step,
+// calcs.jl:732-754) is never materialised: the collocation points are mapped into the inertial
+// frame for the sweep and the induced velocity is rotated back (a rigid transform preserves the
+// Vatistas kernel).  Each iteration: k_lve_head, k_sweep (collocation points x wake),
+// k_lve_solve (influence matrix, dense (ndiv x ndiv) Gauss-Jordan with partial pivoting in shared
+// memory, LEV ejection logic, panel pressures and loads), then the usual roll-up + finish.
+// =============================================================================================
+constexpr int kLveArrays = 14;
+enum { LV_DS, LV_CSD, LV_NX, LV_NZ, LV_TX, LV_TZ, LV_VX, LV_VZ, LV_CX, LV_CZ, LV_PREV, LV_CHG, LV_CIRC, LV_REL };
+struct LveState {
+    double gamma_crit, rho, lev_stop, t_start, te_x, te_cam, le_x, le_cam, ifr_u0, ifr_hdot0;
+    double alpha, X0, Z0;    // frame of the current iteration
+    long long iter;          // iterations completed (LVE.jl:60 loop index i)
+};
+
+__device__ __forceinline__ void lve_ifr(double pvt, double sa, double ca, double X0, double Z0, double x, double z, double *X, double *Z) {
+    *X = (x - pvt) * ca + z * sa + X0 + pvt;        // IFR, calcs.jl:652-663
+    *Z = -(x - pvt) * sa + z * ca + Z0;
+}
+__device__ __forceinline__ void lve_bfr(double pvt, double sa, double ca, double X0, double Z0, double X, double Z, double *x, double *z) {
+    *x = (X - X0 - pvt) * ca - (Z - Z0) * sa + pvt;   // BFR, calcs.jl:665-676
+    *z = (X - X0 - pvt) * sa + (Z - Z0) * ca;
+}
+
+__device__ void lve_head(const LdvmDev &d) {
+    StepState *s = d.st;
+    LveState *L = d.lve;
+    const int tid = threadIdx.x, nd = d.ndiv, np = nd - 1;
+    __shared__ double sh[4];
+    if (tid == 0) {
+        const long long row = s->step < d.kin_rows ? s->step : d.kin_rows - 1;
+        const double *r = d.kin + 9 * row;
+        s->t = r[0];
+        s->kin[0] = r[1]; s->kin[1] = r[2]; s->kin[2] = r[3]; s->kin[3] = r[4]; s->kin[4] = r[5]; s->kin[5] = r[6];   // update_kinem, LVE.jl:64
+        L->alpha = r[1]; L->X0 = r[7]; L->Z0 = r[8];
+        sh[0] = r[1]; sh[1] = r[7]; sh[2] = r[8];
+    }
+    __syncthreads();
+    double sa, ca;
+    sincos(sh[0], &sa, &ca);
+    const double X0 = sh[1], Z0 = sh[2];
+    const long long bv0 = s->wake.begin[3];
+    for (int j = tid; j < np; j += blockDim.x) {
+        // IFR_vor (LVE.jl:67-68) and the collocation points in the inertial frame (sweep targets)
+        lve_ifr(d.pvt, sa, ca, X0, Z0, d.lvea[LV_VX * nd + j], d.lvea[LV_VZ * nd + j], &d.wx[bv0 + j], &d.wz[bv0 + j]);
+        lve_ifr(d.pvt, sa, ca, X0, Z0, d.lvea[LV_CX * nd + j], d.lvea[LV_CZ * nd + j], &d.bnd_x[j], &d.bnd_z[j]);
+    }
+    if (tid == 0) {   // place_tev2(IFR_surf, IFR_field, dtstar, t), calcs.jl:688-709
+        const long long b = s->wake.begin[0], e = s->wake.end[0];
+        double TE_x, TE_z, xloc, zloc;
+        lve_ifr(d.pvt, sa, ca, X0, Z0, L->te_x, L->te_cam, &TE_x, &TE_z);
+        if (e == b) { xloc = TE_x + 0.5 * L->ifr_u0 * d.dt; zloc = TE_z + 0.5 * L->ifr_hdot0 * d.dt; }
+        else { xloc = TE_x + (1. / 3.) * (d.wx[e - 1] - TE_x); zloc = TE_z + (1. / 3.) * (d.wz[e - 1] - TE_z); }
+        d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0; d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new; d.wvx[e] = 0.0; d.wvz[e] = 0.0;
+        s->wake.end[0] = e + 1;
+    }
+}
+
+// Gauss-Jordan with partial pivoting on the augmented matrix A[n][n+1] in shared memory
+// (stands in for Julia's a\RHS, LVE.jl:93,140); all threads of the CTA take part
+__device__ void cta_solve(double *A, int n, int *piv_sh) {
+    const int tid = threadIdx.x, ld = n + 1;
+    for (int c = 0; c < n; c++) {
+        if (tid < 32) {
+            double best = -1.0; int bi = c;
+            for (int r = c + tid; r < n; r += 32) { const double v = fabs(A[r * ld + c]); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) *piv_sh = bi;
+        }
+        __syncthreads();
+        const int p = *piv_sh;
+        if (p != c) for (int j = tid; j <= n; j += blockDim.x) { const double t = A[c * ld + j]; A[c * ld + j] = A[p * ld + j]; A[p * ld + j] = t; }
+        __syncthreads();
+        const double inv = 1.0 / A[c * ld + c];
+        // eliminate column c from every other row (factors read before any write: column c is not written)
+        const int w = n - c;                    // columns c+1 .. n (incl. rhs)
+        for (int e = tid; e < n * w; e += blockDim.x) {
+            const int r = e / w, j = c + 1 + e % w;
+            if (r != c) A[r * ld + j] -= (A[r * ld + c] * inv) * A[c * ld + j];
+        }
+        __syncthreads();
+    }
+    // x_i = A[i][n] / A[i][i]  (left to the caller)
+}
+
+__device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1) */) {
+    StepState *s = d.st;
+    LveState *L = d.lve;
+    const int tid = threadIdx.x, nd = d.ndiv, np = nd - 1, ld = nd + 1;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    __shared__ double uind[kNdMax], wind[kNdMax], relx[kNdMax], relz[kNdMax], circ[kNdMax], a1[kNdMax], sc[16];
+    __shared__ int piv_sh, lev_shed;
+    double *la = d.lvea;
+    const double alpha = s->kin[0], alphadot = s->kin[2], hdot = s->kin[3], u = s->kin[4];
+    double sa, ca;
+    sincos(alpha, &sa, &ca);
+    const double X0 = L->X0, Z0 = L->Z0, t = s->t;
+    const long long tb = s->wake.begin[0], te = s->wake.end[0];
+    const long long iter = L->iter;
+    // ---- induced velocity at the collocation points: inertial-frame sums -> body axes -----------
+    for (int j = tid; j < np; j += blockDim.x) {
+        double su = 0.0, sw = 0.0;
+        for (int k = 0; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + j]; sw += d.p2w[(long long)k * d.p2stride + j]; }
+        su *= kInvTwoPi; sw *= kInvTwoPi;
+        double ub = su * ca - sw * sa, wb = su * sa + sw * ca;
+        if (te - tb <= 1) { ub = d.uind[j]; wb = d.wind[j]; }     // LVE.jl:80: only once curfield holds vortices
+        uind[j] = ub; wind[j] = wb;
+        d.uind[j] = ub; d.wind[j] = wb;
+        const double cx = la[LV_CX * nd + j], cz = la[LV_CZ * nd + j];
+        relx[j] = (ca * u - sa * (-hdot)) + (-alphadot * cz);      // LVE.jl:86
+        relz[j] = (sa * u + ca * (-hdot)) + alphadot * (cx - d.pvt);
+    }
+    if (tid == 0) {
+        lve_bfr(d.pvt, sa, ca, X0, Z0, d.wx[te - 1], d.wz[te - 1], &sc[0], &sc[1]);   // x_w, z_w  :74
+        double sp = 0.0;
+        for (int j = 0; j < np; j++) sp += la[LV_PREV * nd + j];
+        sc[2] = sp;
+        lev_shed = 0;
+    }
+    __syncthreads();
+    const double x_w = sc[0], z_w = sc[1];
+    // ---- influence_coeff (calcs.jl:756-787) + RHS (LVE.jl:78-90) into the augmented matrix -------
+    auto build = [&](bool lev, double x_lev, double z_lev, double gcu) {
+        for (int e = tid; e < nd * nd; e += blockDim.x) {
+            const int i = e / nd, j = e % nd;
+            double v;
+            if (i == np) v = 1.0;
+            else {
+                const double t_x = la[LV_CX * nd + i], t_z = la[LV_CZ * nd + i];
+                double uu, ww;
+                // column j of the (possibly shifted) matrix: unshifted source index
+                const int js = lev ? j + 1 : j;                      // mod_influence_coeff shifts left (:818)
+                if (lev && j == nd - 1) {
+                    const double xd = x_lev - t_x, zd = z_lev - t_z, dsq = xd * xd + zd * zd;
+                    const double den = kTwoPi * sqrt(d.vc4_new + dsq * dsq);
+                    uu = -zd / den; ww = xd / den;
+                } else if (js < np) {
+                    const double xd = la[LV_VX * nd + js] - t_x, zd = la[LV_VZ * nd + js] - t_z, dsq = xd * xd + zd * zd;
+                    uu = -zd / (kTwoPi * dsq); ww = xd / (kTwoPi * dsq);
+                } else {
+                    const double xd = x_w - t_x, zd = z_w - t_z, dsq = xd * xd + zd * zd;
+                    const double den = kTwoPi * sqrt(d.vc4_new + dsq * dsq);
+                    uu = -zd / den; ww = xd / den;
+                }
+                v = uu * la[LV_NX * nd + i] + ww * la[LV_NZ * nd + i];
+            }
+            A[i * ld + j] = v;
+        }
+        for (int i = tid; i < nd; i += blockDim.x) {
+            double rhs;
+            if (i == np) rhs = sc[2] - (lev ? gcu : 0.0);                                  // :78, :138
+            else {
+                rhs = -((relx[i] + uind[i]) * la[LV_NX * nd + i] + (relz[i] + wind[i]) * la[LV_NZ * nd + i]);
+                if (lev) rhs -= gcu * a1[i];                                               // :136
+            }
+            A[i * ld + nd] = rhs;
+        }
+    };
+    build(false, 0.0, 0.0, 0.0);
+    __syncthreads();
+    for (int i = tid; i < nd; i += blockDim.x) a1[i] = A[i * ld + 0];                      // first column (calcs.jl:817)
+    __syncthreads();
+    cta_solve(A, nd, &piv_sh);
+    for (int i = tid; i < nd; i += blockDim.x) circ[i] = A[i * ld + nd] / A[i * ld + i];   // circ = a\RHS :93
+    __syncthreads();
+    for (int j = tid; j < np; j += blockDim.x) {                                            // :96-100
+        double g1 = 0.0, g2 = 0.0;
+        for (int k = 0; k < j; k++) { g1 += la[LV_PREV * nd + k]; g2 += circ[k]; }
+        la[LV_CHG * nd + j] = (g2 - g1) / d.dt;
+    }
+    const double xx = 1 - 2 * la[LV_DS * nd] / d.c;
+    const double geo = u * d.c * (acos(xx) + sin(acos(xx)));
+    if (tid == 0) {
+        if (fabs(circ[0]) > L->gamma_crit) {                                                // :104
+            double gcu;
+            if (s->levflag == 0 && t < L->lev_stop) { gcu = fabs(circ[0]) / circ[0] * L->gamma_crit; L->t_start = t; }   // :105-108
+            else {                                                                          // :109-115
+                const double m_slp = -d.lespcrit / (L->lev_stop - L->t_start);
+                const double c_slp = d.lespcrit - (m_slp * L->t_start);
+                gcu = fabs(circ[0]) / circ[0] * ((m_slp * t) + c_slp) / 1.13 * geo;
+            }
+            // place_lev2(surf, IFR_field, dtstar, t), calcs.jl:712-730
+            const long long lb = s->wake.begin[1], le = s->wake.end[1];
+            double LE_x, LE_z, xl, zl;
+            lve_ifr(d.pvt, sa, ca, X0, Z0, L->le_x, L->le_cam, &LE_x, &LE_z);
+            const double vx = u - alphadot * sa * d.pvt * d.c + uind[0];
+            const double vz = -alphadot * ca * d.pvt * d.c - hdot + wind[0];
+            if (s->levflag == 0 || le == lb) { xl = LE_x + 0.5 * vx * d.dt; zl = LE_z + 0.5 * vz * d.dt; }
+            else { xl = LE_x + (1. / 3.) * (d.wx[le - 1] - LE_x); zl = LE_z + (1. / 3.) * (d.wz[le - 1] - LE_z); }
+            d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = 0.0; d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new; d.wvx[le] = 0.0; d.wvz[le] = 0.0;
+            s->wake.end[1] = le + 1;
+            lve_bfr(d.pvt, sa, ca, X0, Z0, xl, zl, &sc[4], &sc[5]);                         // x_lev, z_lev :126
+            sc[6] = gcu;
+            lev_shed = 1;
+        }
+    }
+    __syncthreads();
+    if (lev_shed) {
+        const double gcu = sc[6];
+        build(true, sc[4], sc[5], gcu);                                                     // mod_influence_coeff + RHS :127-138
+        __syncthreads();
+        cta_solve(A, nd, &piv_sh);
+        __shared__ double c2[kNdMax];
+        for (int i = tid; i < nd; i += blockDim.x) c2[i] = A[i * ld + nd] / A[i * ld + i];  // :140
+        __syncthreads();
+        if (tid == 0) d.wg[s->wake.end[1] - 1] = c2[nd - 1];                                // :142
+        for (int i = tid; i < nd; i += blockDim.x) circ[i] = i == 0 ? gcu : c2[i - 1];      // :144-145
+        __syncthreads();
+    }
+    // ---- strengths (:154-162), loads (:203-232) -------------------------------------------------
+    const long long bv0 = s->wake.begin[3];
+    for (int j = tid; j < np; j += blockDim.x) {
+        la[LV_PREV * nd + j] = circ[j];
+        la[LV_CIRC * nd + j] = circ[j];
+        d.wg[bv0 + j] = circ[j];
+    }
+    if (tid == 0) {
+        la[LV_CIRC * nd + np] = circ[np];
+        if (te - tb > 1) d.wg[te - 1] = circ[np];
+        s->levflag = lev_shed;
+    }
+    if (warp == 1 % nwarps) {
+        double cn = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int j = lane; j < np; j += 32) {
+            const double dsj = la[LV_DS * nd + j];
+            const double dp = L->rho * (((relx[j] + uind[j]) * la[LV_TX * nd + j] + (relz[j] + wind[j]) * la[LV_TZ * nd + j]) * circ[j] / dsj
+                                        + la[LV_CHG * nd + j]);
+            cn += dp * dsj;
+            m1 += dp * dsj * la[LV_TX * nd + j] * (la[LV_VX * nd + j] - d.pvt);    // cosd(cam_slope) = tau_x
+            m2 += dp * dsj * la[LV_TZ * nd + j] * la[LV_VZ * nd + j];               // sind(cam_slope) = tau_z
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cn += __shfl_xor_sync(0xffffffffu, cn, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        }
+        if (lane == 0) {
+            double *m = d.mat + 9 * s->mat_row;     // 9th column: LEV shed in this iteration (LEVhist, LVE.jl:147-149)
+            m[0] = t; m[1] = alpha * 180 / kPi; m[2] = s->kin[1]; m[3] = u;
+            m[4] = 0.0; m[5] = 0.0; m[6] = 0.0; m[7] = 0.0; m[8] = lev_shed;
+            if (iter > 0) {
+                double ndem = .5 * L->rho * u * u * d.c;
+                cn /= ndem;
+                const double a0 = 1.13 * circ[0] / geo;
+                const double cs = 2 * kPi * a0 * a0;
+                ndem *= d.c;
+                m[4] = a0; m[5] = cn * ca + cs * sa; m[6] = cn * sa - cs * ca; m[7] = -m1 / ndem + m2 / ndem;
+                s->a0 = a0; s->cl = m[5]; s->cd = m[6]; s->cm = m[7];
+            }
+            s->mat_row += 1;
+            s->step += 1;
+            L->iter = iter + 1;
+            s->fs[0] = 0.0; s->fs[1] = 0.0;     // IFR_field.u, w stay 0 (TwoDFlowField(), LVE.jl:16)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_lve_head(const LdvmDev d) { lve_head(d); }
+__global__ void __launch_bounds__(kSolveThreads) k_lve_solve(const LdvmDev d) {
+    extern __shared__ __align__(16) double lve_dyn[];
+    lve_solve(d, lve_dyn);
+}
+
 __global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) { step_head(d); }
 __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) { step_solve(d); }
 
@@ -1109,6 +1383,8 @@ struct unsflow_ldvm {
     int ndiv = 0, naterm = 0;
     int nsurf = 1, mat_cols = 8;
     DevBuf<SurfState> ms;
+    DevBuf<LveState> lves;    // LVE driver only
+    DevBuf<double> lvea;
     int64_t cap_t = 0, cap_l = 0, cap_e = 0, bvpad = 0, tot = 0;
     int64_t off_t = 0, off_l = 0, off_e = 0, off_b = 0;
     int64_t ntev0 = 0, nlev0 = 0, nextv = 0;
@@ -1171,7 +1447,9 @@ int unsflow_ldvm_destroy(unsflow_ldvm *h) {
     return 0;
 }
 
-static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *sfs, const unsflow_field *fl, const unsflow_opts *op) {
+#define UNSFLOW_DRIVER_LVE_INTERNAL 4
+static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *sfs, const unsflow_field *fl, const unsflow_opts *op,
+                            bool allow_lve = false) {
     UF_CHECK(out != nullptr, "unsflow_ldvm_create: null handle pointer");
     *out = nullptr;
     UF_CHECK(sfs && fl && op, "unsflow_ldvm_create: null argument");
@@ -1186,7 +1464,7 @@ static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *s
     UF_CHECK(nsurf == 1 || op->driver == UNSFLOW_DRIVER_LDVM, "unsflow_ldvm_create: several surfaces are supported by the ldvm driver only");
     UF_CHECK(sf->ndiv >= 3 && sf->ndiv <= kNdMax, "unsflow_ldvm_create: ndiv=%d outside [3,%d]", sf->ndiv, kNdMax);
     UF_CHECK(sf->naterm >= 3 && sf->naterm <= kNaMax, "unsflow_ldvm_create: naterm=%d outside [3,%d]", sf->naterm, kNaMax);
-    UF_CHECK(op->driver >= 0 && op->driver <= 3, "unsflow_ldvm_create: bad driver %d", op->driver);
+    UF_CHECK(op->driver >= 0 && (op->driver <= 3 || (allow_lve && op->driver == UNSFLOW_DRIVER_LVE_INTERNAL)), "unsflow_ldvm_create: bad driver %d", op->driver);
     UF_CHECK(op->solve_mode == 0 || op->solve_mode == 1, "unsflow_ldvm_create: bad solve_mode %d", op->solve_mode);
     UF_CHECK(op->delvort_kind == 0 || op->delvort_kind == 1, "unsflow_ldvm_create: bad delvort_kind %d", op->delvort_kind);
     UF_CHECK(op->max_steps >= 0 && op->dt > 0, "unsflow_ldvm_create: need max_steps >= 0 and dt > 0");
@@ -1202,7 +1480,7 @@ static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *s
     h->opts = *op;
     const int nd = h->ndiv = sf->ndiv, na = h->naterm = sf->naterm;
     const int ns = h->nsurf = nsurf;
-    h->mat_cols = nsurf == 1 ? 8 : 1 + 7 * nsurf;
+    h->mat_cols = op->driver == UNSFLOW_DRIVER_LVE_INTERNAL ? 9 : (nsurf == 1 ? 8 : 1 + 7 * nsurf);
     h->ntev0 = fl->tev.n; h->nlev0 = fl->lev.n; h->nextv = fl->extv.n;
     // slabs start on pair-tile boundaries (kSymTB is a multiple of the direct kernel's kTS)
     h->cap_t = round_up(h->ntev0 + ns * op->max_steps + ns, kSymTB);
@@ -1332,6 +1610,65 @@ int unsflow_ldvm_multi_create(unsflow_ldvm **out, int32_t nsurf, const unsflow_s
     return ldvm_create_impl(out, nsurf, surfs, fl, op);
 }
 
+int unsflow_lve_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow_field *ifr_field, const unsflow_opts *op,
+                       double rho, double lev_stop, double ifr_xend, double ifr_camend, double ifr_u0, double ifr_hdot0) {
+    UF_CHECK(out && sf && ifr_field && op, "unsflow_lve_create: null argument");
+    UF_CHECK(sf->ndiv >= 3 && (size_t)sf->ndiv * (sf->ndiv + 1) * sizeof(double) <= 200 * 1024, "unsflow_lve_create: ndiv=%d too large for the in-CTA dense solve (max 159)", sf->ndiv);
+    unsflow_opts o = *op;
+    o.driver = UNSFLOW_DRIVER_LVE_INTERNAL;
+    o.delvort_kind = UNSFLOW_DEL_NONE;
+    if (int rc = ldvm_create_impl(out, 1, sf, ifr_field, &o, true)) return rc;
+    unsflow_ldvm *h = *out;
+    auto fail = [&](int rc) { unsflow_ldvm_destroy(h); *out = nullptr; return rc; };
+    const int nd = h->ndiv, np = nd - 1;
+    if (h->lves.alloc(1) || h->lvea.alloc((int64_t)kLveArrays * nd)) return fail(2);
+    std::vector<double> a((size_t)kLveArrays * nd, 0.0);
+    const double d2r = kPi / 180.0;
+    for (int j = 0; j < np; j++) {                         // LVE.jl:29-47
+        const double dx = sf->x[j] - sf->x[j + 1], dc = sf->cam[j] - sf->cam[j + 1];
+        const double ds = std::sqrt(dx * dx + dc * dc);
+        const double csd = std::asin((sf->cam[j + 1] - sf->cam[j]) / ds) / d2r;
+        const double sd = std::sin(csd * d2r), cd = std::cos(csd * d2r);
+        a[LV_DS * nd + j] = ds; a[LV_CSD * nd + j] = csd;
+        a[LV_NX * nd + j] = -sd; a[LV_NZ * nd + j] = cd; a[LV_TX * nd + j] = cd; a[LV_TZ * nd + j] = sd;
+        a[LV_VX * nd + j] = sf->x[j] + .25 * ds * cd; a[LV_VZ * nd + j] = sf->cam[j] + .25 * ds * sd;
+        a[LV_CX * nd + j] = sf->x[j] + .75 * ds * cd; a[LV_CZ * nd + j] = sf->cam[j] + .75 * ds * sd;
+    }
+    LveState L;
+    memset(&L, 0, sizeof(L));
+    const double x = 1 - 2 * a[LV_DS * nd] / sf->c;        // LVE.jl:50-52
+    L.gamma_crit = sf->lespcrit / 1.13 * (sf->kinem[4] * sf->c * (std::acos(x) + std::sin(std::acos(x))));
+    L.rho = rho; L.lev_stop = lev_stop; L.te_x = ifr_xend; L.te_cam = ifr_camend; L.le_x = sf->x[0]; L.le_cam = sf->cam[0];
+    L.ifr_u0 = ifr_u0; L.ifr_hdot0 = ifr_hdot0;
+    if (cudaMemcpy(h->lves.p, &L, sizeof(L), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->lvea.p, a.data(), sizeof(double) * a.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("unsflow_lve_create: upload failed");
+        return fail(2);
+    }
+    const size_t dyn = sizeof(double) * nd * (nd + 1);
+    // static + dynamic shared memory exceed the 48 KB default already at ndiv = 70: always opt in
+    if (cudaFuncSetAttribute(k_lve_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+        set_error("unsflow_lve_create: cannot reserve %zu bytes of shared memory", dyn);
+        return fail(2);
+    }
+    h->dev.lve = h->lves.p;
+    h->dev.lvea = h->lvea.p;
+    return 0;
+}
+
+/* LVE extras of the state: circ (ndiv: panel circulations + shed TEV strength), circChange, prevCirc (ndiv-1 used) */
+int unsflow_lve_get_circ(unsflow_ldvm *h, double *circ_ndiv, double *gamma_crit) {
+    UF_CHECK(h && h->lvea.p && circ_ndiv, "unsflow_lve_get_circ: not an LVE handle");
+    UF_CUDA(cudaStreamSynchronize(h->stream));
+    UF_CUDA(cudaMemcpy(circ_ndiv, h->lvea.p + (int64_t)LV_CIRC * h->ndiv, sizeof(double) * h->ndiv, cudaMemcpyDeviceToHost));
+    if (gamma_crit) {
+        LveState L;
+        UF_CUDA(cudaMemcpy(&L, h->lves.p, sizeof(L), cudaMemcpyDeviceToHost));
+        *gamma_crit = L.gamma_crit;
+    }
+    return 0;
+}
+
 int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *table) {
     UF_CHECK(h != nullptr, "unsflow_ldvm_set_kinematics: null handle");
     UF_CHECK(nrows > 0 && table != nullptr, "unsflow_ldvm_set_kinematics: empty table");
@@ -1396,7 +1733,9 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     const int driver = h->opts.driver, smc = sm_count(), order = rsqrt_order();
     const int64_t tot = h->tot, nwake_ub = ntev_ub + nlev_ub + h->nextv;
     const bool multi = h->nsurf > 1;
-    if (multi) k_mstep_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+    const bool lve = driver == UNSFLOW_DRIVER_LVE_INTERNAL;
+    if (lve) k_lve_head<<<1, kSolveThreads, 0, st>>>(h->dev);
+    else if (multi) k_mstep_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     else k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;
     if (driver != UNSFLOW_DRIVER_LAUTAT) {
@@ -1408,18 +1747,19 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         a.sreg = &h->st.p->wake; a.treg = &h->st.p->bnd; a.nsreg = 3; a.ntreg = 1;
         a.vc4_uniform = h->vc4u;
         a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
-        if (!multi && sweep_supported(h->ndiv)) {
+        if (lve || (!multi && sweep_supported(h->ndiv))) {
             // dedicated few-targets kernel (sweep.cuh): one partial plane per block
             const long long tsrc = (nwake_ub + kTS - 1) / kTS + 3;
             p2.S = (int)std::max<long long>(1, std::min<long long>(tsrc, h->S2max));
-            if (int rc = launch_sweep(a, h->ndiv, p2.S, h->uniform, st)) return rc;
+            if (int rc = launch_sweep(a, lve ? h->ndiv - 1 : h->ndiv, p2.S, h->uniform, st)) return rc;
         } else {
             if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
         }
         h->dev.S2 = p2.S;
         h->launches++;
     }
-    if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+    if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * (h->ndiv + 1), st>>>(h->dev);
+    else if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     else k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;
     // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound

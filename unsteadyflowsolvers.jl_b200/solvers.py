@@ -294,3 +294,93 @@ def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM,
     ms = C.c_float(0)
     cabi.check(cabi.lib().unsflow_ldvm_batch_timing(C.byref(ms)))
     return np.ascontiguousarray(mats.transpose(0, 2, 1)), ntev, nlev, ms.value
+
+
+def lve_table(surf, nsteps, dtstar):
+    """Host-tabulated motion for LVE (LVE.jl:57-64): iterations i = 0..nsteps at the running-sum
+    times t = -dtstar + dtstar + dtstar ... plus one more row (vor_BFR uses t + dtstar,
+    LVE.jl:242).  Columns [t, alpha, h, alphadot, hdot, u, udot, X0, Z0] where alpha, h, ... are
+    what update_kinem sets and X0 = -kindef.u(t)*t, Z0 = kindef.h(t) are the frame offsets of
+    IFR/BFR (calcs.jl:654-656)."""
+    tab = np.zeros((nsteps + 2, 9))
+    k = KinemPar(**vars(surf.kinem))
+    t = -dtstar
+    for i in range(nsteps + 2):
+        t += dtstar
+        k = eval_kinem(surf.kindef, t, surf.c, surf.uref, k)
+        tab[i] = [t, surf.kindef.alpha(t), k.h, k.alphadot, k.hdot, k.u, k.udot, -surf.kindef.u(t) * t, surf.kindef.h(t)]
+    return tab
+
+
+def LVE(surf, curfield, nsteps=500, dtstar=0.015, frameCnt=20, view="square", LEV_Stop=1000, anim=False, animStep=30,
+        wflag=False, writeInterval=50):
+    """LVE(surf, curfield, nsteps, dtstar, frameCnt, view, LEV_Stop, anim, animStep, wflag, writeInterval)
+    -> (frames, IFR_field, mat, TEVhist, LEVhist), src/lowOrder2D/LVE.jl:6-302.  The time loop runs on the
+    GPU (unsflow_lve_create + unsflow_ldvm_run); the plotting / animation outputs of the reference
+    (`frames`, anim) are not produced (frames = 0, its initial value LVE.jl:21)."""
+    from .typedefs import TwoDFlowField as _FF, TwoDSurf as _TS
+    if anim or wflag:
+        raise NotImplementedError("LVE: anim / wflag outputs are host-side plotting and are not mirrored")
+    ifr_surf = _TS(surf.coord_file, surf.pvt, surf.kindef, surf.lespcrit, ndiv=surf.ndiv, camberType="linear")   # LVE.jl:17
+    ifr_field = _FF()
+    nd, npan = surf.ndiv, surf.ndiv - 1
+    # refresh_vortex(surf, vor_loc), LVE.jl:55 (geometry as in LVE.jl:29-41)
+    dsv = np.sqrt((surf.x[:-1] - surf.x[1:]) ** 2 + (surf.cam[:-1] - surf.cam[1:]) ** 2)
+    csd = np.degrees(np.arcsin((surf.cam[1:] - surf.cam[:-1]) / dsv))
+    vor_x = surf.x[:-1] + 0.25 * dsv * np.cos(np.radians(csd))
+    vor_z = surf.cam[:-1] + 0.25 * dsv * np.sin(np.radians(csd))
+    surf.bv.x[:] = vor_x
+    surf.bv.z[:] = vor_z
+    table = lve_table(surf, nsteps, dtstar)
+    opts = _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 1, delNone(), cabi.SOLVE_EXACT)
+    keep = []
+    sst = surf_struct(surf, keep)
+    fst = field_struct(ifr_field, keep)
+    h = C.c_void_p()
+    L = cabi.lib()
+    cabi.check(L.unsflow_lve_create(C.byref(h), C.byref(sst), C.byref(fst), C.byref(opts), surf.rho, float(LEV_Stop),
+                                    float(ifr_surf.x[-1]), float(ifr_surf.cam[-1]), ifr_surf.kinem.u, ifr_surf.kinem.hdot))
+    try:
+        t9 = cabi.f64(table)
+        cabi.check(L.unsflow_ldvm_set_kinematics(h, t9.shape[0], cabi.dptr(t9)))
+        niter = nsteps + 1
+        m9 = np.zeros((niter, 9), order="F")
+        cabi.check(L.unsflow_ldvm_run(h, niter, m9.ctypes.data_as(cabi.c_double_p)))
+        nt, nl, ne = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        cabi.check(L.unsflow_ldvm_counts(h, C.byref(nt), C.byref(nl), C.byref(ne)))
+        ifr_field.tev.resize(nt.value)
+        ifr_field.lev.resize(nl.value)
+        keep2 = []
+        bnd_keep = (surf.bnd_x.copy(), surf.bnd_z.copy())
+        s2 = surf_struct(surf, keep2)
+        f2 = field_struct(ifr_field, keep2)
+        cabi.check(L.unsflow_ldvm_get_state(h, C.byref(s2), C.byref(f2)))
+        circ = np.zeros(nd)
+        gcrit = C.c_double(0)
+        cabi.check(L.unsflow_lve_get_circ(h, cabi.dptr(circ), C.byref(gcrit)))
+        ms, nl_ = C.c_float(0), C.c_int64(0)
+        cabi.check(L.unsflow_ldvm_timing(h, C.byref(ms), C.byref(nl_)))
+        LVE.last_timing = (ms.value, nl_.value)
+    finally:
+        L.unsflow_ldvm_destroy(h)
+    surf.bnd_x[:], surf.bnd_z[:] = bnd_keep                  # LVE never touches surf.bnd_x/z
+    k = surf.kinem
+    k.alpha, k.h, k.alphadot, k.hdot, k.u, k.udot = list(s2.kinem)
+    surf.levflag[0] = s2.levflag
+    surf.a0[0] = s2.a0
+    for v, arrs in zip((ifr_surf.bv, ifr_field.tev, ifr_field.lev, ifr_field.extv), keep2):
+        v.assign(*arrs)
+    surf.bv.s[:] = circ[:npan]                               # LVE.jl:156-157
+    # curfield = body-frame twin of IFR_field at t + dtstar (LVE.jl:238-242, vor_BFR calcs.jl:732-754)
+    al, X0, Z0 = table[-1, 1], table[-1, 7], table[-1, 8]
+    pvt = surf.pvt
+    for src, dst in ((ifr_field.tev, curfield.tev), (ifr_field.lev, curfield.lev)):
+        n = len(src)
+        bx = (src.x - X0 - pvt) * np.cos(al) - (src.z - Z0) * np.sin(al) + pvt
+        bz = (src.x - X0 - pvt) * np.sin(al) + (src.z - Z0) * np.cos(al)
+        dst.assign(bx, bz, src.s.copy(), np.full(n, 0.02 * surf.c), np.zeros(n), np.zeros(n))
+    mat = np.ascontiguousarray(m9[1:, :8])                   # the reference records loads for i > 0 only
+    tevhist = np.stack([table[:niter, 0], ifr_field.tev.s[:niter]], axis=1)
+    shed = m9[:, 8] > 0.5
+    levhist = np.stack([table[:niter, 0][shed], ifr_field.lev.s[: int(shed.sum())]], axis=1) if shed.any() else np.zeros((0, 2))
+    return 0, ifr_field, mat, tevhist, levhist
