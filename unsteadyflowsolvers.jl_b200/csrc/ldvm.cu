@@ -1024,29 +1024,31 @@ __device__ void lve_head(const LdvmDev &d) {
 // Gauss-Jordan with partial pivoting on the augmented matrix A[n][n+1] in shared memory
 // (stands in for Julia's a\RHS, LVE.jl:93,140); all threads of the CTA take part
 __device__ void cta_solve(double *A, int n, int *piv_sh) {
-    const int tid = threadIdx.x, ld = n + 1;
+    const int tid = threadIdx.x, ld = n + 1, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    (void)piv_sh;
     for (int c = 0; c < n; c++) {
-        if (tid < 32) {
+        if (warp == 0) {   // pivot search + row swap by one warp (no CTA barrier in between)
             double best = -1.0; int bi = c;
-            for (int r = c + tid; r < n; r += 32) { const double v = fabs(A[r * ld + c]); if (v > best) { best = v; bi = r; } }
+            for (int r = c + lane; r < n; r += 32) { const double v = fabs(A[r * ld + c]); if (v > best) { best = v; bi = r; } }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
             }
-            if (tid == 0) *piv_sh = bi;
+            if (bi != c) for (int j = c + lane; j <= n; j += 32) { const double t = A[c * ld + j]; A[c * ld + j] = A[bi * ld + j]; A[bi * ld + j] = t; }
         }
         __syncthreads();
-        const int p = *piv_sh;
-        if (p != c) for (int j = tid; j <= n; j += blockDim.x) { const double t = A[c * ld + j]; A[c * ld + j] = A[p * ld + j]; A[p * ld + j] = t; }
-        __syncthreads();
         const double inv = 1.0 / A[c * ld + c];
-        // eliminate column c from every other row (factors read before any write: column c is not written)
-        const int w = n - c;                    // columns c+1 .. n (incl. rhs)
-        for (int e = tid; e < n * w; e += blockDim.x) {
-            const int r = e / w, j = c + 1 + e % w;
-            if (r != c) A[r * ld + j] -= (A[r * ld + c] * inv) * A[c * ld + j];
+        // eliminate column c from every other row: lanes own columns right of c, each warp a strided set
+        // of rows; the row loop is unrolled so the shared-memory round trips of independent rows overlap
+        // (column c itself is only read and row c only read, so there is no hazard inside the step)
+        for (int j = c + 1 + lane; j <= n; j += 32) {
+            const double pc = A[c * ld + j] * inv;
+#pragma unroll 4
+            for (int r = warp; r < n; r += nwarps) {
+                if (r != c) A[r * ld + j] -= A[r * ld + c] * pc;
+            }
         }
         __syncthreads();
     }
@@ -1058,7 +1060,7 @@ __device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1)
     LveState *L = d.lve;
     const int tid = threadIdx.x, nd = d.ndiv, np = nd - 1, ld = nd + 1;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    __shared__ double uind[kNdMax], wind[kNdMax], relx[kNdMax], relz[kNdMax], circ[kNdMax], a1[kNdMax], sc[16];
+    __shared__ double uind[kNdMax], wind[kNdMax], relx[kNdMax], relz[kNdMax], circ[kNdMax], a1[kNdMax], prev[kNdMax], sc[16];
     __shared__ int piv_sh, lev_shed;
     double *la = d.lvea;
     const double alpha = s->kin[0], alphadot = s->kin[2], hdot = s->kin[3], u = s->kin[4];
@@ -1079,11 +1081,13 @@ __device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1)
         const double cx = la[LV_CX * nd + j], cz = la[LV_CZ * nd + j];
         relx[j] = (ca * u - sa * (-hdot)) + (-alphadot * cz);      // LVE.jl:86
         relz[j] = (sa * u + ca * (-hdot)) + alphadot * (cx - d.pvt);
+        prev[j] = la[LV_PREV * nd + j];
     }
+    __syncthreads();
     if (tid == 0) {
         lve_bfr(d.pvt, sa, ca, X0, Z0, d.wx[te - 1], d.wz[te - 1], &sc[0], &sc[1]);   // x_w, z_w  :74
         double sp = 0.0;
-        for (int j = 0; j < np; j++) sp += la[LV_PREV * nd + j];
+        for (int j = 0; j < np; j++) sp += prev[j];
         sc[2] = sp;
         lev_shed = 0;
     }
@@ -1135,7 +1139,7 @@ __device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1)
     __syncthreads();
     for (int j = tid; j < np; j += blockDim.x) {                                            // :96-100
         double g1 = 0.0, g2 = 0.0;
-        for (int k = 0; k < j; k++) { g1 += la[LV_PREV * nd + k]; g2 += circ[k]; }
+        for (int k = 0; k < j; k++) { g1 += prev[k]; g2 += circ[k]; }
         la[LV_CHG * nd + j] = (g2 - g1) / d.dt;
     }
     const double xx = 1 - 2 * la[LV_DS * nd] / d.c;
