@@ -65,6 +65,14 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # fresh checkout: compile the extension in-tree once (nvcc cross-compiles without a GPU);
+        # this is a build step, not a fallback -- if it fails the error below is raised
+        import subprocess
+        try:
+            subprocess.run(["make", "-s", "-j8", "-C", os.path.join(_HERE, "csrc")], check=True, capture_output=True, timeout=900)
+        except Exception:
+            pass
+    if not os.path.exists(LIB_PATH):
         raise UnsflowError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C unsteadyflowsolvers.jl_b200/csrc). There is no CPU fallback."
