@@ -377,3 +377,38 @@ def test_lve_panel_solver(gpu_lib, uf, oracle):
         assert tevhist.shape == (n + 1, 2) and levhist.shape[0] == len(ifr_field.lev)
         if lesp < 1:
             assert len(ifr_field.lev) > 10
+
+
+def test_error_paths_on_device(gpu_lib, uf):
+    """reference-like error behaviour through the C ABI: bad arguments and exceeded capacities are
+    reported as errors with a message (no crash, no silent truncation)"""
+    import ctypes as C
+    from unsflow_b200.solvers import LdvmHandle, _opts
+    cabi = uf._cabi
+    surf, fld, _, dtstar = c1_surf(uf)
+    h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, 5, uf.delNone(), cabi.SOLVE_EXACT))
+    mat = np.zeros((6, 8), order="F")
+    assert gpu_lib.unsflow_ldvm_run(h._h, 3, mat.ctypes.data_as(cabi.c_double_p)) != 0          # no kinematics yet
+    assert b"set_kinematics" in gpu_lib.unsflow_last_error()
+    h.set_kinematics(uf.kinematics_table(surf, fld, 5, dtstar))
+    assert gpu_lib.unsflow_ldvm_run(h._h, 6, mat.ctypes.data_as(cabi.c_double_p)) != 0          # beyond max_steps
+    assert b"max_steps" in gpu_lib.unsflow_last_error()
+    h.run(5)
+    # get_state into arrays that are too small
+    small = uf.TwoDFlowField()
+    small.tev.resize(2)
+    keep = []
+    from unsflow_b200.solvers import field_struct, surf_struct
+    s, f = surf_struct(surf, keep), field_struct(small, keep)
+    assert gpu_lib.unsflow_ldvm_get_state(h._h, C.byref(s), C.byref(f)) != 0
+    assert b"capacity" in gpu_lib.unsflow_last_error()
+    h.close()
+    with pytest.raises(ValueError):
+        uf.ldvm(surf, fld, 3, dtstar, 2)                                                         # invalid start flag (solvers.jl:157)
+    with pytest.raises(uf.UnsflowError, match="ndiv"):
+        bad = uf.TwoDSurf("FlatPlate", 0.25, surf.kindef, [0.1], ndiv=300)
+        uf.ldvm(bad, uf.TwoDFlowField(), 2, dtstar, write_summary=False)
+    with pytest.raises(uf.UnsflowError, match="share"):
+        a = uf.TwoDSurf("FlatPlate", 0.25, surf.kindef, [0.1], ndiv=70)
+        b = uf.TwoDSurf("FlatPlate", 0.25, surf.kindef, [0.1], ndiv=60)
+        uf.ldvm([a, b], uf.TwoDFlowField(), 2, dtstar, write_summary=False)
