@@ -44,10 +44,18 @@ __global__ void __launch_bounds__(kSolveThreads) k_lve_solve(const LdvmDev d) {
     lve_solve(d, lve_dyn);
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_ensemble(const LdvmDev *members, long long nsteps) {
-    __shared__ double tile[4 * kEnsTile];
+__global__ void __launch_bounds__(kSolveThreads, 3) k_ensemble(const LdvmDev *members, long long nsteps, long long tot) {
+    extern __shared__ __align__(16) double ens_smem[];      // [5][tot]: x, z, g, vx, vz of this member
     __shared__ LdvmDev d;
-    if (threadIdx.x == 0) d = members[blockIdx.x];
+    const LdvmDev *g = members + blockIdx.x;
+    for (long long k = threadIdx.x; k < tot; k += blockDim.x) {
+        ens_smem[k] = g->wx[k]; ens_smem[tot + k] = g->wz[k]; ens_smem[2 * tot + k] = g->wg[k];
+        ens_smem[3 * tot + k] = g->wvx[k]; ens_smem[4 * tot + k] = g->wvz[k];
+    }
+    if (threadIdx.x == 0) {
+        d = *g;
+        d.wx = ens_smem; d.wz = ens_smem + tot; d.wg = ens_smem + 2 * tot; d.wvx = ens_smem + 3 * tot; d.wvz = ens_smem + 4 * tot;
+    }
     __syncthreads();
     double *p2u = const_cast<double *>(d.p2u), *p2w = const_cast<double *>(d.p2w);
     for (long long is = 0; is < nsteps; is++) {
@@ -55,13 +63,17 @@ __global__ void __launch_bounds__(kSolveThreads) k_ensemble(const LdvmDev *membe
         __syncthreads();
         if (d.driver != UNSFLOW_DRIVER_LAUTAT) {
             int S2;
-            ens_sweep(d, p2u, p2w, &S2, tile);
+            ens_sweep(d, p2u, p2w, &S2, ens_smem, tot);
             if (threadIdx.x == 0) d.S2 = S2;
             __syncthreads();
         }
         step_solve(d);
         __syncthreads();
-        ens_rollup(d, tile);
+        ens_rollup(d, ens_smem, tot);
+    }
+    for (long long k = threadIdx.x; k < tot; k += blockDim.x) {
+        g->wx[k] = ens_smem[k]; g->wz[k] = ens_smem[tot + k]; g->wg[k] = ens_smem[2 * tot + k];
+        g->wvx[k] = ens_smem[3 * tot + k]; g->wvz[k] = ens_smem[4 * tot + k];
     }
 }
 
@@ -801,7 +813,10 @@ int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64
     UF_CUDA(cudaEventCreate(&e0));
     UF_CUDA(cudaEventCreate(&e1));
     UF_CUDA(cudaEventRecord(e0, stream));
-    k_ensemble<<<(unsigned)M, kSolveThreads, 0, stream>>>(devs.p, nsteps);
+    const size_t ens_dyn = sizeof(double) * 5 * (size_t)tot;
+    UF_CHECK(ens_dyn <= 180 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 180 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
+    UF_CUDA(cudaFuncSetAttribute(k_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
+    k_ensemble<<<(unsigned)M, kSolveThreads, ens_dyn, stream>>>(devs.p, nsteps, tot);
     UF_CUDA(cudaGetLastError());
     UF_CUDA(cudaEventRecord(e1, stream));
     std::vector<double> hm((size_t)(M * nsteps * 8));

@@ -5,11 +5,14 @@
 namespace unsflow {
 
 // ---------------------------------------------------------------------------------------------
-// Ensemble kernel (config 3): one CTA per member runs the WHOLE step loop; the member's state
-// (a few hundred vortices, <100 KB) stays in L1/L2, induction tiles are staged in shared memory.
+// Ensemble kernel (config 3): one CTA per member runs the WHOLE step loop.  The member's wake
+// slabs (x, z, strength, vx, vz -- a few hundred to a few thousand vortices) live in SHARED
+// MEMORY for the whole run: k_ensemble points the member's LdvmDev at them, so the unchanged
+// single-surface step functions (step_head / step_solve) and the two block-level induction
+// loops below all work in place, with no staging tiles and no barriers inside the pair loops.
 // Members are independent: no inter-CTA communication, any number of GPUs by sharding members.
+// All ensemble vortices share the core radius 0.02c (calcs.jl:385,423), hence the scalar vc4.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEnsTile = 256;   // sources staged per shared-memory tile
 constexpr int kEnsR = 4;        // targets per thread in the member roll-up
 
 // pair kernel shared by the two block-level induction loops (13 FP64 instr, cubic rsqrt)
@@ -22,102 +25,90 @@ __device__ __forceinline__ void pair_acc(double xj, double zj, double gj, double
     w = fma(dx, m, w);
 }
 
-// cooperative load of sources [b, b+cnt) into a zero-strength-padded tile
-__device__ __forceinline__ void ens_stage(const LdvmDev &d, long long b, int cnt, double *sx, double *sz, double *sg, double *sv) {
-    for (int k = threadIdx.x; k < kEnsTile; k += blockDim.x) {
-        const bool ok = k < cnt;
-        sx[k] = ok ? d.wx[b + k] : 0.0;
-        sz[k] = ok ? d.wz[b + k] : 0.0;
-        sg[k] = ok ? d.wg[b + k] : 0.0;
-        sv[k] = ok ? d.wvc4[b + k] : 1.0;
-    }
-}
-
-// update_indbound (calcs.jl:35-38) inside one CTA: group g of threads owns sources j = g (mod G)
-__device__ void ens_sweep(const LdvmDev &d, double *p2u, double *p2w, int *S2_out, double *tile) {
+// update_indbound (calcs.jl:35-38) inside one CTA: group g of threads owns sources j = g (mod G);
+// 2 independent source chains per thread
+// (sm = the member's shared-memory slabs [x | z | g | vx | vz], each `tot` long: passed as a raw
+// shared pointer so the loops compile to LDS instead of generic loads)
+__device__ __forceinline__ void ens_sweep(const LdvmDev &d, double *p2u, double *p2w, int *S2_out, const double *sm, long long tot) {
+    const double *wx = sm, *wz = sm + tot, *wg = sm + 2 * tot;
     const StepState *s = d.st;
     const int nd = d.ndiv, G = max(1, (int)blockDim.x / nd);
     const int grp = threadIdx.x / nd, i = threadIdx.x - grp * nd;
     const bool act = grp < G;
-    double *sx = tile, *sz = tile + kEnsTile, *sg = tile + 2 * kEnsTile, *sv = tile + 3 * kEnsTile;
-    const double tx = act ? d.bnd_x[i] : 0.0, tz = act ? d.bnd_z[i] : 0.0;
-    double u = 0.0, w = 0.0;
-    for (int r = 0; r < 3; r++) {
-        for (long long b = s->wake.begin[r]; b < s->wake.end[r]; b += kEnsTile) {
-            const int cnt = (int)min((long long)kEnsTile, s->wake.end[r] - b);
-            __syncthreads();
-            ens_stage(d, b, cnt, sx, sz, sg, sv);
-            __syncthreads();
-            if (act)
-                for (int j = grp; j < cnt; j += G) pair_acc(sx[j], sz[j], sg[j], sv[j], tx, tz, u, w);
+    const double vc4 = d.vc4_new;
+    if (act) {
+        const double tx = d.bnd_x[i], tz = d.bnd_z[i];
+        double u0 = 0.0, w0 = 0.0, u1 = 0.0, w1 = 0.0;
+        for (int r = 0; r < 3; r++) {
+            const long long e = s->wake.end[r];
+            long long j = s->wake.begin[r] + grp;
+            for (; j + G < e; j += 2 * G) {
+                pair_acc(wx[j], wz[j], wg[j], vc4, tx, tz, u0, w0);
+                pair_acc(wx[j + G], wz[j + G], wg[j + G], vc4, tx, tz, u1, w1);
+            }
+            if (j < e) pair_acc(wx[j], wz[j], wg[j], vc4, tx, tz, u0, w0);
         }
+        p2u[grp * d.p2stride + i] = u0 + u1;
+        p2w[grp * d.p2stride + i] = w0 + w1;
     }
-    if (act) { p2u[grp * d.p2stride + i] = u; p2w[grp * d.p2stride + i] = w; }
     *S2_out = G;
-    __syncthreads();
 }
 
-// one chunk of RR*blockDim targets of region tr against all sources (free + bound vortices)
+// one chunk of RR*blockDim targets of region tr against all sources (free + bound vortices);
+// velocities go to vx, vz -- positions are convected only after every chunk is done
 template <int RR>
-__device__ __forceinline__ void ens_rollup_chunk(const LdvmDev &d, const StepState *s, int tr, long long tb, double *tile) {
-    double *sx = tile, *sz = tile + kEnsTile, *sg = tile + 2 * kEnsTile, *sv = tile + 3 * kEnsTile;
+__device__ __forceinline__ void ens_rollup_chunk(const LdvmDev &d, const StepState *s, int tr, long long tb, double *sm, long long tot) {
+    const double *wx = sm, *wz = sm + tot, *wg = sm + 2 * tot;
+    double *wvx = sm + 3 * tot, *wvz = sm + 4 * tot;
     const long long tend = s->wake.end[tr];
+    if (tb + (threadIdx.x & ~31) >= tend) return;      // warps without a single live target
+    const double vc4 = d.vc4_new;
     double tx[RR], tz[RR], u[RR], w[RR];
 #pragma unroll
     for (int r = 0; r < RR; r++) {
         const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
         const bool ok = i < tend;
-        tx[r] = ok ? d.wx[i] : 0.0; tz[r] = ok ? d.wz[i] : 0.0; u[r] = 0.0; w[r] = 0.0;
+        tx[r] = ok ? wx[i] : 0.0; tz[r] = ok ? wz[i] : 0.0; u[r] = 0.0; w[r] = 0.0;
     }
-    // warps without a single live target skip the arithmetic (they still help staging)
-    const bool warp_live = tb + (threadIdx.x & ~31) < tend;
     for (int sr = 0; sr < 4; sr++) {
-        for (long long b = s->wake.begin[sr]; b < s->wake.end[sr]; b += kEnsTile) {
-            const int cnt = (int)min((long long)kEnsTile, s->wake.end[sr] - b);
-            __syncthreads();
-            ens_stage(d, b, cnt, sx, sz, sg, sv);
-            __syncthreads();
-            if (warp_live) {
-                const int cpad = (cnt + 1) & ~1;
+        const long long b = s->wake.begin[sr], e = s->wake.end[sr];
 #pragma unroll 2
-                for (int j = 0; j < cpad; j++) {
-                    const double xj = sx[j], zj = sz[j], gj = sg[j], vj = sv[j];
+        for (long long j = b; j < e; j++) {
+            const double xj = wx[j], zj = wz[j], gj = wg[j];      // broadcast shared-memory reads
 #pragma unroll
-                    for (int r = 0; r < RR; r++) pair_acc(xj, zj, gj, vj, tx[r], tz[r], u[r], w[r]);
-                }
-            }
+            for (int r = 0; r < RR; r++) pair_acc(xj, zj, gj, vc4, tx[r], tz[r], u[r], w[r]);
         }
     }
 #pragma unroll
     for (int r = 0; r < RR; r++) {
         const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
         if (i < tend) {
-            d.wvx[i] = u[r] * kInvTwoPi + s->fs[0];      // calcs.jl:252-277
-            d.wvz[i] = w[r] * kInvTwoPi + s->fs[1];
+            wvx[i] = u[r] * kInvTwoPi + s->fs[0];      // calcs.jl:252-277
+            wvz[i] = w[r] * kInvTwoPi + s->fs[1];
         }
     }
 }
 
 // wakeroll (calcs.jl:222-294) inside one CTA
-__device__ void ens_rollup(const LdvmDev &d, double *tile) {
+__device__ __forceinline__ void ens_rollup(const LdvmDev &d, double *sm, long long tot) {
     StepState *s = d.st;
     for (int tr = 0; tr < 3; tr++) {
         for (long long tb = s->wake.begin[tr]; tb < s->wake.end[tr]; tb += (long long)kEnsR * blockDim.x) {
             const long long rem = s->wake.end[tr] - tb;
             const int nrow = (int)min((long long)kEnsR, (rem + blockDim.x - 1) / blockDim.x);   // block-uniform
             switch (nrow) {
-                case 1: ens_rollup_chunk<1>(d, s, tr, tb, tile); break;
-                case 2: ens_rollup_chunk<2>(d, s, tr, tb, tile); break;
-                case 3: ens_rollup_chunk<3>(d, s, tr, tb, tile); break;
-                default: ens_rollup_chunk<4>(d, s, tr, tb, tile); break;
+                case 1: ens_rollup_chunk<1>(d, s, tr, tb, sm, tot); break;
+                case 2: ens_rollup_chunk<2>(d, s, tr, tb, sm, tot); break;
+                case 3: ens_rollup_chunk<3>(d, s, tr, tb, sm, tot); break;
+                default: ens_rollup_chunk<4>(d, s, tr, tb, sm, tot); break;
             }
         }
     }
     __syncthreads();
     for (int tr = 0; tr < 3; tr++)                                // calcs.jl:280-291
         for (long long i = s->wake.begin[tr] + threadIdx.x; i < s->wake.end[tr]; i += blockDim.x) {
-            d.wx[i] += d.dt * d.wvx[i];
-            d.wz[i] += d.dt * d.wvz[i];
+            sm[i] += d.dt * sm[3 * tot + i];
+            sm[tot + i] += d.dt * sm[4 * tot + i];
         }
     __syncthreads();
 }
