@@ -254,10 +254,12 @@ def main():
     if world == 1:
         # the drop-in call itself: wakeroll(surf, curfield, dt) -> unsflow_wakeroll, host arrays
         xx, zz = x.copy(), z.copy()
-        a0 = time.perf_counter()
-        cabi.check(L.unsflow_wakeroll(n, cabi.dptr(xx), cabi.dptr(zz), up[2], up[3], dn[2], dn[3], NBV, up[4], up[5], up[6], up[7],
-                                      uinf, 0.0, dt))
-        extra["e2e_wakeroll_call_interactions_per_s"] = inter_step / (time.perf_counter() - a0)
+        for rep in range(2):      # the first call allocates the per-thread device scratch, the second is steady state
+            a0 = time.perf_counter()
+            cabi.check(L.unsflow_wakeroll(n, cabi.dptr(xx), cabi.dptr(zz), up[2], up[3], dn[2], dn[3], NBV, up[4], up[5], up[6], up[7],
+                                          uinf, 0.0, dt))
+            extra["e2e_wakeroll_call_interactions_per_s"] = inter_step / (time.perf_counter() - a0)
+        cabi.check(L.unsflow_release_scratch())
     # ---- verification on the same handle (all ranks take part): one step with dt = 0 on the
     # original field, 32 sampled targets against the oracle's long-double truth ----------------
     cabi.check(L.unsflow_wake_upload(h, *up))

@@ -64,6 +64,10 @@ int unsflow_update_indbound(int64_t n, const double *x, const double *z, const d
                             int64_t ndiv, const double *bnd_x, const double *bnd_z,
                             double *uind_out, double *wind_out);
 
+/* The four entry points above keep their device scratch (staging slabs, partial planes) per calling
+ * thread between calls; this frees it. */
+int unsflow_release_scratch(void);
+
 /* ---- device-resident wake (config "synthetic large-N rollup"; multi-GPU target slices) -- */
 typedef struct unsflow_wake unsflow_wake;
 

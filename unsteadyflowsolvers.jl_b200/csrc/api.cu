@@ -71,6 +71,12 @@ static bool uniform_vc(const HostGroup *g, int ng, double *vc_out) {
     return true;
 }
 
+struct Scratch {
+    DevBuf<double> src, t, part, out;
+    DevBuf<Regions> reg;
+};
+static thread_local Scratch g_scratch;
+
 // targets == nullptr -> targets are the first source group (mutual induction)
 static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx, const double *tz,
                        double *u_inout, double *w_inout, int accumulate, double fs_u, double fs_w, double dt,
@@ -84,10 +90,14 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     double vcu = 1.0;
     const bool uni = uniform_vc(g, ng, &vcu);
 
-    DevBuf<double> d_src, d_t, d_part, d_out;
-    DevBuf<Regions> d_reg;
+    // per-thread scratch reused across calls: the drop-in entry points (ind_vel, mutual_ind, wakeroll,
+    // update_indbound) are called once per time step by host-side solvers, and cudaMalloc/cudaFree of
+    // the partial planes would otherwise cost as much as a mid-size kernel (freed by
+    // unsflow_release_scratch or at thread exit)
+    DevBuf<double> &d_src = g_scratch.src, &d_t = g_scratch.t, &d_part = g_scratch.part, &d_out = g_scratch.out;
+    DevBuf<Regions> &d_reg = g_scratch.reg;
     const int narr = 4;
-    if (d_src.alloc(narr * tot)) return 2;
+    if (d_src.ensure(narr * tot)) return 2;
     // host staging: [x | z | g | vc4], padding g = 0, vc4 = 1
     std::vector<double> h((size_t)(narr * tot), 0.0);
     for (int64_t i = 0; i < tot; i++) h[3 * tot + i] = 1.0;
@@ -109,7 +119,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
         d_tx = d_src.p;
         d_tz = d_src.p + tot;
     } else {
-        if (d_t.alloc(2 * ntp)) return 2;
+        if (d_t.ensure(2 * ntp)) return 2;
         UF_CUDA(cudaMemcpyAsync(d_t.p, tx, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
         UF_CUDA(cudaMemcpyAsync(d_t.p + ntp, tz, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
         d_tx = d_t.p;
@@ -121,7 +131,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     for (int k = 0; k < ng; k++) { hreg[0].begin[k] = off[k]; hreg[0].end[k] = off[k] + g[k].n; }
     hreg[1].begin[0] = 0;
     hreg[1].end[0] = nt;
-    if (d_reg.alloc(2)) return 2;
+    if (d_reg.ensure(2)) return 2;
     UF_CUDA(cudaMemcpyAsync(d_reg.p, hreg, sizeof(hreg), cudaMemcpyHostToDevice, st));
 
     int64_t ns = 0;
@@ -135,8 +145,9 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     // few targets against many sources (update_indbound): dedicated sweep kernel
     const bool sweep = !sym && !self_targets && nt <= 256 && ns >= 2048 && sweep_supported((int)nt);
     if (sweep) plan.S = (int)std::max<int64_t>(1, std::min<int64_t>((ns + kTS - 1) / kTS + ng, 256));
-    if (d_part.alloc(sym ? (int64_t)ctas * 2 * tot : 2 * (int64_t)plan.S * ntp)) return 2;
-    if (d_out.alloc(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
+    const int64_t npart = sym ? (int64_t)ctas * 2 * tot : 2 * (int64_t)plan.S * ntp;
+    if (d_part.ensure(npart)) return 2;
+    if (d_out.ensure(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
 
     InduceArgs a;
     a.sx = d_src.p; a.sz = d_src.p + tot; a.sg = d_src.p + 2 * tot; a.svc4 = d_src.p + 3 * tot;
@@ -147,7 +158,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     a.pu = d_part.p; a.pw = d_part.p + (int64_t)plan.S * ntp;
     a.tstride = ntp;
     if (sym) {
-        if (d_part.zero(st)) return 2;
+        UF_CUDA(cudaMemsetAsync(d_part.p, 0, sizeof(double) * (size_t)npart, st));
         SymArgs sa;
         sa.x = a.sx; sa.z = a.sz; sa.g = a.sg;
         sa.reg = d_reg.p; sa.nreg = 1; sa.bv_reg = ng > 1 ? 1 : -1;
@@ -304,6 +315,11 @@ int unsflow_wakeroll(int64_t n, double *x, double *z, const double *s, const dou
 int unsflow_update_indbound(int64_t n, const double *x, const double *z, const double *s, const double *vc,
                             int64_t ndiv, const double *bnd_x, const double *bnd_z, double *uind, double *wind) {
     return unsflow_ind_vel(n, x, z, s, vc, ndiv, bnd_x, bnd_z, uind, wind);
+}
+
+int unsflow_release_scratch(void) {
+    g_scratch.src.release(); g_scratch.t.release(); g_scratch.part.release(); g_scratch.out.release(); g_scratch.reg.release();
+    return 0;
 }
 
 int unsflow_fp64_peak(double *tflops, double *sm_mhz_est) {

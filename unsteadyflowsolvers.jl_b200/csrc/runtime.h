@@ -21,6 +21,12 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    // grow-only variant for scratch that is reused across calls (keeps the allocation when it is
+    // already large enough)
+    int ensure(int64_t count) {
+        if (p && n >= count) return 0;
+        return alloc(count);
+    }
     int alloc(int64_t count) {
         release();
         if (count <= 0) count = 1;
