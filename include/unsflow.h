@@ -37,6 +37,15 @@ int unsflow_set_device(int device);
 /* SM count, SM clock (kHz), L2 bytes, total HBM bytes of the current device */
 int unsflow_device_info(int *sm_count, int *sm_clock_khz, int64_t *l2_bytes, int64_t *hbm_bytes);
 
+/* Accuracy of 1/sqrt(vc^4 + d^4) in the induction kernels (process-wide, affects later launches):
+ * FULL (default): one MUFU.RSQ64H seed + a cubic step, 2.7e-16 relative error per pair (measured) --
+ *   the same accuracy class as the reference's IEEE sqrt and divide;
+ * FAST: seed + a bias-centred Newton step, <= 6.5e-13 per pair (measured), two FP64 instructions less
+ *   per pair (+9 % throughput); still inside the 1e-12 parity tolerance but no longer round-off exact. */
+#define UNSFLOW_PRECISION_FULL 0
+#define UNSFLOW_PRECISION_FAST 1
+int unsflow_set_precision(int mode);
+
 /* ---- stateless kernels on HOST buffers ------------------------------------------------ */
 
 /* ind_vel(src::Vector{TwoDVort}, t_x, t_z) -> (uind, wind)   src/lowOrder2D/calcs.jl:462-477

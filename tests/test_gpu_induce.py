@@ -151,3 +151,22 @@ def test_measurement_helpers(gpu_lib, uf):
     assert e0.value < 1e-5 and e3.value < 1e-15
     print(f"\nFP64 DFMA peak {tf.value:.2f} TFLOP/s (~{mhz.value:.0f} MHz); rsqrt rel err seed {e0.value:.3e} "
           f"newton {e2.value:.3e} cubic {e3.value:.3e}")
+
+
+def test_fast_precision_mode_stays_inside_the_parity_tolerance(gpu_lib, uf, oracle):
+    """unsflow_set_precision(FAST): bias-centred Newton rsqrt, <= 6.5e-13 per pair -- still <= 1e-12
+    normalised, but measurably above the round-off level of the default FULL mode"""
+    x, z, g, vc = oracle.s_wake(60000)
+    idx = np.arange(0, 60000, 1000)
+    tu, tw, au, aw = oracle.ind_vel_truth(x, z, g, vc, x[idx], z[idx])
+    errs = {}
+    try:
+        for mode in (1, 0):
+            uf._cabi.check(gpu_lib.unsflow_set_precision(mode))
+            v = _vl(uf, x, z, g, vc)
+            uf.mutual_ind(v)                       # 60000 >= 36864: symmetric pair-tile kernel
+            errs[mode] = max(rel_err_normalised(v.vx[idx], tu, au), rel_err_normalised(v.vz[idx], tw, aw))
+    finally:
+        gpu_lib.unsflow_set_precision(0)
+    assert errs[0] < 1e-14 and 1e-15 < errs[1] <= TOL
+    assert gpu_lib.unsflow_set_precision(7) != 0

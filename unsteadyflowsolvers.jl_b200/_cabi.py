@@ -90,6 +90,7 @@ def lib():
         "unsflow_wakeroll": [i64, d, d, d, d, d, d, i64, d, d, d, d, C.c_double, C.c_double, C.c_double],
         "unsflow_update_indbound": [i64, d, d, d, d, i64, d, d, d, d],
         "unsflow_release_scratch": [],
+        "unsflow_set_precision": [C.c_int],
         "unsflow_nccl_unique_id": [vp],
         "unsflow_partition": [i64, C.c_int, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)],
         "unsflow_wake_create": [C.POINTER(vp), i64, i64, C.c_int, C.c_int, vp, C.c_int],

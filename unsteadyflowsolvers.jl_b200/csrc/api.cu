@@ -32,7 +32,10 @@ int require_device() {
     return 0;
 }
 
+static int g_order_override = 0;   // 0 = environment/default, 2 or 3 = set through the API
+
 int rsqrt_order() {
+    if (g_order_override) return g_order_override;
     static int order = [] {
         const char *e = getenv("UNSFLOW_RSQRT_ORDER");
         int o = e ? atoi(e) : 3;
@@ -315,6 +318,12 @@ int unsflow_wakeroll(int64_t n, double *x, double *z, const double *s, const dou
 int unsflow_update_indbound(int64_t n, const double *x, const double *z, const double *s, const double *vc,
                             int64_t ndiv, const double *bnd_x, const double *bnd_z, double *uind, double *wind) {
     return unsflow_ind_vel(n, x, z, s, vc, ndiv, bnd_x, bnd_z, uind, wind);
+}
+
+int unsflow_set_precision(int mode) {
+    UF_CHECK(mode == UNSFLOW_PRECISION_FULL || mode == UNSFLOW_PRECISION_FAST, "unsflow_set_precision: mode must be 0 (full) or 1 (fast)");
+    g_order_override = mode == UNSFLOW_PRECISION_FAST ? 2 : 3;
+    return 0;
 }
 
 int unsflow_release_scratch(void) {
