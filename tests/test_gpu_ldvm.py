@@ -412,3 +412,19 @@ def test_error_paths_on_device(gpu_lib, uf):
         a = uf.TwoDSurf("FlatPlate", 0.25, surf.kindef, [0.1], ndiv=70)
         b = uf.TwoDSurf("FlatPlate", 0.25, surf.kindef, [0.1], ndiv=60)
         uf.ldvm([a, b], uf.TwoDFlowField(), 2, dtstar, write_summary=False)
+
+
+def test_500_step_attached_history(gpu_lib, uf, oracle):
+    """north_star criterion verbatim: Cl/Cd/Cm histories <= 1e-8 over the first 500 steps (attached
+    flow: pitch-plunge below the LESP threshold, so round-off does not amplify)"""
+    kin = uf.KinemDef(uf.SinDef(2 * math.pi / 180, 4 * math.pi / 180, 0.3, 0.0), uf.CosDef(0.0, 0.05, 0.3, 0.0), uf.ConstDef(1.0))
+    surf = uf.TwoDSurf("FlatPlate", 0.3, kin, [5.0])
+    fld = uf.TwoDFlowField()
+    n, dtstar = 500, 0.015
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    assert len(fld.lev) == 0 and len(fld.tev) == n
+    err = np.max(np.abs(mat[:, 5:8] - omat[:, 5:8]))
+    assert err <= HTOL, err
+    assert err < 1e-11            # in practice round-off level
+    _cmp_state(surf, fld, sim)
