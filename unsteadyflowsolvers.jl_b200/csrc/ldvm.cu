@@ -89,7 +89,7 @@ struct unsflow_ldvm {
     int nsurf = 1, mat_cols = 8;
     DevBuf<SurfState> ms;
     DevBuf<LveState> lves;    // LVE driver only
-    DevBuf<double> lvea;
+    DevBuf<double> lvea, lve_binv;
     int64_t cap_t = 0, cap_l = 0, cap_e = 0, bvpad = 0, tot = 0;
     int64_t off_t = 0, off_l = 0, off_e = 0, off_b = 0;
     int64_t ntev0 = 0, nlev0 = 0, nextv = 0;
@@ -339,6 +339,38 @@ int unsflow_lve_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow
         a[LV_VX * nd + j] = sf->x[j] + .25 * ds * cd; a[LV_VZ * nd + j] = sf->cam[j] + .25 * ds * sd;
         a[LV_CX * nd + j] = sf->x[j] + .75 * ds * cd; a[LV_CZ * nd + j] = sf->cam[j] + .75 * ds * sd;
     }
+    // constant part B of influence_coeff (calcs.jl:756-787): bound-vortex columns (singular kernel, body
+    // frame), Kelvin row of ones, and the unit vector e_np in place of the moving wake column; inverted
+    // once (Gauss-Jordan, partial pivoting, long double) for the per-step Sherman-Morrison update
+    std::vector<long double> B((size_t)nd * nd, 0.0L), Bi((size_t)nd * nd, 0.0L);
+    for (int i = 0; i < np; i++)
+        for (int j = 0; j < np; j++) {
+            const double xd = a[LV_VX * nd + j] - a[LV_CX * nd + i], zd = a[LV_VZ * nd + j] - a[LV_CZ * nd + i];
+            const double dsq = xd * xd + zd * zd;
+            const double uu = -zd / (kTwoPi * dsq), ww = xd / (kTwoPi * dsq);
+            B[(size_t)i * nd + j] = uu * a[LV_NX * nd + i] + ww * a[LV_NZ * nd + i];
+        }
+    for (int j = 0; j < nd; j++) B[(size_t)np * nd + j] = 1.0L;
+    for (int i = 0; i < nd; i++) a[LV_A1 * nd + i] = (double)B[(size_t)i * nd];      // first column of a (calcs.jl:817)
+    for (int i = 0; i < nd; i++) Bi[(size_t)i * nd + i] = 1.0L;
+    for (int c = 0; c < nd; c++) {
+        int piv = c;
+        for (int r = c + 1; r < nd; r++) if (fabsl(B[(size_t)r * nd + c]) > fabsl(B[(size_t)piv * nd + c])) piv = r;
+        if (fabsl(B[(size_t)piv * nd + c]) == 0.0L) { set_error("unsflow_lve_create: singular panel influence matrix"); return fail(1); }
+        if (piv != c) for (int j = 0; j < nd; j++) { std::swap(B[(size_t)c * nd + j], B[(size_t)piv * nd + j]); std::swap(Bi[(size_t)c * nd + j], Bi[(size_t)piv * nd + j]); }
+        const long double inv = 1.0L / B[(size_t)c * nd + c];
+        for (int j = 0; j < nd; j++) { B[(size_t)c * nd + j] *= inv; Bi[(size_t)c * nd + j] *= inv; }
+        for (int r = 0; r < nd; r++) {
+            if (r == c) continue;
+            const long double f = B[(size_t)r * nd + c];
+            if (f == 0.0L) continue;
+            for (int j = 0; j < nd; j++) { B[(size_t)r * nd + j] -= f * B[(size_t)c * nd + j]; Bi[(size_t)r * nd + j] -= f * Bi[(size_t)c * nd + j]; }
+        }
+    }
+    std::vector<double> binv((size_t)nd * nd);
+    for (size_t k = 0; k < binv.size(); k++) binv[k] = (double)Bi[k];
+    if (h->lve_binv.alloc((int64_t)nd * nd)) return fail(2);
+    if (cudaMemcpy(h->lve_binv.p, binv.data(), sizeof(double) * binv.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("unsflow_lve_create: upload failed"); return fail(2); }
     LveState L;
     memset(&L, 0, sizeof(L));
     const double x = 1 - 2 * a[LV_DS * nd] / sf->c;        // LVE.jl:50-52
@@ -350,7 +382,7 @@ int unsflow_lve_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow
         set_error("unsflow_lve_create: upload failed");
         return fail(2);
     }
-    const size_t dyn = sizeof(double) * nd * (nd + 1);
+    const size_t dyn = sizeof(double) * nd * nd;
     // static + dynamic shared memory exceed the 48 KB default already at ndiv = 70: always opt in
     if (cudaFuncSetAttribute(k_lve_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
         set_error("unsflow_lve_create: cannot reserve %zu bytes of shared memory", dyn);
@@ -358,6 +390,7 @@ int unsflow_lve_create(unsflow_ldvm **out, const unsflow_surf *sf, const unsflow
     }
     h->dev.lve = h->lves.p;
     h->dev.lvea = h->lvea.p;
+    h->dev.lve_binv = h->lve_binv.p;
     return 0;
 }
 
@@ -463,7 +496,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         h->dev.S2 = p2.S;
         h->launches++;
     }
-    if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * (h->ndiv + 1), st>>>(h->dev);
+    if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * h->ndiv, st>>>(h->dev);
     else if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     else k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;

@@ -11,11 +11,12 @@ namespace unsflow {
 // calcs.jl:732-754) is never materialised: the collocation points are mapped into the inertial
 // frame for the sweep and the induced velocity is rotated back (a rigid transform preserves the
 // Vatistas kernel).  Each iteration: k_lve_head, k_sweep (collocation points x wake),
-// k_lve_solve (influence matrix, dense (ndiv x ndiv) Gauss-Jordan with partial pivoting in shared
-// memory, LEV ejection logic, panel pressures and loads), then the usual roll-up + finish.
+// k_lve_solve (the influence matrix is a rank-1 / rank-2 update of a constant matrix whose inverse is
+// computed once on the host: Sherman-Morrison / Woodbury with 2-4 warp-parallel mat-vecs per step,
+// LEV ejection logic, panel pressures and loads), then the usual roll-up + finish.
 // =============================================================================================
-constexpr int kLveArrays = 14;
-enum { LV_DS, LV_CSD, LV_NX, LV_NZ, LV_TX, LV_TZ, LV_VX, LV_VZ, LV_CX, LV_CZ, LV_PREV, LV_CHG, LV_CIRC, LV_REL };
+constexpr int kLveArrays = 15;
+enum { LV_DS, LV_CSD, LV_NX, LV_NZ, LV_TX, LV_TZ, LV_VX, LV_VZ, LV_CX, LV_CZ, LV_PREV, LV_CHG, LV_CIRC, LV_REL, LV_A1 };
 struct LveState {
     double gamma_crit, rho, lev_stop, t_start, te_x, te_cam, le_x, le_cam, ifr_u0, ifr_hdot0;
     double alpha, X0, Z0;    // frame of the current iteration
@@ -65,47 +66,27 @@ __device__ void lve_head(const LdvmDev &d) {
     }
 }
 
-// Gauss-Jordan with partial pivoting on the augmented matrix A[n][n+1] in shared memory
-// (stands in for Julia's a\RHS, LVE.jl:93,140); all threads of the CTA take part
-__device__ void cta_solve(double *A, int n, int *piv_sh) {
-    const int tid = threadIdx.x, ld = n + 1, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    (void)piv_sh;
-    for (int c = 0; c < n; c++) {
-        if (warp == 0) {   // pivot search + row swap by one warp (no CTA barrier in between)
-            double best = -1.0; int bi = c;
-            for (int r = c + lane; r < n; r += 32) { const double v = fabs(A[r * ld + c]); if (v > best) { best = v; bi = r; } }
+// y = Binv * v for the shared-memory copy of Binv (n x n, row-major): one warp per row, lanes strided
+// over the columns, butterfly sum.
+__device__ __forceinline__ void cta_matvec(const double *Binv, int n, const double *v, double *y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < n; r += nwarps) {
+        double acc = 0.0;
+        for (int j = lane; j < n; j += 32) acc = fma(Binv[r * n + j], v[j], acc);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (bi != c) for (int j = c + lane; j <= n; j += 32) { const double t = A[c * ld + j]; A[c * ld + j] = A[bi * ld + j]; A[bi * ld + j] = t; }
-        }
-        __syncthreads();
-        const double inv = 1.0 / A[c * ld + c];
-        // eliminate column c from every other row: lanes own columns right of c, each warp a strided set
-        // of rows; the row loop is unrolled so the shared-memory round trips of independent rows overlap
-        // (column c itself is only read and row c only read, so there is no hazard inside the step)
-        for (int j = c + 1 + lane; j <= n; j += 32) {
-            const double pc = A[c * ld + j] * inv;
-#pragma unroll 4
-            for (int r = warp; r < n; r += nwarps) {
-                if (r != c) A[r * ld + j] -= A[r * ld + c] * pc;
-            }
-        }
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[r] = acc;
     }
-    // x_i = A[i][n] / A[i][i]  (left to the caller)
 }
 
-__device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1) */) {
+__device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*nd doubles for Binv */) {
     StepState *s = d.st;
     LveState *L = d.lve;
-    const int tid = threadIdx.x, nd = d.ndiv, np = nd - 1, ld = nd + 1;
+    const int tid = threadIdx.x, nd = d.ndiv, np = nd - 1;
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    __shared__ double uind[kNdMax], wind[kNdMax], relx[kNdMax], relz[kNdMax], circ[kNdMax], a1[kNdMax], prev[kNdMax], sc[16];
-    __shared__ int piv_sh, lev_shed;
+    __shared__ double uind[kNdMax], wind[kNdMax], relx[kNdMax], relz[kNdMax], circ[kNdMax], prev[kNdMax], sc[16];
+    __shared__ double rhs[kNdMax], wcol[kNdMax], lcol[kNdMax], yv[kNdMax], zw[kNdMax], zl[kNdMax];
+    __shared__ int lev_shed;
     double *la = d.lvea;
     const double alpha = s->kin[0], alphadot = s->kin[2], hdot = s->kin[3], u = s->kin[4];
     double sa, ca;
@@ -137,49 +118,44 @@ __device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1)
     }
     __syncthreads();
     const double x_w = sc[0], z_w = sc[1];
-    // ---- influence_coeff (calcs.jl:756-787) + RHS (LVE.jl:78-90) into the augmented matrix -------
-    auto build = [&](bool lev, double x_lev, double z_lev, double gcu) {
-        for (int e = tid; e < nd * nd; e += blockDim.x) {
-            const int i = e / nd, j = e % nd;
-            double v;
-            if (i == np) v = 1.0;
-            else {
-                const double t_x = la[LV_CX * nd + i], t_z = la[LV_CZ * nd + i];
-                double uu, ww;
-                // column j of the (possibly shifted) matrix: unshifted source index
-                const int js = lev ? j + 1 : j;                      // mod_influence_coeff shifts left (:818)
-                if (lev && j == nd - 1) {
-                    const double xd = x_lev - t_x, zd = z_lev - t_z, dsq = xd * xd + zd * zd;
-                    const double den = kTwoPi * sqrt(d.vc4_new + dsq * dsq);
-                    uu = -zd / den; ww = xd / den;
-                } else if (js < np) {
-                    const double xd = la[LV_VX * nd + js] - t_x, zd = la[LV_VZ * nd + js] - t_z, dsq = xd * xd + zd * zd;
-                    uu = -zd / (kTwoPi * dsq); ww = xd / (kTwoPi * dsq);
-                } else {
-                    const double xd = x_w - t_x, zd = z_w - t_z, dsq = xd * xd + zd * zd;
-                    const double den = kTwoPi * sqrt(d.vc4_new + dsq * dsq);
-                    uu = -zd / den; ww = xd / den;
-                }
-                v = uu * la[LV_NX * nd + i] + ww * la[LV_NZ * nd + i];
-            }
-            A[i * ld + j] = v;
-        }
+    // ---- a\RHS (LVE.jl:93) without refactorising every step -----------------------------------------
+    // The influence matrix of influence_coeff (calcs.jl:756-787) is  A = B + (w - e_np) e_np^T : the
+    // bound-vortex columns and the Kelvin row of ones never change (B, with the unit vector e_np as its
+    // last column, is inverted ONCE on the host), only the wake column w moves.  Sherman-Morrison:
+    //   x = y - z * y_np / (1 + z_np),   y = Binv RHS,   z = Binv w - Binv[:, np].
+    double *Binv = A;                                   // dynamic shared memory: nd x nd
+    for (int e = tid; e < nd * nd; e += blockDim.x) Binv[e] = d.lve_binv[e];
+    auto fill_column = [&](double *col, double xs, double zs) {      // Vatistas-core source (calcs.jl:776-782)
         for (int i = tid; i < nd; i += blockDim.x) {
-            double rhs;
-            if (i == np) rhs = sc[2] - (lev ? gcu : 0.0);                                  // :78, :138
-            else {
-                rhs = -((relx[i] + uind[i]) * la[LV_NX * nd + i] + (relz[i] + wind[i]) * la[LV_NZ * nd + i]);
-                if (lev) rhs -= gcu * a1[i];                                               // :136
-            }
-            A[i * ld + nd] = rhs;
+            if (i == np) { col[i] = 1.0; continue; }
+            const double xd = xs - la[LV_CX * nd + i], zd = zs - la[LV_CZ * nd + i], dsq = xd * xd + zd * zd;
+            const double den = kTwoPi * sqrt(d.vc4_new + dsq * dsq);
+            col[i] = (-zd / den) * la[LV_NX * nd + i] + (xd / den) * la[LV_NZ * nd + i];
         }
     };
-    build(false, 0.0, 0.0, 0.0);
+    auto fill_rhs = [&](bool lev, double gcu) {
+        for (int i = tid; i < nd; i += blockDim.x) {
+            double r;
+            if (i == np) r = sc[2] - (lev ? gcu : 0.0);                                    // :78, :138
+            else {
+                r = -((relx[i] + uind[i]) * la[LV_NX * nd + i] + (relz[i] + wind[i]) * la[LV_NZ * nd + i]);   // :89
+                if (lev) r -= gcu * la[LV_A1 * nd + i];                                    // :136 (a1 = first column of a)
+            }
+            rhs[i] = r;
+        }
+    };
+    fill_column(wcol, x_w, z_w);
+    fill_rhs(false, 0.0);
     __syncthreads();
-    for (int i = tid; i < nd; i += blockDim.x) a1[i] = A[i * ld + 0];                      // first column (calcs.jl:817)
+    cta_matvec(Binv, nd, rhs, yv);
+    cta_matvec(Binv, nd, wcol, zw);
     __syncthreads();
-    cta_solve(A, nd, &piv_sh);
-    for (int i = tid; i < nd; i += blockDim.x) circ[i] = A[i * ld + nd] / A[i * ld + i];   // circ = a\RHS :93
+    for (int i = tid; i < nd; i += blockDim.x) zw[i] -= Binv[i * nd + np];
+    __syncthreads();
+    {
+        const double fac = yv[np] / (1.0 + zw[np]);
+        for (int i = tid; i < nd; i += blockDim.x) circ[i] = yv[i] - zw[i] * fac;           // circ = a\RHS :93
+    }
     __syncthreads();
     for (int j = tid; j < np; j += blockDim.x) {                                            // :96-100
         double g1 = 0.0, g2 = 0.0;
@@ -215,14 +191,32 @@ __device__ void lve_solve(const LdvmDev &d, double *A /* dynamic smem: nd*(nd+1)
     __syncthreads();
     if (lev_shed) {
         const double gcu = sc[6];
-        build(true, sc[4], sc[5], gcu);                                                     // mod_influence_coeff + RHS :127-138
+        // mod_influence_coeff (calcs.jl:789-836) drops the first bound column, shifts left and appends the
+        // LEV column l: a' = [b_1 .. b_{np-1}, w, l].  Moving l to the front, a'' = [l, b_1 .. b_{np-1}, w]
+        //   = B + (l - b_0) e_0^T + (w - e_np) e_np^T  -- a rank-2 update of the same B (Woodbury):
+        //   x'' = y - Z (I + V^T Z)^{-1} V^T y,  Z = [Binv l - e_0, z],  V = [e_0, e_np],
+        // with x'' = [G_lev, G_1 .. G_{np-1}, G_wake]  (the reference's shifted circ, LVE.jl:142-145).
+        fill_column(lcol, sc[4], sc[5]);
+        fill_rhs(true, gcu);
         __syncthreads();
-        cta_solve(A, nd, &piv_sh);
-        __shared__ double c2[kNdMax];
-        for (int i = tid; i < nd; i += blockDim.x) c2[i] = A[i * ld + nd] / A[i * ld + i];  // :140
+        cta_matvec(Binv, nd, rhs, yv);
+        cta_matvec(Binv, nd, lcol, zl);
         __syncthreads();
-        if (tid == 0) d.wg[s->wake.end[1] - 1] = c2[nd - 1];                                // :142
-        for (int i = tid; i < nd; i += blockDim.x) circ[i] = i == 0 ? gcu : c2[i - 1];      // :144-145
+        if (tid == 0) {
+            zl[0] -= 1.0;
+            const double m00 = 1.0 + zl[0], m01 = zw[0], m10 = zl[np], m11 = 1.0 + zw[np];
+            const double det = m00 * m11 - m01 * m10;
+            sc[8] = (yv[0] * m11 - m01 * yv[np]) / det;
+            sc[9] = (m00 * yv[np] - yv[0] * m10) / det;
+        }
+        __syncthreads();
+        {
+            const double c0 = sc[8], c1 = sc[9];
+            for (int i = tid; i < nd; i += blockDim.x) rhs[i] = yv[i] - zl[i] * c0 - zw[i] * c1;   // x''
+        }
+        __syncthreads();
+        if (tid == 0) d.wg[s->wake.end[1] - 1] = rhs[0];                                    // LEV strength :142
+        for (int i = tid; i < nd; i += blockDim.x) circ[i] = i == 0 ? gcu : rhs[i];         // :144-145
         __syncthreads();
     }
     // ---- strengths (:154-162), loads (:203-232) -------------------------------------------------

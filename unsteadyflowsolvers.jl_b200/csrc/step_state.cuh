@@ -50,6 +50,7 @@ struct LdvmDev {
     SurfState *ms;       // [nsurf] (multi-surface driver only)
     LveState *lve;       // LVE driver only
     double *lvea;        // LVE panel arrays [kLveArrays][ndiv]
+    const double *lve_binv;   // LVE: inverse of the constant part of the influence matrix [ndiv][ndiv]
     int nsurf;
     int ndiv, naterm, driver, solve_mode, del_kind;
     long long del_limit;
