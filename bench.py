@@ -327,14 +327,9 @@ def main():
         except Exception as e:
             ens = {"error": str(e)[:200]}
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- extra: LDVM steps/s with a 1e5-vortex wake (config C2 regime), single GPU ------------
-    if world == 1 and args.ldvm_steps > 0:
+    # ---- extra: LDVM steps/s with a 1e5-vortex wake (config C2 regime); with several GPUs the roll-up
+    # pair tiles are split over the ranks (unsflow_ldvm_set_parallel), everything else is replicated ----
+    if args.ldvm_steps > 0:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             from cases import c2_surf
@@ -345,15 +340,35 @@ def main():
             fld.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
             ns = args.ldvm_steps
             hh = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, ns + 3, uf.delNone(), cabi.SOLVE_EXACT))
+            if world > 1:
+                uid2 = (C.c_ubyte * 128)()
+                t2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    cabi.check(L.unsflow_nccl_unique_id(uid2))
+                    t2.copy_(torch.tensor(list(uid2), dtype=torch.uint8))
+                dist.broadcast(t2, 0)
+                for i, v in enumerate(t2.cpu().tolist()):
+                    uid2[i] = v
+                hh.set_parallel(rank, world, uid2)
             hh.set_kinematics(uf.kinematics_table(surf, fld, ns + 3, dtstar))
             hh.run(3)
+            barrier()
             hh.run(ns)
             ms, nl = hh.timing()
             hh.close()
-            extra["ldvm_steps_per_s_at_N1e5"] = ns / (ms * 1e-3)
+            tl = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            extra["ldvm_steps_per_s_at_N1e5"] = ns / (tl.item() * 1e-3)
             extra["ldvm_launches_per_step"] = nl / ns
         except Exception as e:   # never lose the headline line
             extra["ldvm_error"] = str(e)[:200]
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     ach = FLOP_PER_INTERACTION * inter_step * K / (Tk_ms * 1e-3) / 1e12 / 1.0   # per-rank kernel = 1/world of the pairs
     ach_per_gpu = ach / world
