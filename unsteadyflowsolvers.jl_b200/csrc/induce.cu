@@ -59,17 +59,21 @@ int launch_induce_direct(const InduceArgs &a, const InducePlan &p, bool uniform,
 
 int sweep_supported(int ndiv) { return ndiv >= 1 && ndiv <= 256; }
 
-template <int RT>
+template <int RT, int TS>
 static void launch_sweep_rt(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
-    if (uniform) k_sweep<RT, true><<<S, kThreads, 0, st>>>(a, ndiv);
-    else k_sweep<RT, false><<<S, kThreads, 0, st>>>(a, ndiv);
+    if (uniform) k_sweep<RT, true, TS><<<S, kThreads, 0, st>>>(a, ndiv);
+    else k_sweep<RT, false, TS><<<S, kThreads, 0, st>>>(a, ndiv);
 }
 
-int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
+int sweep_tile(int ndiv, long long nsrc_ub) { return (ndiv <= 9 * kSweepTG && nsrc_ub <= 16384) ? 64 : kTS; }
+
+int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st, int ts) {
     if (!sweep_supported(ndiv)) { set_error("launch_sweep: ndiv=%d not supported", ndiv); return 1; }
-    if (ndiv <= 9 * kSweepTG) launch_sweep_rt<9>(a, ndiv, S, uniform, st);
-    else if (ndiv <= 16 * kSweepTG) launch_sweep_rt<16>(a, ndiv, S, uniform, st);
-    else launch_sweep_rt<32>(a, ndiv, S, uniform, st);
+    if (ndiv <= 9 * kSweepTG) {
+        if (ts == 64) launch_sweep_rt<9, 64>(a, ndiv, S, uniform, st);
+        else launch_sweep_rt<9, kTS>(a, ndiv, S, uniform, st);
+    } else if (ndiv <= 16 * kSweepTG) launch_sweep_rt<16, kTS>(a, ndiv, S, uniform, st);
+    else launch_sweep_rt<32, kTS>(a, ndiv, S, uniform, st);
     UF_CUDA(cudaGetLastError());
     return 0;
 }

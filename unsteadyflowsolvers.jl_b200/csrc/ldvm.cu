@@ -487,9 +487,11 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         a.pu = h->p2.p; a.pw = h->p2.p + (int64_t)h->S2max * h->ndivpad; a.tstride = h->ndivpad;
         if (lve || (!multi && sweep_supported(h->ndiv))) {
             // dedicated few-targets kernel (sweep.cuh): one partial plane per block
-            const long long tsrc = (nwake_ub + kTS - 1) / kTS + 3;
+            const int nt2 = lve ? h->ndiv - 1 : h->ndiv;
+            const int ts2 = sweep_tile(nt2, nwake_ub);
+            const long long tsrc = (nwake_ub + ts2 - 1) / ts2 + 3;
             p2.S = (int)std::max<long long>(1, std::min<long long>(tsrc, h->S2max));
-            if (int rc = launch_sweep(a, lve ? h->ndiv - 1 : h->ndiv, p2.S, h->uniform, st)) return rc;
+            if (int rc = launch_sweep(a, nt2, p2.S, h->uniform, st, ts2)) return rc;
         } else {
             if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
         }

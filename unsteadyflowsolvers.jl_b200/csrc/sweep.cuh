@@ -19,17 +19,20 @@ constexpr int kSweepGroups = kThreads / kSweepTG; // 32 source groups per block
 
 int sweep_supported(int ndiv);                    // 1 when a k_sweep instantiation covers ndiv
 // grid.x = number of source splits = number of partial planes written (a.pu/pw, stride a.tstride)
-int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st);
+int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st, int ts = kTS);
+int sweep_tile(int ndiv, long long nsrc_ub);     // 64 for small wakes (ndiv <= 72), else 512
 
 #if defined(__CUDACC__) && defined(UNSFLOW_INDUCE_KERNELS)
 
-template <int RT, bool UNIFORM>
+// TS = sources per tile: 512 (throughput) or 64 (latency: small wakes spread over more CTAs)
+template <int RT, bool UNIFORM, int TS>
 __global__ void __launch_bounds__(kThreads) k_sweep(const InduceArgs a, int ndiv) {
     constexpr int NARR = UNIFORM ? 3 : 4;
-    constexpr int TS = kTS;
-    __shared__ __align__(128) double s_buf[2][4][TS];      // 4 arrays always: reused by the reduction
+    constexpr int kRed = (kThreads / 32) * 2 * RT * kSweepTG;          // reduction scratch (doubles)
+    constexpr int kBuf = 2 * 4 * TS > kRed ? 2 * 4 * TS : kRed;         // tile buffers, reused by the reduction
+    __shared__ __align__(128) double s_raw[kBuf];
+    double (*s_buf)[4][TS] = reinterpret_cast<double (*)[4][TS]>(s_raw);   // [2][4][TS]
     __shared__ __align__(8) uint64_t s_bar[2];
-    static_assert((kThreads / 32) * 2 * RT * kSweepTG <= 2 * 4 * TS, "reduction scratch must fit the tile buffers");
 
     const int tid = threadIdx.x, lane8 = tid & (kSweepTG - 1), grp = tid / kSweepTG;
     const Regions sreg = *a.sreg;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const InduceArgs a, int ndiv
     }
     // fixed-order reduction: the 4 groups of a warp by butterfly, then the 8 warps through the
     // (now free) tile buffers
-    double *s_red = &s_buf[0][0][0];                       // [warp][2 * RT * kSweepTG]
+    double *s_red = s_raw;                                 // [warp][2 * RT * kSweepTG]
     const int warp = tid >> 5;
 #pragma unroll
     for (int r = 0; r < RT; r++) {
