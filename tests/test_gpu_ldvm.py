@@ -310,6 +310,19 @@ def test_multi_surface_tandem_ldvm(gpu_lib, uf, oracle):
         assert np.max(np.abs(surf.uind - so["uind"])) < 1e-8
 
 
+def test_multi_surface_write_stamps(gpu_lib, uf, tmp_path, monkeypatch):
+    """postprocess.jl:115-182 layout for several surfaces (placeholder LEVs are not written)"""
+    monkeypatch.chdir(tmp_path)
+    surfs, fld = _tandem(uf), uf.TwoDFlowField()
+    mat, surfs, fld = uf.ldvm(surfs, fld, 100, 0.012, 0, 1, 0.6, uf.delNone(), maxwrite=3)
+    assert sorted(d for d in os.listdir(".") if os.path.isdir(d)) == ["0.6", "1.2"]
+    names = sorted(os.listdir("1.2"))
+    assert names == ["FourierCoeffs-1", "FourierCoeffs-2", "boundv-1", "boundv-2", "lev", "tev", "timeKinem-1", "timeKinem-2"]
+    lev = np.loadtxt(os.path.join("1.2", "lev")).reshape(-1, 3)
+    assert lev.shape[0] == int(np.sum(fld.lev.vc != 0)) and lev.shape[0] < len(fld.lev)
+    assert np.loadtxt(os.path.join("1.2", "tev")).shape == (200, 3) and os.path.exists("resultsSummary")
+
+
 def test_multi_surface_one_surface_equals_single(gpu_lib, uf):
     a, fa = _tandem(uf)[:1], uf.TwoDFlowField()
     b, fb = _tandem(uf)[0], uf.TwoDFlowField()

@@ -102,3 +102,38 @@ def writeStamp(dirname, t, surf, curfield):
         delcp, delcp_in, delcp_out = calc_delcp(surf, vels)
         qu, ql = calc_edgeVel(surf, vels)
         _writedlm(f, np.stack([surf.x, delcp, delcp_in, delcp_out, qu, ql], axis=1))
+
+
+def writeStampMulti(dirname, t, surfs, curfield):
+    """writeStamp(dirname, t, surf::Vector{TwoDSurf}, curfield), postprocess.jl:115-182.  Unlike the
+    single-surface method it writes into `<cwd>/<dirname>` (no "Step Files" level, :116-121), one
+    timeKinem-i / FourierCoeffs-i / boundv-i per surface, and skips the zero-core placeholder LEVs
+    (`vc != 0`, :149-155)."""
+    if os.path.isdir(dirname):
+        shutil.rmtree(dirname)
+    os.mkdir(dirname)
+    for i, surf in enumerate(surfs, start=1):
+        k = surf.kinem
+        with open(os.path.join(dirname, f"timeKinem-{i}"), "w") as f:
+            f.write("#time \talpha (deg) \th/c \tu/uref \t\n")
+            _writedlm(f, [[t, k.alpha, k.h, k.u]])
+        with open(os.path.join(dirname, f"FourierCoeffs-{i}"), "w") as f:
+            f.write("#Fourier coeffs (0-n) \td/dt (Fourier coeffs)  \n")
+            m = np.zeros((surf.naterm + 1, 2))
+            m[:, 0] = np.concatenate([[surf.a0[0]], surf.aterm])
+            m[:, 1] = np.concatenate([[surf.a0dot[0]], surf.adot])
+            _writedlm(f, m)
+        with open(os.path.join(dirname, f"boundv-{i}"), "w") as f:
+            f.write("#strength \tx-position \tz-position  \n")
+            _writedlm(f, np.stack([surf.bv.s, surf.bv.x, surf.bv.z], axis=1))
+    with open(os.path.join(dirname, "tev"), "w") as f:
+        f.write("#strength \tx-position \tz-position  \n")
+        if len(curfield.tev):
+            _writedlm(f, np.stack([curfield.tev.s, curfield.tev.x, curfield.tev.z], axis=1))
+    with open(os.path.join(dirname, "lev"), "w") as f:
+        f.write("#strength \tx-position \tz-position  \n")
+        lv = curfield.lev
+        if len(lv):
+            keep = lv.vc != 0.0
+            if keep.any():
+                _writedlm(f, np.stack([lv.s[keep], lv.x[keep], lv.z[keep]], axis=1))

@@ -220,8 +220,10 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
                 from .postprocess import writeStamp
                 tstamp = float(table[stop - 1].reshape(-1)[0])
                 if multi:
-                    raise NotImplementedError("writeStamp for several surfaces (postprocess.jl:115-182) is not mirrored")
-                writeStamp(_round_sig(tstamp, nround), tstamp, surf, curfield)
+                    from .postprocess import writeStampMulti
+                    writeStampMulti(_round_sig(tstamp, nround), tstamp, surf, curfield)
+                else:
+                    writeStamp(_round_sig(tstamp, nround), tstamp, surf, curfield)
         h.download()
         if two_dof:
             h.get_2dof(kinem)
