@@ -170,3 +170,32 @@ def test_fast_precision_mode_stays_inside_the_parity_tolerance(gpu_lib, uf, orac
         gpu_lib.unsflow_set_precision(0)
     assert errs[0] < 1e-14 and 1e-15 < errs[1] <= TOL
     assert gpu_lib.unsflow_set_precision(7) != 0
+
+
+@pytest.mark.parametrize("ns,nt,uniform", [
+    (2047, 255, True), (2048, 256, True), (2049, 257, True),        # sweep-kernel switch (nt <= 256, ns >= 2048)
+    (16383, 256, False), (16384, 257, False), (16385, 1023, True),  # 64- vs 512-source tiles of the direct kernel
+    (511, 511, True), (512, 512, False), (513, 1, True), (1, 513, True),
+])
+def test_ind_vel_dispatch_boundaries(gpu_lib, uf, oracle, ns, nt, uniform):
+    """sizes on either side of every kernel-selection rule of api.cu / induce.cuh (plan_induce)"""
+    x, z, g, vc = oracle.s_wake(ns, uniform_vc=uniform)
+    tx, tz, _, _ = oracle.s_wake(nt, seed=77)
+    u, w = uf.ind_vel(_vl(uf, x, z, g, vc), tx, tz)
+    tu, tw, au, aw = oracle.ind_vel_truth(x, z, g, vc, tx, tz)
+    assert rel_err_normalised(u, tu, au) <= TOL and rel_err_normalised(w, tw, aw) <= TOL
+
+
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4096, 36863, 36864, 36865, 149_999, 150_000])
+def test_mutual_ind_dispatch_boundaries(gpu_lib, uf, oracle, n):
+    """direct <-> pair-tile switch (36864), 1024 <-> 2048 pair tiles (150000), tile-size multiples; every
+    tile edge is sampled"""
+    x, z, g, vc = oracle.s_wake(n)
+    v = _vl(uf, x, z, g, vc)
+    uf.mutual_ind(v)
+    edges = np.unique(np.clip(np.concatenate([np.arange(0, n, 1024) - 1, np.arange(0, n, 1024), [n - 2, n - 1]]), 0, n - 1))
+    idx = edges if len(edges) <= 96 else edges[np.linspace(0, len(edges) - 1, 96).astype(int)]
+    tu, tw, au, aw = oracle.ind_vel_truth(x, z, g, vc, x[idx], z[idx])
+    assert rel_err_normalised(v.vx[idx], tu, au) <= TOL and rel_err_normalised(v.vz[idx], tw, aw) <= TOL
+    assert abs(np.sum(g * v.vx)) <= 1e-12 * np.sum(np.abs(g)) * np.max(au)
+    assert np.all(np.isfinite(v.vx)) and np.all(np.isfinite(v.vz))
