@@ -78,7 +78,15 @@ function ind_vel(src::Vector{TwoDVort}, t_x::Vector{Float64}, t_z::Vector{Float6
         length(src), a.x, a.z, a.s, a.vc, length(t_x), t_x, t_z, uind, wind))
     uind, wind
 end
-ind_vel(src::TwoDVort, t_x, t_z) = ind_vel([src], collect(Float64, t_x), collect(Float64, t_z))   # calcs.jl:480-488
+function ind_vel(src::TwoDVort, t_x, t_z)            # calcs.jl:480-488: broadcasts, so matrix-shaped targets (a meshgrid) keep their shape
+    u, w = ind_vel([src], vec(collect(Float64, t_x)), vec(collect(Float64, t_z)))
+    reshape(u, size(t_x)), reshape(w, size(t_x))
+end
+"velocity induced by ALL of `vorts` at mesh points in one device call (the per-vortex loop of LVE.jl:176-183)"
+function ind_vel(src::Vector{TwoDVort}, t_x::Matrix{Float64}, t_z::Matrix{Float64})
+    u, w = ind_vel(src, vec(t_x), vec(t_z))
+    reshape(u, size(t_x)), reshape(w, size(t_x))
+end
 
 "mutual_ind(vorts) -> vorts (accumulates into vx, vz)   replaces calcs.jl:491-510"
 function mutual_ind(vorts::Vector{TwoDVort})

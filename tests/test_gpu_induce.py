@@ -199,3 +199,20 @@ def test_mutual_ind_dispatch_boundaries(gpu_lib, uf, oracle, n):
     assert rel_err_normalised(v.vx[idx], tu, au) <= TOL and rel_err_normalised(v.vz[idx], tw, aw) <= TOL
     assert abs(np.sum(g * v.vx)) <= 1e-12 * np.sum(np.abs(g)) * np.max(au)
     assert np.all(np.isfinite(v.vx)) and np.all(np.isfinite(v.vz))
+
+
+def test_meshgrid_velocity_sampling(gpu_lib, uf, oracle):
+    """one->many ind_vel over a meshgrid (typedefs.jl:422-512 + LVE.jl:176-183): matrix-shaped
+    targets keep their shape; sum over vortices == the reference's per-vortex accumulation"""
+    surf, fld, _, _ = c1_surf(uf)
+    x, z, g, vc = oracle.s_wake(700)
+    tev = _vl(uf, 0.002 * x - 0.9, 0.8 * z, g, vc)
+    lev = _vl(uf, 0.001 * x[:50] - 0.5, 0.5 * z[:50] + 0.2, -g[:50], vc[:50])
+    m = uf.meshgrid(surf, tev, lev, 0.25, 0.3, 100, "square")
+    m.sample_velocity([tev, lev, surf.bv], t=0.3)
+    sx, sz, sg, svc = (np.concatenate([getattr(v, k) for v in (tev, lev, surf.bv)]) for k in ("x", "z", "s", "vc"))
+    tu, tw, au, aw = oracle.ind_vel_truth(sx, sz, sg, svc, m.x.reshape(-1), m.z.reshape(-1))
+    assert m.uMat.shape == (100, 100) and m.t == 0.3
+    assert rel_err_normalised((m.uMat - surf.kinem.u).reshape(-1), tu, au) <= TOL
+    assert rel_err_normalised((m.wMat - surf.kinem.hdot).reshape(-1), tw, aw) <= TOL
+    assert np.allclose(m.velMag, np.hypot(m.uMat, m.wMat))

@@ -62,3 +62,20 @@ def test_writestamp_layout_cpu(uf, tmp_path, monkeypatch):
     assert dc.shape == (70, 6) and np.all(np.isfinite(dc))
     qu, ql = uf.calc_edgeVel(surf, [0.0, 0.0])
     assert abs(qu[0] - 0.05 / math.sqrt(0.5 * 0.016)) < 1e-14          # postprocess.jl:230
+
+
+def test_meshgrid_geometry(uf):
+    """meshgrid, typedefs.jl:422-512: window, mesh orientation, wake filter (host-only part)"""
+    surf = uf.TwoDSurf("FlatPlate", 0.25, uf.KinemDef(uf.ConstDef(0.1), uf.ConstDef(0.2), uf.ConstDef(1.0)), [10.15])
+    tev = uf.VortList.from_arrays([0.4, 3.0, -1.5], [0.1, 0.0, 0.2], [1, 1, 1], [0.02] * 3)
+    m = uf.meshgrid(surf, tev, uf.VortList(), 0.25, 0.5, 100, "square")
+    assert m.x.shape == m.z.shape == (100, 100)
+    step = 1.5 / 99
+    assert abs(m.x[0, 1] - m.x[0, 0] - step) < 1e-14 and abs(m.z[0, 0] - m.z[1, 0] - step) < 1e-14
+    assert abs(m.x[0, 0] - (-0.25 - 0.5 - 0.25)) < 1e-14           # nearBnd + X0 - pvt*c
+    assert abs(m.z[0, 0] - (0.75 + 0.2)) < 1e-14                    # top row = uppZ
+    assert m.tev.shape == (1, 2) and m.tev[0, 0] == 0.4 and m.lev.shape == (0, 2)
+    assert np.all(m.uMat == 1.0) and np.all(m.wMat == 0.0) and np.all(m.velMag == 0.0)
+    assert abs(m.camX[0] - ((0 - 0.25) * np.cos(0.1) - 0.5 + 0.25)) < 1e-14
+    w = uf.meshgrid(surf, tev, uf.VortList(), 0.25, 0.5, 100, "wake")
+    assert w.x.shape == w.z.shape == (55, 100) and w.tev.shape[0] == 1

@@ -21,12 +21,14 @@ def ind_vel(src, t_x, t_z):
     tx, tz = cabi.f64(t_x), cabi.f64(t_z)
     if tx.shape != tz.shape:
         raise ValueError("t_x and t_z must have the same length")
+    shape = tx.shape                      # matrix-shaped targets (a meshgrid, calcs.jl:480-488 broadcasts) keep their shape
+    tx, tz = tx.reshape(-1), tz.reshape(-1)
     u = np.zeros(tx.shape[0])
     w = np.zeros(tx.shape[0])
     sx, sz, ss, svc = (cabi.f64(a) for a in (v.x, v.z, v.s, v.vc))
     cabi.check(cabi.lib().unsflow_ind_vel(len(v), cabi.dptr(sx), cabi.dptr(sz), cabi.dptr(ss), cabi.dptr(svc),
                                           tx.shape[0], cabi.dptr(tx), cabi.dptr(tz), cabi.dptr(u), cabi.dptr(w)))
-    return u, w
+    return u.reshape(shape), w.reshape(shape)
 
 
 def mutual_ind(vorts):

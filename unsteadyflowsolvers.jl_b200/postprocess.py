@@ -137,3 +137,72 @@ def writeStampMulti(dirname, t, surfs, curfield):
             keep = lv.vc != 0.0
             if keep.any():
                 _writedlm(f, np.stack([lv.s[keep], lv.x[keep], lv.z[keep]], axis=1))
+
+
+class meshgrid:
+    """meshgrid(surf, tevs, levs, offset, t, width=100, view="square"), typedefs.jl:422-512: the
+    sampling window for flow visualisation around the surface in the inertial frame -- mesh
+    coordinates `x, z` (rows top to bottom), `uMat = kinem.u`, `wMat = kinem.hdot`, `velMag = 0`,
+    the camber line in the inertial frame and the TEV / LEV positions inside the window.
+    `sample_velocity(vorts)` adds the velocity the vortices induce at every mesh point (the
+    disabled block of LVE.jl:166-190: a one->many `ind_vel` per vortex; here ONE device call over
+    all sources through unsflow_ind_vel)."""
+
+    def __init__(self, surf, tevs, levs, offset, t, width=100, view="square"):
+        far = surf.x[-1] + surf.c * offset
+        near = surf.x[0] - surf.c * offset
+        zb = (far - near) / 2
+        if view == "wake":
+            far = 2 * far
+        elif view == "largewake":
+            far, zb = 3 * far, 2 * zb
+        elif view == "longwake":
+            far, zb = 5 * far, 2 * zb
+        elif view == "UI Window":
+            far = 2 * far
+            zb = 3 / 4 * far
+        X0 = -surf.kindef.u(t) * t
+        Z0 = surf.kindef.h(t)
+        lowX, uppX = near + X0 - surf.pvt * surf.c, far + X0 - surf.pvt * surf.c
+        lowZ, uppZ = -zb + Z0, zb + Z0
+        alpha = surf.kindef.alpha(t)                                   # IFR, calcs.jl:652-663
+        self.camX = (surf.x - surf.pvt) * math.cos(alpha) + surf.cam * math.sin(alpha) + X0 + surf.pvt
+        self.camZ = -(surf.x - surf.pvt) * math.sin(alpha) + surf.cam * math.cos(alpha) + Z0
+        step = (far - near) / (width - 1)
+        xs = lowX + step * np.arange(int(math.floor((uppX - lowX) / step + 1e-9)) + 1)     # lowX:step:uppX
+        # `height = zBnd*2/step + 1` rows, each a copy of the x range (typedefs.jl:466-467; Julia
+        # truncates the comprehension range 1:height to floor(height) rows)
+        nrow_x = int(math.floor(zb * 2 / step + 1 + 1e-9))
+        zs = uppZ - step * np.arange(int(math.floor((uppZ - lowZ) / step + 1e-9)) + 1)     # uppZ:-step:lowZ
+        self.x = np.tile(xs, (nrow_x, 1))
+        self.z = np.tile(zs[:, None], (1, xs.shape[0]))
+        self.uMat = np.zeros_like(self.x) + surf.kinem.u
+        self.wMat = np.zeros_like(self.x) + surf.kinem.hdot
+        self.velMag = np.zeros_like(self.x)
+        self.t = 0.0
+        self.alpha = surf.kinem.alpha
+
+        def inside(v):
+            vx, vz = np.asarray(v.x, float), np.asarray(v.z, float)
+            m = (vx >= lowX) & (vx <= uppX) & (vz >= lowZ) & (vz <= uppZ)
+            return np.stack([vx[m], vz[m]], axis=1)
+        self.tev = inside(tevs)
+        self.lev = inside(levs)
+
+    def sample_velocity(self, vorts, t=None):
+        """uMat, wMat += velocity induced by `vorts` (VortList or list of them); velMag updated."""
+        from .calcs import ind_vel
+        from .typedefs import VortList
+        if isinstance(vorts, (list, tuple)):
+            parts = [v for v in vorts if len(v)]
+            vorts = VortList.from_arrays(*(np.concatenate([np.asarray(getattr(v, k), float) for v in parts])
+                                           for k in ("x", "z", "s", "vc"))) if parts else VortList()
+        if self.x.shape != self.z.shape:
+            raise ValueError("mesh x and z differ in shape (non-square view): sample on matching sub-blocks")
+        u, w = ind_vel(vorts, self.x, self.z)
+        self.uMat = self.uMat + u
+        self.wMat = self.wMat + w
+        self.velMag = np.sqrt(self.uMat ** 2 + self.wMat ** 2)
+        if t is not None:
+            self.t = t
+        return self
