@@ -167,7 +167,7 @@ def test_chunked_runs_equal_one_run(gpu_lib, uf):
 
 
 def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
-    """with >= 36864 free vortices the stepper switches to the symmetric pair-tile kernel;
+    """with >= 28672 free vortices the stepper switches to the symmetric pair-tile kernel;
     it must agree with the (oracle-validated) direct kernel on the same state.  Run in two
     subprocesses because the switch threshold is read once per process."""
     import subprocess, sys, textwrap

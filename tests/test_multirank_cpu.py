@@ -60,14 +60,19 @@ def test_partition_covers_work_exactly_once_world2():
     # direct: target slices tile [0, n) with no gap/overlap
     assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == n
     # symmetric: tile ranges tile [0, W)
-    W = _ntiles(n)
+    W = _ntiles(n, 2)
     assert parts[0][2] == 0 and parts[0][3] == parts[1][2] and parts[1][3] == W
     assert abs((parts[0][3] - parts[0][2]) - (parts[1][3] - parts[1][2])) <= 1    # balanced
     assert uid == list(range(128)) and tmax == 11.0
 
 
-def _ntiles(n):
-    tb = 2048 if n >= 150000 else 1024      # pair-tile width rule of the library (induce.cu)
+def _ntiles(n, world=1):
+    # pair-tile width rule of the library (sym_rows_per_thread, induce.cu): cheaper of 2048- and 1024-wide
+    # tiles under the round model
+    def est(r, ctas, t_round):
+        t = -(-n // (256 * r)); w = t * (t + 1) // 2
+        return -(-(-(-w // world)) // ctas) * t_round
+    tb = 2048 if est(8, 148, 0.645) <= est(4, 296, 0.35) else 1024
     nb = (n + tb - 1) // tb
     return nb * (nb + 1) // 2
 
@@ -79,7 +84,7 @@ def test_partition_many_ranks_single_process():
     L = uf.lib()
     for n in (1, 1023, 1024, 1025, 99_999, 1_000_000):
         for world in (1, 2, 4, 8):
-            for variant, total in ((1, n), (2, _ntiles(n))):
+            for variant, total in ((1, n), (2, _ntiles(n, world))):
                 prev = 0
                 for r in range(world):
                     b, e = C.c_int64(), C.c_int64()

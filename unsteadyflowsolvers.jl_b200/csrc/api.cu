@@ -141,7 +141,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     for (int k = 0; k < ng; k++) ns += g[k].n;
     InducePlan plan = plan_induce(nt, 1, ns, ng, sm_count(), 64);
     // large uniform-core mutual induction: symmetric pair-tile kernel (induce_sym.cuh)
-    const bool sym = self_targets && uni && g[0].n >= 36864;
+    const bool sym = self_targets && uni && g[0].n >= sym_threshold();
     const int symR = sym_rows_per_thread(g[0].n);
     const int ctas = sym ? sym_ctas(symR) : 0;
     if (sym) { plan.S = ctas; }

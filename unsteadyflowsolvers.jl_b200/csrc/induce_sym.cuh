@@ -47,7 +47,8 @@ inline void split_range(long long total, long long part, long long nparts, long 
 }
 
 size_t sym_smem_bytes(int R);
-int sym_rows_per_thread(long long n);   // rows per thread R (tile = 256*R) chosen for n free vortices
+int sym_rows_per_thread(long long n, int nranks = 1);   // rows per thread R (tile = 256*R) chosen for n free vortices split over nranks GPUs
+long long sym_threshold();                               // free vortices from which the pair-tile kernel is used
 int sym_ctas(int R);                    // persistent CTAs = resident CTAs per SM x SMs (= number of partial planes)
 int sym_ctas_max();
 int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st);

@@ -513,7 +513,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
     if (sym) {
         if (!h->planes.p && h->planes.alloc((int64_t)sym_ctas_max() * 2 * tot)) return 2;
-        const int symR = sym_rows_per_thread(nwake_ub);
+        const int symR = sym_rows_per_thread(nwake_ub, h->nranks);
         h->ctas = sym_ctas(symR);
         // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
         const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};

@@ -11,12 +11,6 @@ namespace unsflow {
 constexpr int kNdMax = 256;    // max ndiv
 constexpr int kNaMax = 128;    // max naterm
 constexpr int kSolveThreads = 256;
-// free vortices from which the pair-tile kernel wins (env UNSFLOW_SYM_THRESHOLD overrides, for tests)
-static int64_t sym_threshold() {
-    static int64_t v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? (int64_t)atoll(e) : (int64_t)36864; }();
-    return v;
-}
-
 struct StepState {
     Regions wake;        // [0] tev, [1] lev, [2] extv, [3] bound vortices (absolute slab indices)
     Regions bnd;         // [0] = [0, ndiv): targets of the bound sweep

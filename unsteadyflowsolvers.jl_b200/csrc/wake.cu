@@ -83,7 +83,7 @@ extern "C" {
 int unsflow_partition(int64_t n, int nranks, int rank, int variant, int64_t *begin, int64_t *end) {
     UF_CHECK(n > 0 && nranks >= 1 && rank >= 0 && rank < nranks && begin && end, "unsflow_partition: bad arguments");
     if (variant == UNSFLOW_KERNEL_SYMMETRIC) {
-        const long long tb = (long long)kThreads * sym_rows_per_thread(n);
+        const long long tb = (long long)kThreads * sym_rows_per_thread(n, nranks);
         const long long nb = (n + tb - 1) / tb, W = nb * (nb + 1) / 2;
         long long b, e;
         split_range(W, rank, nranks, &b, &e);
@@ -130,8 +130,8 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     const int64_t my_t = std::max<int64_t>(0, std::min(n, (rank + 1) * w->slice) - rank * w->slice);
     w->plan = plan_induce(my_t, 1, n + nbv, 2, sm_count(), 64);
     if (w->part.alloc(2 * (int64_t)w->plan.S * w->npad)) return fail(2);
-    w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= 36864);
-    w->symR = sym_rows_per_thread(n);
+    w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= sym_threshold());
+    w->symR = sym_rows_per_thread(n, nranks);
     w->ctas = sym_ctas(w->symR);
     if (w->want_sym && w->planes.alloc((int64_t)w->ctas * 2 * w->tot)) return fail(2);
     if (w->src.zero(w->st) || w->vel.zero(w->st)) return fail(2);
