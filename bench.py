@@ -269,7 +269,7 @@ def main():
     if rank == 0:
         b_, e_ = C.c_int64(), C.c_int64()
         cabi.check(L.unsflow_partition(n, world, 0, 1, C.byref(b_), C.byref(e_)))
-        hi = n if args.variant != 1 and n >= 28672 else e_.value    # direct: rank 0 only holds its slice
+        hi = n if args.variant != 1 and n >= 16384 else e_.value    # direct: rank 0 only holds its slice
         idx = np.arange(0, hi, max(1, hi // 32))[:32]
         sx = np.concatenate([x, bx]); sz = np.concatenate([z, bz]); sg = np.concatenate([g, bs]); sv = np.concatenate([vc, bvc])
         tu, tw, au, aw = O.ind_vel_truth(sx, sz, sg, sv, x[idx], z[idx])

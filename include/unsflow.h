@@ -91,8 +91,8 @@ typedef struct unsflow_wake unsflow_wake;
  * rank 0, identical on all ranks (ignored when nranks == 1). */
 int unsflow_nccl_unique_id(void *id128);
 /* The share of the step owned by `rank` of `nranks` (pure arithmetic, no GPU needed):
- * DIRECT: target index range [begin,end) of the n free vortices; SYMMETRIC: range of the
- * row-major upper-triangle list of pair tiles (2048 or 1024 wide: the cheaper for (n, nranks) under the round model of sym_rows_per_thread). */
+ * DIRECT: target index range [begin,end) of the n free vortices; SYMMETRIC: range of work
+ * units, a unit being 1/32 of a pair tile of the row-major upper-triangle list of 2048-wide tiles. */
 int unsflow_partition(int64_t n, int nranks, int rank, int variant, int64_t *begin, int64_t *end);
 int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, int nranks,
                         const void *nccl_unique_id, int kernel_variant);

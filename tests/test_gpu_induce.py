@@ -164,7 +164,7 @@ def test_fast_precision_mode_stays_inside_the_parity_tolerance(gpu_lib, uf, orac
         for mode in (1, 0):
             uf._cabi.check(gpu_lib.unsflow_set_precision(mode))
             v = _vl(uf, x, z, g, vc)
-            uf.mutual_ind(v)                       # 60000 >= 28672: symmetric pair-tile kernel
+            uf.mutual_ind(v)                       # 60000 >= 16384: symmetric pair-tile kernel
             errs[mode] = max(rel_err_normalised(v.vx[idx], tu, au), rel_err_normalised(v.vz[idx], tw, aw))
     finally:
         gpu_lib.unsflow_set_precision(0)
@@ -186,9 +186,9 @@ def test_ind_vel_dispatch_boundaries(gpu_lib, uf, oracle, ns, nt, uniform):
     assert rel_err_normalised(u, tu, au) <= TOL and rel_err_normalised(w, tw, aw) <= TOL
 
 
-@pytest.mark.parametrize("n", [2047, 2048, 2049, 4096, 28671, 28672, 28673, 32768, 32769, 40000, 90_000, 150_000])
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4096, 16383, 16384, 16385, 18433, 28672, 32769, 40000, 90_000, 150_000])
 def test_mutual_ind_dispatch_boundaries(gpu_lib, uf, oracle, n):
-    """direct <-> pair-tile switch (28672), 2048- / 1024-wide pair tiles (round model), tile-size multiples; every
+    """direct <-> pair-tile switch (16384), partial last tiles, tile-size multiples; every
     tile edge is sampled"""
     x, z, g, vc = oracle.s_wake(n)
     v = _vl(uf, x, z, g, vc)

@@ -167,7 +167,7 @@ def test_chunked_runs_equal_one_run(gpu_lib, uf):
 
 
 def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
-    """with >= 28672 free vortices the stepper switches to the symmetric pair-tile kernel;
+    """with >= 16384 free vortices the stepper switches to the symmetric pair-tile kernel;
     it must agree with the (oracle-validated) direct kernel on the same state.  Run in two
     subprocesses because the switch threshold is read once per process."""
     import subprocess, sys, textwrap
@@ -195,6 +195,39 @@ def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
     assert np.max(np.abs(a["mat"] - b["mat"])) <= 1e-11
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-12
     assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-12 * max(1.0, np.max(np.abs(b["vz"])))
+
+
+def test_wake_growing_through_the_pair_tile_threshold_inside_graph_chunks(gpu_lib, uf, oracle):
+    """a wake that grows from 16300 to 16400 vortices crosses the default direct -> pair-tile switch
+    (16384) while steps are replayed as 32-step CUDA graphs sized for a quantised bound; result must
+    equal the all-direct run (plane allocation must not happen during stream capture)"""
+    import subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent("""
+        import sys, os, numpy as np
+        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+        import unsflow_b200 as uf
+        from oracle import oracle as O
+        from cases import c1_surf
+        surf, fld, _, dtstar = c1_surf(uf)
+        x, z, g, vc = O.s_wake(16300)
+        fld.tev = uf.VortList.from_arrays(x + 0.5, z, g, vc)
+        mat, surf, fld = uf.ldvm(surf, fld, 100, dtstar, write_summary=False)
+        np.savez(sys.argv[1], mat=mat, x=fld.tev.x, vz=fld.tev.vz)
+    """)
+    outs = []
+    for thr in (None, "100000000"):
+        f = tempfile.mktemp(suffix=".npz")
+        env = dict(os.environ)
+        env.pop("UNSFLOW_SYM_THRESHOLD", None)
+        if thr:
+            env["UNSFLOW_SYM_THRESHOLD"] = thr
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+        outs.append(np.load(f))
+    a, b = outs
+    assert a["x"].shape == (16400,)
+    assert np.max(np.abs(a["mat"] - b["mat"])) <= 1e-10
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-11
+    assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-11 * max(1.0, np.max(np.abs(b["vz"])))
 
 
 def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):

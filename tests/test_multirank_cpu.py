@@ -67,14 +67,8 @@ def test_partition_covers_work_exactly_once_world2():
 
 
 def _ntiles(n, world=1):
-    # pair-tile width rule of the library (sym_rows_per_thread, induce.cu): cheaper of 2048- and 1024-wide
-    # tiles under the round model
-    def est(r, ctas, t_round):
-        t = -(-n // (256 * r)); w = t * (t + 1) // 2
-        return -(-(-(-w // world)) // ctas) * t_round
-    tb = 2048 if est(8, 148, 0.645) <= est(4, 296, 0.35) else 1024
-    nb = (n + tb - 1) // tb
-    return nb * (nb + 1) // 2
+    nb = (n + 2047) // 2048                   # 2048-wide pair tiles (sym_rows_per_thread, induce.cu)
+    return 32 * (nb * (nb + 1) // 2)          # work units: 1/32 of a pair tile (kSymSub)
 
 
 def test_partition_many_ranks_single_process():

@@ -89,26 +89,19 @@ int launch_induce_finish(const FinishArgs &a, long long nt_ub, cudaStream_t st) 
 size_t sym_smem_bytes(int R) { return sizeof(double) * (size_t)(2 * 3 + 2) * kThreads * R + 2 * sizeof(uint64_t) + 16; }
 
 int sym_rows_per_thread(long long n, int nranks) {
-    // env UNSFLOW_SYM_R in {1,2,4,8} forces a tile size (experiments).  Default: the cheaper of 2048-wide
-    // (R = 8, one CTA per SM) and 1024-wide (R = 4, two CTAs per SM) pair tiles under a round model --
-    // every CTA owns ceil(W_rank / CTAs) tile pairs, one "round" of R = 8 tiles costs 0.645 ms, of R = 4
-    // tiles 0.35 ms (profiles/r01_sym_tile_width_scan.md; B200, 148 SMs).  Pure function of (n, nranks):
-    // all ranks pick the same tiling, and unsflow_partition works without a device.
+    // env UNSFLOW_SYM_R in {1,2,4,8} forces a tile size (experiments).  Default: 2048-wide tiles (R = 8, one
+    // CTA per SM).  With the work split in 1/32-tile units the widest tile wins at every N
+    // (profiles/r01_sym_tile_width_scan.md); kept a pure function of (n, nranks) so that all ranks pick the
+    // same tiling and unsflow_partition works without a device.
     static int forced = [] { const char *e = getenv("UNSFLOW_SYM_R"); int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0; }();
-    if (forced) return forced;
-    if (nranks < 1) nranks = 1;
-    auto est = [&](int R, int ctas, double t_round) {
-        const long long T = (n + 256LL * R - 1) / (256LL * R), W = T * (T + 1) / 2;
-        const long long Wr = (W + nranks - 1) / nranks, rounds = (Wr + ctas - 1) / ctas;
-        return (double)rounds * t_round;
-    };
-    return est(8, 148, 0.645) <= est(4, 296, 0.35) ? 8 : 4;
+    (void)n; (void)nranks;
+    return forced ? forced : 8;
 }
 
 long long sym_threshold() {
-    // free vortices from which the pair-tile kernel beats the direct one (same scan: direct 0.72 ms vs one
-    // R = 8 round at N = 28672); env UNSFLOW_SYM_THRESHOLD overrides (tests)
-    static long long v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? atoll(e) : 28672LL; }();
+    // free vortices from which the pair-tile kernel beats the direct one (same scan: 0.21 vs 0.26 ms at
+    // N = 16000, 0.21 vs 0.16 ms at 12000); env UNSFLOW_SYM_THRESHOLD overrides (tests)
+    static long long v = [] { const char *e = getenv("UNSFLOW_SYM_THRESHOLD"); return e ? atoll(e) : 16384LL; }();
     return v;
 }
 

@@ -6,8 +6,11 @@
 // that saving on the GPU:
 //
 //   * vortices are cut into blocks of TB = 256*R; the upper triangle of block pairs (I <= J) is
-//     linearised row-major and cut into equal contiguous chunks, one per persistent CTA
-//     (and per rank first, when the pair work is split over GPUs);
+//     linearised row-major, every pair tile is cut into kSymSub = 32 sub-units (quarters of the 8 phases
+//     of the Latin square below / 32 column slices of a diagonal tile), and the list of sub-units is
+//     cut into equal contiguous chunks, one per persistent CTA (and per rank first, when the pair work
+//     is split over GPUs) -- the load balance is 1/32 tile fine, which matters while there are only
+//     a few tiles per CTA (N < 10^5, or several GPUs);
 //   * rows (block I) live in registers, R per thread; columns (block J) are staged in shared
 //     memory by 1-D TMA bulk copies, double-buffered on mbarriers;
 //   * inside a tile warp w works on column chunk (w + phase) mod 8 and lane l on column
@@ -25,6 +28,7 @@ namespace unsflow {
 
 constexpr int kSymRMax = 8;
 constexpr int kSymTB = kThreads * kSymRMax;        // slab alignment: largest pair-tile block (2048)
+constexpr int kSymSub = 32;                        // work units per pair tile (quarters of the 8 phases of the lane/warp rotation)
 
 struct SymArgs {
     const double *x, *z, *g;     // slabs (absolute indexing); dead entries have g = 0
@@ -84,12 +88,13 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
     long long nb = 0;
     for (int r = 0; r < a.nreg; r++) nb += sym_blocks_in<TB>(reg.begin[r], reg.end[r]);
     const long long W = nb * (nb + 1) / 2;
-    // rank range, then this CTA's contiguous chunk of it
+    // rank range, then this CTA's contiguous chunk of it, in sub-units of 1/kSymSub tile
     long long r0, r1, c0, c1;
-    split_range(W, a.rank, a.nranks, &r0, &r1);
+    split_range(W * kSymSub, a.rank, a.nranks, &r0, &r1);
     split_range(r1 - r0, blockIdx.x, gridDim.x, &c0, &c1);
-    const long long t0 = r0 + c0, t1 = r0 + c1;
-    if (t0 >= t1) return;
+    const long long u0 = r0 + c0, u1 = r0 + c1;
+    if (u0 >= u1) return;
+    const long long t0 = u0 / kSymSub, t1 = (u1 + kSymSub - 1) / kSymSub;
 
     // (I, J) of tile t0
     long long I = (long long)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t0)) * 0.5);
@@ -149,11 +154,14 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             }
         }
         const double *sx = s_col + stage * 3 * TB, *sz = sx + TB, *sg = sx + 2 * TB;
+        // sub-units [pb, pe) of this tile belong to this CTA (all of them except on its first / last tile)
+        const int pb = t == t0 ? (int)(u0 - t0 * kSymSub) : 0;
+        const int pe = t == t1 - 1 ? (int)(u1 - (t1 - 1) * kSymSub) : kSymSub;
         if (I == J) {
             // ---- diagonal tile: one-sided, broadcast column reads (self pair is an exact 0) ----
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
 #pragma unroll 2
-            for (int j = 0; j < TB; j++) {
+            for (int j = pb * (TB / kSymSub); j < pe * (TB / kSymSub); j++) {
                 const double xj = sx[j], zj = sz[j], gj = sg[j];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     w[r] = fma(dx, m, w[r]);
                 }
             }
-            if (a.bv_reg >= 0) {   // bound vortices act on this row block exactly once (here)
+            if (a.bv_reg >= 0 && pb == 0) {   // bound vortices act on this row block exactly once (here)
                 for (long long j = reg.begin[a.bv_reg]; j < reg.end[a.bv_reg]; j++) {
                     const double xj = __ldg(a.x + j), zj = __ldg(a.z + j), gj = __ldg(a.g + j);
 #pragma unroll
@@ -185,14 +193,15 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             for (int c = tid; c < TB; c += kThreads) s_acc[c] = make_double2(0.0, 0.0);
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
             __syncthreads();
-            for (int p = 0; p < kThreads / 32; p++) {
+            // one phase: warp w works on column chunk (w + p) mod 8, steps [sb, se) of the lane rotation
+            auto run_phase = [&](const int p, const int sb, const int se) {
                 const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
                 // software pipeline: the column read for step s+1 is issued before the
                 // accumulator read-modify-write of step s (column data is read-only in a tile)
-                int j = base + (lane & (kChunk - 1));
+                int j = base + ((sb + lane) & (kChunk - 1));
                 double xj = sx[j], zj = sz[j], gj = sg[j];
 #pragma unroll 1
-                for (int s = 0; s < kChunk; s++) {
+                for (int s = sb; s < se; s++) {
                     const int jn = base + ((s + 1 + lane) & (kChunk - 1));
                     const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
                     double cu = 0.0, cw = 0.0;
@@ -215,6 +224,18 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     j = jn; xj = xn; zj = zn; gj = gn;
                 }
                 __syncthreads();
+            };
+            if (pb == 0 && pe == kSymSub) {
+                // whole tile (the common case): compile-time loop bounds
+#pragma unroll 1
+                for (int p = 0; p < kThreads / 32; p++) run_phase(p, 0, kChunk);
+            } else {
+                // first / last tile of this CTA's share: a unit = kUnit consecutive steps of the
+                // (phase, step) sequence of the tile
+                constexpr int kUnit = (kThreads / 32) * kChunk / kSymSub;
+                const int gs0 = pb * kUnit, gs1 = pe * kUnit;
+                for (int p = gs0 / kChunk; p * kChunk < gs1; p++)
+                    run_phase(p, max(gs0 - p * kChunk, 0), min(gs1 - p * kChunk, kChunk));
             }
             // flush the column accumulators into this CTA's private plane
             const long long cstart = sym_block_start<TB>(reg, a.nreg, J);

@@ -512,8 +512,8 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     a.vc4_uniform = h->vc4u;
     a.pu = h->p1.p; a.pw = h->p1.p + (int64_t)h->S1max * tot; a.tstride = tot;
     if (sym) {
-        if (!h->planes.p && h->planes.alloc((int64_t)sym_ctas_max() * 2 * tot)) return 2;
         const int symR = sym_rows_per_thread(nwake_ub, h->nranks);
+        UF_CHECK(h->planes.p != nullptr, "internal: pair-tile planes not allocated before the step was enqueued");
         h->ctas = sym_ctas(symR);
         // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
         const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
@@ -570,6 +570,12 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     return 0;
 }
 
+// partial planes of the pair-tile kernel, allocated on first need and OUTSIDE stream capture
+static int ensure_planes(unsflow_ldvm *h, int64_t nwake_ub) {
+    if (h->planes.p || !h->uniform || nwake_ub < sym_threshold()) return 0;
+    return h->planes.alloc((int64_t)sym_ctas(sym_rows_per_thread(nwake_ub, h->nranks)) * 2 * h->tot) ? 2 : 0;
+}
+
 static void poll_readback(unsflow_ldvm *h) {
     if (h->readback_pending && cudaEventQuery(h->evc) == cudaSuccess) {
         h->readback_pending = false;
@@ -611,6 +617,7 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         const bool small = tev_ub + lev_ub + h->nextv < 16384;
         if (graphs_enabled() && small && nsteps - is >= kGraphChunk) {
             const int64_t qt = std::min(h->cap_t, round_up(tev_ub, kGraphQuant)), ql = std::min(h->cap_l, round_up(lev_ub, kGraphQuant));
+            if (int rc = ensure_planes(h, qt + ql + h->nextv)) return rc;
             if (!h->gexec || h->gkey_t != qt || h->gkey_l != ql || h->gkey_kin != h->dev.kin) {
                 if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
                 cudaGraph_t g = nullptr;
@@ -632,6 +639,7 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
             is += kGraphChunk;
         } else {
             step_bounds(h, 1, &tev_ub, &lev_ub);
+            if (int rc = ensure_planes(h, tev_ub + lev_ub + h->nextv)) return rc;
             if (int rc = enqueue_step(h, tev_ub, lev_ub, st)) return rc;
             UF_CUDA(cudaGetLastError());
             h->steps_done++;

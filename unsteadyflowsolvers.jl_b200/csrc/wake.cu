@@ -86,7 +86,7 @@ int unsflow_partition(int64_t n, int nranks, int rank, int variant, int64_t *beg
         const long long tb = (long long)kThreads * sym_rows_per_thread(n, nranks);
         const long long nb = (n + tb - 1) / tb, W = nb * (nb + 1) / 2;
         long long b, e;
-        split_range(W, rank, nranks, &b, &e);
+        split_range(W * kSymSub, rank, nranks, &b, &e);   // in sub-units of 1/kSymSub pair tile
         *begin = b; *end = e;
     } else {
         const int64_t sl = slice_len(n, nranks);
