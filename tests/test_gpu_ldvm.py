@@ -166,9 +166,11 @@ def test_chunked_runs_equal_one_run(gpu_lib, uf):
     assert np.array_equal(outs[1], outs[2])
 
 
-def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
+@pytest.mark.parametrize("ntev,nlev", [(50000, 16000), (20000, 17), (18000, 300)])
+def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle, ntev, nlev):
     """with >= 16384 free vortices the stepper switches to the symmetric pair-tile kernel;
-    it must agree with the (oracle-validated) direct kernel on the same state.  Run in two
+    it must agree with the (oracle-validated) direct kernel on the same state -- also when one family
+    is short (a block with <= 256 live entries becomes the column side of its tiles).  Run in two
     subprocesses because the switch threshold is read once per process."""
     import subprocess, sys, textwrap
     code = textwrap.dedent("""
@@ -178,18 +180,20 @@ def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle):
         from oracle import oracle as O
         from cases import c2_surf
         surf, fld, dtstar = c2_surf(uf)
-        x, z, g, vc = O.s_wake(66000)
-        fld.tev = uf.VortList.from_arrays(x[:50000] + 0.5, z[:50000], g[:50000], vc[:50000])
-        fld.lev = uf.VortList.from_arrays(x[50000:] + 0.5, z[50000:], g[50000:], vc[50000:])
+        ntev, nlev = int(sys.argv[2]), int(sys.argv[3])
+        x, z, g, vc = O.s_wake(ntev + nlev)
+        fld.tev = uf.VortList.from_arrays(x[:ntev] + 0.5, z[:ntev], g[:ntev], vc[:ntev])
+        fld.lev = uf.VortList.from_arrays(x[ntev:] + 0.5, z[ntev:], g[ntev:], vc[ntev:])
         mat, surf, fld = uf.ldvm(surf, fld, 3, dtstar, write_summary=False)
         np.savez(sys.argv[1], mat=mat, x=np.concatenate([fld.tev.x, fld.lev.x]), vz=np.concatenate([fld.tev.vz, fld.lev.vz]))
     """)
     import tempfile
     outs = []
-    for thr in ("36864", "100000000"):
+    for thr in ("16384", "100000000"):
         f = tempfile.mktemp(suffix=".npz")
         env = dict(os.environ, UNSFLOW_SYM_THRESHOLD=thr)
-        subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+        subprocess.run([sys.executable, "-c", code, f, str(ntev), str(nlev)], check=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(__file__)))
         outs.append(np.load(f))
     a, b = outs
     assert np.max(np.abs(a["mat"] - b["mat"])) <= 1e-11

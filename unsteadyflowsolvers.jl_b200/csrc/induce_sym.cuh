@@ -72,6 +72,19 @@ __device__ __forceinline__ long long sym_block_start(const Regions &rg, int nreg
     }
     return -1;
 }
+// entries of block k that lie inside their region (the rest of the block is dead padding, g = 0)
+template <int TB>
+__device__ __forceinline__ int sym_block_live(const Regions &rg, int nreg, long long k) {
+    for (int r = 0; r < nreg; r++) {
+        const long long n = sym_blocks_in<TB>(rg.begin[r], rg.end[r]);
+        if (k < n) {
+            const long long left = rg.end[r] - (rg.begin[r] / TB + k) * TB;
+            return (int)(left < TB ? left : TB);
+        }
+        k -= n;
+    }
+    return 0;
+}
 // row-major upper triangle incl. diagonal: row I starts at I*nb - I*(I-1)/2
 __device__ __forceinline__ long long sym_row_offset(long long I, long long nb) { return I * nb - I * (I - 1) / 2; }
 
@@ -122,7 +135,20 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
         tma_load_1d(dst + TB, a.z + e0, bytes, &s_bar[stage]);
         tma_load_1d(dst + 2 * TB, a.g + e0, bytes, &s_bar[stage]);
     };
-    if (tid == 0) issue(J, 0);
+    // A block with at most one column chunk of live entries (a short vortex family next to a long one:
+    // 17 LEVs beside 10^5 TEVs) is always taken as the COLUMN side of its tiles, where the work can be
+    // cut down to the live columns; `rb` / `cb` = row / column block of tile (I, J).
+    auto roles = [&](long long Ib, long long Jb, long long *rb, long long *cb, int *ncol) {
+        const int li = sym_block_live<TB>(reg, a.nreg, Ib), lj = sym_block_live<TB>(reg, a.nreg, Jb);
+        const bool swap = Ib != Jb && li <= kChunk && li < lj;
+        *rb = swap ? Jb : Ib;
+        *cb = swap ? Ib : Jb;
+        *ncol = swap ? li : lj;
+    };
+    long long rb, cb;
+    int ncol;
+    roles(I, J, &rb, &cb, &ncol);
+    if (tid == 0) issue(cb, 0);
 
     double tx[R], tz[R], tg[R], u[R], w[R];
     long long rowI = -1, row_start = 0;
@@ -133,9 +159,12 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
         // next tile in row-major order
         long long In = I, Jn = J + 1;
         if (Jn >= nb) { In = I + 1; Jn = In; }
-        if (tid == 0 && t + 1 < t1) issue(Jn, stage ^ 1);
+        long long rbn = 0, cbn = 0;
+        int ncoln = 0;
+        if (t + 1 < t1) roles(In, Jn, &rbn, &cbn, &ncoln);
+        if (tid == 0 && t + 1 < t1) issue(cbn, stage ^ 1);
 
-        if (I != rowI) {
+        if (rb != rowI) {
             if (rowI >= 0) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -144,8 +173,8 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     Pw[i] += w[r];
                 }
             }
-            rowI = I;
-            row_start = sym_block_start<TB>(reg, a.nreg, I);
+            rowI = rb;
+            row_start = sym_block_start<TB>(reg, a.nreg, rb);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const long long i = row_start + tid + r * kThreads;
@@ -161,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             // ---- diagonal tile: one-sided, broadcast column reads (self pair is an exact 0) ----
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
 #pragma unroll 2
-            for (int j = pb * (TB / kSymSub); j < pe * (TB / kSymSub); j++) {
+            const int jend = min(pe * (TB / kSymSub), ncol);   // columns past the region end are dead
+            for (int j = pb * (TB / kSymSub); j < jend; j++) {
                 const double xj = sx[j], zj = sz[j], gj = sg[j];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -186,6 +216,50 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                         w[r] = fma(dx, m, w[r]);
                     }
                 }
+            }
+            __syncthreads();
+        } else if (ncol <= kChunk) {
+            // ---- off-diagonal tile with a single live column chunk: all warps sweep chunk 0 at once,
+            //      each into its own accumulator row s_acc[warp][.], only over the steps that touch a live
+            //      column.  The whole tile belongs to the CTA that owns its first work unit. ---------------
+            if (pb == 0) {
+                for (int c = tid; c < TB; c += kThreads) s_acc[c] = make_double2(0.0, 0.0);
+                mbar_wait(&s_bar[stage], (k >> 1) & 1);
+                __syncthreads();
+                double2 *acc_w = s_acc + warp * kChunk;
+                for (int s = 0; s < kChunk; s++) {
+                    if (s >= ncol && s < kChunk - 31) { s = kChunk - 32; continue; }   // lanes cover columns s..s+31 (mod chunk)
+                    const int j = (s + lane) & (kChunk - 1);
+                    const double xj = sx[j], zj = sz[j], gj = sg[j];
+                    double cu = 0.0, cw = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double dx = xj - tx[r], dz = zj - tz[r];
+                        const double d2 = fma(dz, dz, dx * dx);
+                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                        const double t1v = y * dz, t2v = y * dx;
+                        u[r] = fma(-gj, t1v, u[r]);
+                        w[r] = fma(gj, t2v, w[r]);
+                        cu = fma(tg[r], t1v, cu);
+                        cw = fma(-tg[r], t2v, cw);
+                    }
+                    double2 acc = acc_w[j];
+                    acc.x += cu;
+                    acc.y += cw;
+                    acc_w[j] = acc;
+                    __syncwarp();
+                }
+                __syncthreads();
+                const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);
+                for (int c = tid; c < kChunk; c += kThreads) {
+                    double su = 0.0, sw = 0.0;
+#pragma unroll
+                    for (int q = 0; q < kThreads / 32; q++) { su += s_acc[q * kChunk + c].x; sw += s_acc[q * kChunk + c].y; }
+                    Pu[cstart + c] += su;
+                    Pw[cstart + c] += sw;
+                }
+            } else {
+                mbar_wait(&s_bar[stage], (k >> 1) & 1);   // keep the barrier phases in step
             }
             __syncthreads();
         } else {
@@ -238,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     run_phase(p, max(gs0 - p * kChunk, 0), min(gs1 - p * kChunk, kChunk));
             }
             // flush the column accumulators into this CTA's private plane
-            const long long cstart = sym_block_start<TB>(reg, a.nreg, J);
+            const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);
             for (int c = tid; c < TB; c += kThreads) {
                 const double2 acc = s_acc[c];
                 Pu[cstart + c] += acc.x;
@@ -248,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
         }
         I = In;
         J = Jn;
+        rb = rbn; cb = cbn; ncol = ncoln;
     }
     if (rowI >= 0) {
 #pragma unroll
