@@ -36,7 +36,7 @@ FLOP_PER_INTERACTION = 13.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_induce_sym<8,3> launch at N = 1e6 from the
 # `ncu --set full` capture summarised in profiles/r01_sym_R8_N1e6_ncu_full.txt (4.42 + 3.90 GB: the
 # per-CTA partial planes' read-modify-write; 0.2 % of DRAM bandwidth -- the kernel is FP64-bound)
-NCU_TRAFFIC_SYM8_N1E6 = 8.3155e9
+NCU_TRAFFIC_SYM8_N1E6 = 8.3268e9
 NBV = 69                        # ndiv - 1 bound vortices (typedefs.jl:68)
 
 
