@@ -102,7 +102,12 @@ end
 
 "update_indbound(surf, curfield) -> surf   replaces calcs.jl:35-38"
 function update_indbound(surf::TwoDSurf, curfield::TwoDFlowField)
-    surf.uind[1:surf.ndiv], surf.wind[1:surf.ndiv] = ind_vel([curfield.tev; curfield.lev; curfield.extv], surf.bnd_x, surf.bnd_z)
+    a = SoA([curfield.tev; curfield.lev; curfield.extv])
+    uind = zeros(surf.ndiv); wind = zeros(surf.ndiv)
+    check(ccall((:unsflow_update_indbound, LIB), Cint,
+        (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        length(a.x), a.x, a.z, a.s, a.vc, surf.ndiv, surf.bnd_x, surf.bnd_z, uind, wind))
+    surf.uind[1:surf.ndiv] = uind; surf.wind[1:surf.ndiv] = wind
     surf
 end
 
