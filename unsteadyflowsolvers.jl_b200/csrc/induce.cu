@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cstdio>
 namespace unsflow {
 
 InducePlan plan_induce(long long nt_ub, int ntreg, long long ns_ub, int nsreg, int sm_count, int max_S) {
@@ -19,9 +20,15 @@ InducePlan plan_induce(long long nt_ub, int ntreg, long long ns_ub, int nsreg, i
     p.R = R;
     // latency regime: few targets (bound sweep) or a small wake -> 64-source tiles, more CTAs
     p.ts = (R == 1 && (nt_ub <= kThreads || ns_ub <= 16384)) ? 64 : kTS;
+    long long mult = 8;
+    // experiments: UNSFLOW_PLAN="R,ts,mult" forces the tiling of the all-pairs launches (nt > 256)
+    static int forced[3] = {0, 0, 0};
+    static bool parsed = [] { const char *e = getenv("UNSFLOW_PLAN"); if (e) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]); return true; }();
+    (void)parsed;
+    if (forced[0] && nt_ub > kThreads) { R = p.R = forced[0]; p.ts = forced[1] == 64 && R == 1 ? 64 : kTS; if (forced[2]) mult = forced[2]; }
     const long long tsrc = tsrc_of(p.ts);
     p.ntiles = (int)std::max<long long>(1, tiles(R));
-    long long S = (8 * slots + p.ntiles - 1) / p.ntiles;
+    long long S = (mult * slots + p.ntiles - 1) / p.ntiles;
     S = std::min<long long>(S, tsrc);
     S = std::min<long long>(S, max_S);
     S = std::min<long long>(S, 65535);
