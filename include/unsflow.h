@@ -232,6 +232,15 @@ int unsflow_ldvm_destroy(unsflow_ldvm *h);
 int unsflow_ldvm_batch_run(const unsflow_surf *surf, const unsflow_opts *opts, int64_t nmember,
                            int64_t nsteps, const double *tables, const double *lespcrit,
                            double *mat_out, int64_t *ntev_out, int64_t *nlev_out);
+/* Same for ldvm2DOF members (solvers.jl:657-788; e.g. a flutter-boundary sweep over structural
+ * parameters): strpar11 = nmember x 11 (TwoDOFPar, typedefs.jl:178-190), kinem22 = nmember x 22 (initial
+ * KinemPar2DOF, typedefs.jl:193-220), both in field order; kinem22_out (may be NULL) receives every member's final
+ * KinemPar2DOF.  opts->driver must be UNSFLOW_DRIVER_LDVM2DOF; only the columns t, U_ext, W_ext of
+ * `tables` are read.  delSpalart merging applies per member when opts asks for it. */
+int unsflow_ldvm2dof_batch_run(const unsflow_surf *surf, const unsflow_opts *opts, int64_t nmember,
+                               int64_t nsteps, const double *tables, const double *lespcrit,
+                               const double *strpar11, const double *kinem22,
+                               double *mat_out, double *kinem22_out, int64_t *ntev_out, int64_t *nlev_out);
 /* CUDA-event milliseconds of the ensemble kernel of the last unsflow_ldvm_batch_run on this thread */
 int unsflow_ldvm_batch_timing(float *ms_kernel);
 

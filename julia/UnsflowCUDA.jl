@@ -377,4 +377,55 @@ function LVE(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtsta
     return 0, IFR_field, mat, TEVhist, LEVhist
 end
 
+# ---- ensembles of independent runs (no reference equivalent: a `for` loop over ldvm / ldvm2DOF calls) ----
+# `surfs[m]` is member m's TwoDSurf as the user would build it for that loop (same geometry and
+# discretisation, own kindef and lespcrit); every member starts from surfs[1]'s state with an empty wake.
+# One thread block per member runs the whole time loop on the GPU.  Returns the members' `mat`
+# matrices (nsteps x 8 each) and their TEV / LEV counts.
+function member_tables(surfs::Vector{TwoDSurf}, nsteps, dt; twodof = false)
+    tabs = zeros(9, nsteps, length(surfs))
+    for (m, sf) in enumerate(surfs)
+        tabs[:, :, m] = kinematics_table(sf, TwoDFlowField(), nsteps, dt, 0.0; twodof = twodof)
+    end
+    tabs
+end
+
+function ldvm_batch(surfs::Vector{TwoDSurf}, nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 0)
+    surf = surfs[1]; M = length(surfs); dt = dtstar * surf.c / surf.uref
+    tabs = member_tables(surfs, nsteps, dt)
+    lesp = [sf.lespcrit[1] for sf in surfs]
+    bv = SoA(surf.bv); mats = zeros(nsteps, 8, M); nt = zeros(Int64, M); nl = zeros(Int64, M)
+    kind, lim, dist, tol = typeof(delvort) == delSpalart ? (1, delvort.limit, delvort.dist, delvort.tol) : (0, 0, 0.0, 0.0)
+    GC.@preserve surf bv begin
+        cs = Ref(csurf(surf, bv)); opts = Ref(COpts(0, solve_mode, kind, -1, lim, dist, tol, dt, nsteps))
+        check(ccall((:unsflow_ldvm_batch_run, LIB), Cint,
+            (Ptr{CSurf}, Ptr{COpts}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}),
+            cs, opts, M, nsteps, tabs, lesp, mats, nt, nl))
+    end
+    [mats[:, :, m] for m = 1:M], nt, nl
+end
+
+# ldvm2DOF members: strpars[m]::TwoDOFPar, kinems[m]::KinemPar2DOF (mutated to the final state)
+function ldvm2DOF_batch(surfs::Vector{TwoDSurf}, strpars::Vector{TwoDOFPar}, kinems::Vector{KinemPar2DOF},
+                        nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 0)
+    surf = surfs[1]; M = length(surfs); dt = dtstar * surf.c / surf.uref
+    tabs = member_tables(surfs, nsteps, dt; twodof = true)
+    lesp = [sf.lespcrit[1] for sf in surfs]
+    sp = [Float64(getfield(strpars[m], f)) for f in fieldnames(TwoDOFPar), m = 1:M]          # 11 x M
+    kk = [Float64(getfield(kinems[m], f)) for f in fieldnames(KinemPar2DOF), m = 1:M]       # 22 x M
+    kout = similar(kk)
+    bv = SoA(surf.bv); mats = zeros(nsteps, 8, M); nt = zeros(Int64, M); nl = zeros(Int64, M)
+    kind, lim, dist, tol = typeof(delvort) == delSpalart ? (1, delvort.limit, delvort.dist, delvort.tol) : (0, 0, 0.0, 0.0)
+    GC.@preserve surf bv begin
+        cs = Ref(csurf(surf, bv)); opts = Ref(COpts(1, solve_mode, kind, -1, lim, dist, tol, dt, nsteps))
+        check(ccall((:unsflow_ldvm2dof_batch_run, LIB), Cint,
+            (Ptr{CSurf}, Ptr{COpts}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}),
+            cs, opts, M, nsteps, tabs, lesp, sp, kk, mats, kout, nt, nl))
+    end
+    for m = 1:M, (i, f) in enumerate(fieldnames(KinemPar2DOF))
+        setfield!(kinems[m], f, kout[i, m])
+    end
+    [mats[:, :, m] for m = 1:M], nt, nl
+end
+
 end # module

@@ -201,6 +201,33 @@ def test_large_wake_pair_tile_kernel_in_stepper(gpu_lib, uf, oracle, ntev, nlev)
     assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-12 * max(1.0, np.max(np.abs(b["vz"])))
 
 
+def test_ensemble_of_ldvm2dof_members_matches_oracle(gpu_lib, uf, oracle):
+    """aeroelastic ensemble: members differ in the structural parameters (TwoDOFPar) and in the
+    initial KinemPar2DOF; each must follow the oracle's ldvm2DOF (incl. Spalart merging)"""
+    surf, fld, strpar, kin0 = c5_2dof(uf)
+    nsteps, dtstar = 80, 0.015
+    tab = uf.kinematics_table(surf, fld, nsteps, dtstar, two_dof=True)
+    strpars, kinems = [], []
+    for kappa, w_h, a0 in ((0.05, 0.5, 0.1), (0.1, 0.8, 0.2), (0.02, 0.3, -0.15)):
+        sp = copy.deepcopy(strpar)
+        sp.kappa, sp.w_h = kappa, w_h
+        strpars.append(sp)
+        kinems.append(uf.KinemPar2DOF(a0, 0.0, 0.0, 0.0, 1.0))
+    delv = uf.delSpalart(40, 10.0, 1e-6)
+    mats, finals, ntev, nlev, ms = uf.ldvm2DOF_batch(surf, np.array([tab] * 3), 0.2, strpars, kinems, dtstar, delvort=delv)
+    assert mats.shape == (3, nsteps, 8) and ms > 0
+    for m in range(3):
+        s2 = copy.deepcopy(surf)
+        s2.lespcrit[0] = 0.2
+        sim = oracle.Sim(s2, uf.TwoDFlowField())
+        sim.set_2dof(strpars[m].as_array(), kinems[m].as_array())
+        om = sim.run(oracle.DRIVER_LDVM2DOF, tab, dtstar, delvort=(1, 40, 10.0, 1e-6))
+        assert np.max(np.abs(mats[m] - om)) < 1e-8, m
+        assert ntev[m] == len(sim.get_vorts(0)["x"]) and nlev[m] == len(sim.get_vorts(1)["x"])
+        assert np.max(np.abs(finals[m].as_array() - sim.get_2dof())) < 1e-9
+    assert np.max(np.abs(mats[0] - mats[1])) > 1e-3          # members really differ
+
+
 def test_wake_growing_through_the_pair_tile_threshold_inside_graph_chunks(gpu_lib, uf, oracle):
     """a wake that grows from 16300 to 16400 vortices crosses the default direct -> pair-tile switch
     (16384) while steps are replayed as 32-step CUDA graphs sized for a quantised bound; result must

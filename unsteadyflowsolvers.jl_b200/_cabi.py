@@ -116,6 +116,7 @@ def lib():
         "unsflow_ldvm_timing": [vp, C.POINTER(C.c_float), C.POINTER(i64)],
         "unsflow_ldvm_destroy": [vp],
         "unsflow_ldvm_batch_run": [C.POINTER(Surf), C.POINTER(Opts), i64, i64, d, d, d, C.POINTER(i64), C.POINTER(i64)],
+        "unsflow_ldvm2dof_batch_run": [C.POINTER(Surf), C.POINTER(Opts), i64, i64, d, d, d, d, d, d, C.POINTER(i64), C.POINTER(i64)],
         "unsflow_ldvm_batch_timing": [C.POINTER(C.c_float)],
         "unsflow_bench_sweep": [i64, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "unsflow_fp64_peak": [d, d],

@@ -762,14 +762,21 @@ int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {
     return 0;
 }
 
-int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
-                           const double *tables, const double *lespcrit, double *mat_out, int64_t *ntev_out,
-                           int64_t *nlev_out) {
+}  // extern "C"
+
+// shared body of the two ensemble entry points; strpar/kinem2dof non-null <=> ldvm2DOF members
+static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
+                          const double *tables, const double *lespcrit, const double *strpar, const double *kinem2dof,
+                          double *mat_out, double *kinem2dof_out, int64_t *ntev_out, int64_t *nlev_out) {
     UF_CHECK(sf && op && tables && mat_out, "unsflow_ldvm_batch_run: null argument");
     UF_CHECK(nmember > 0 && nsteps > 0, "unsflow_ldvm_batch_run: need nmember > 0 and nsteps > 0");
     UF_CHECK(sf->ndiv >= 3 && sf->ndiv <= kNdMax && sf->naterm >= 3 && sf->naterm <= kNaMax, "unsflow_ldvm_batch_run: bad ndiv/naterm");
-    UF_CHECK(op->driver == UNSFLOW_DRIVER_LDVM || op->driver == UNSFLOW_DRIVER_LDVMLIN || op->driver == UNSFLOW_DRIVER_LAUTAT,
-             "unsflow_ldvm_batch_run: prescribed-motion drivers only (ldvm, ldvmLin, lautat)");
+    if (strpar) {
+        UF_CHECK(op->driver == UNSFLOW_DRIVER_LDVM2DOF && kinem2dof, "unsflow_ldvm2dof_batch_run: driver must be UNSFLOW_DRIVER_LDVM2DOF and kinem2dof given");
+    } else {
+        UF_CHECK(op->driver == UNSFLOW_DRIVER_LDVM || op->driver == UNSFLOW_DRIVER_LDVMLIN || op->driver == UNSFLOW_DRIVER_LAUTAT,
+                 "unsflow_ldvm_batch_run: prescribed-motion drivers only (ldvm, ldvmLin, lautat); use unsflow_ldvm2dof_batch_run for ldvm2DOF");
+    }
     UF_CHECK(op->dt > 0, "unsflow_ldvm_batch_run: dt must be > 0");
     UF_CHECK(sf->bv.n == sf->ndiv - 1, "unsflow_ldvm_batch_run: surf.bv must hold ndiv-1 vortices");
     if (int rc = require_device()) return rc;
@@ -822,6 +829,10 @@ int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64
     s0.a0 = sf->a0; s0.a0dot = sf->a0dot; s0.a0prev = sf->a0prev;
     for (int64_t m = 0; m < M; m++) {
         hst[m] = s0;
+        if (strpar) {
+            memcpy(hst[m].sp, strpar + 11 * m, sizeof(double) * 11);
+            memcpy(hst[m].k2, kinem2dof + 22 * m, sizeof(double) * 22);
+        }
         LdvmDev &d = hd[m];
         memset(&d, 0, sizeof(d));
         d.st = st.p + m;
@@ -876,8 +887,24 @@ int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64
             for (int j = 0; j < 8; j++) mo[i + j * nsteps] = mi[8 * i + j];
         if (ntev_out) ntev_out[m] = hst[m].wake.end[0] - hst[m].wake.begin[0];
         if (nlev_out) nlev_out[m] = hst[m].wake.end[1] - hst[m].wake.begin[1];
+        if (kinem2dof_out) memcpy(kinem2dof_out + 22 * m, hst[m].k2, sizeof(double) * 22);
     }
     return 0;
+}
+
+extern "C" {
+
+int unsflow_ldvm_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
+                           const double *tables, const double *lespcrit, double *mat_out, int64_t *ntev_out,
+                           int64_t *nlev_out) {
+    return batch_run_impl(sf, op, nmember, nsteps, tables, lespcrit, nullptr, nullptr, mat_out, nullptr, ntev_out, nlev_out);
+}
+
+int unsflow_ldvm2dof_batch_run(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
+                               const double *tables, const double *lespcrit, const double *strpar11, const double *kinem22,
+                               double *mat_out, double *kinem22_out, int64_t *ntev_out, int64_t *nlev_out) {
+    UF_CHECK(strpar11 && kinem22, "unsflow_ldvm2dof_batch_run: null strpar / kinem");
+    return batch_run_impl(sf, op, nmember, nsteps, tables, lespcrit, strpar11, kinem22, mat_out, kinem22_out, ntev_out, nlev_out);
 }
 
 int unsflow_ldvm_batch_timing(float *ms_kernel) {

@@ -298,6 +298,40 @@ def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM,
     return np.ascontiguousarray(mats.transpose(0, 2, 1)), ntev, nlev, ms.value
 
 
+def ldvm2DOF_batch(surf, tables, lespcrit, strpars, kinems, dtstar=0.015, *, delvort=None, solve_mode=cabi.SOLVE_EXACT):
+    """Ensemble of independent ldvm2DOF runs (solvers.jl:657-788), e.g. a sweep over structural
+    parameters: member m uses TwoDOFPar strpars[m], starts from KinemPar2DOF kinems[m] and follows
+    tables[m] (kinematics_table(..., two_dof=True): only t and the external velocities are read).
+    Returns (mats [nmember, nsteps, 8], final KinemPar2DOF list, ntev, nlev, kernel_ms)."""
+    tables = cabi.f64(tables)
+    nmember, nsteps, ncol = tables.shape
+    if ncol != 9 or len(strpars) != nmember or len(kinems) != nmember:
+        raise ValueError("tables must be nmember x nsteps x 9 and strpars / kinems one per member")
+    lesp = cabi.f64(np.broadcast_to(np.asarray(lespcrit, dtype=np.float64), (nmember,)))
+    sp = cabi.f64(np.stack([p.as_array() for p in strpars]))
+    k0 = cabi.f64(np.stack([k.as_array() for k in kinems]))
+    kout = np.zeros_like(k0)
+    dt = dtstar * surf.c / surf.uref
+    keep = []
+    sst = surf_struct(surf, keep)
+    opts = _opts(cabi.DRIVER_LDVM2DOF, dt, nsteps, delvort or delNone(), solve_mode)
+    mats = np.zeros((nmember, 8, nsteps))
+    ntev = np.zeros(nmember, dtype=np.int64)
+    nlev = np.zeros(nmember, dtype=np.int64)
+    i64p = C.POINTER(C.c_int64)
+    cabi.check(cabi.lib().unsflow_ldvm2dof_batch_run(C.byref(sst), C.byref(opts), nmember, nsteps, cabi.dptr(tables), cabi.dptr(lesp),
+                                                     cabi.dptr(sp), cabi.dptr(k0), mats.ctypes.data_as(cabi.c_double_p),
+                                                     cabi.dptr(kout), ntev.ctypes.data_as(i64p), nlev.ctypes.data_as(i64p)))
+    ms = C.c_float(0)
+    cabi.check(cabi.lib().unsflow_ldvm_batch_timing(C.byref(ms)))
+    finals = []
+    for m in range(nmember):
+        k = KinemPar2DOF(0.0, 0.0, 0.0, 0.0, 0.0)
+        k.from_array(kout[m])
+        finals.append(k)
+    return np.ascontiguousarray(mats.transpose(0, 2, 1)), finals, ntev, nlev, ms.value
+
+
 def lve_table(surf, nsteps, dtstar):
     """Host-tabulated motion for LVE (LVE.jl:57-64): iterations i = 0..nsteps at the running-sum
     times t = -dtstar + dtstar + dtstar ... plus one more row (vor_BFR uses t + dtstar,
