@@ -21,6 +21,7 @@ with the NCCL exchange; total work is fixed => "scaling": "strong".
 import argparse
 import ctypes as C
 import json
+import copy
 import os
 import subprocess
 import sys
@@ -363,6 +364,27 @@ def main():
             extra["ldvm_launches_per_step"] = nl / ns
         except Exception as e:   # never lose the headline line
             extra["ldvm_error"] = str(e)[:200]
+        # config C1 (the reference's own test case, test/ldvmLinTest.jl through ldvm, 468 steps from an empty
+        # wake): device-resident steps/s on rank 0, with the CPU oracle's steps/s beside it
+        if rank == 0:
+            try:
+                from cases import c1_surf
+                surf1, fld1, n1, dts1 = c1_surf(uf)
+                uf.ldvm(copy.deepcopy(surf1), uf.TwoDFlowField(), n1, dts1, write_summary=False)        # warm-up (graph capture)
+                hh = LdvmHandle(surf1, fld1, _opts(cabi.DRIVER_LDVM, dts1 * surf1.c / surf1.uref, n1, uf.delNone(), cabi.SOLVE_EXACT))
+                hh.set_kinematics(uf.kinematics_table(surf1, fld1, n1, dts1))
+                hh.run(n1)
+                ms1, nl1 = hh.timing()
+                hh.close()
+                c1 = {"steps": n1, "device_ms": ms1, "steps_per_s": n1 / (ms1 * 1e-3), "launches_per_step": nl1 / n1}
+                if not args.no_cpu_baseline:
+                    from oracle import oracle as O
+                    t0 = time.perf_counter()
+                    O.Sim(surf1, uf.TwoDFlowField()).run(O.DRIVER_LDVM, uf.kinematics_table(surf1, uf.TwoDFlowField(), n1, dts1), dts1)
+                    c1["cpu_oracle_steps_per_s"] = n1 / (time.perf_counter() - t0)
+                extra["ldvm_C1"] = c1
+            except Exception as e:
+                extra["ldvm_C1"] = {"error": str(e)[:200]}
 
     if rank != 0:
         if world > 1:
