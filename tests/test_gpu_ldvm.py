@@ -505,3 +505,14 @@ def test_500_step_attached_history(gpu_lib, uf, oracle):
     assert err <= HTOL, err
     assert err < 1e-11            # in practice round-off level
     _cmp_state(surf, fld, sim)
+
+
+def test_randomised_configurations_against_oracle(gpu_lib, uf, oracle):
+    """tools/fuzz_ldvm.py in miniature: random motion types, pivots, LESP thresholds, discretisations, chord /
+    reference speed, camber, gust fields, external vortices, Spalart merging, ldvm / ldvmLin / lautat, both solve
+    modes -- every history within tolerance of the oracle"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_ldvm", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_ldvm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(ncase=16, seed=7) == 0
