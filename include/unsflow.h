@@ -147,7 +147,7 @@ typedef struct unsflow_field {
 #define UNSFLOW_DRIVER_LAUTAT   3   /* lautat    solvers.jl:42-142  */
 
 #define UNSFLOW_SOLVE_EXACT   0     /* state left at the root of the (affine) Kelvin/Kutta residual */
-#define UNSFLOW_SOLVE_NLSOLVE 1     /* state left at NLsolve's last finite-difference probe */
+#define UNSFLOW_SOLVE_NLSOLVE 1     /* NLsolve trust-region iteration restated on the device; state left at its last finite-difference probe */
 
 #define UNSFLOW_DEL_NONE    0       /* delNone     delVort.jl:3 */
 #define UNSFLOW_DEL_SPALART 1       /* delSpalart  delVort.jl:5-9 */

@@ -1,6 +1,7 @@
 // step_single.cuh -- single-surface step: ldvm / ldvm2DOF / ldvmLin / lautat (k_step_head, k_step_solve bodies)
 #pragma once
 #include "step_state.cuh"
+#include "nlsolve_dev.cuh"
 
 namespace unsflow {
 
@@ -220,10 +221,16 @@ __device__ void step_solve(const LdvmDev &d) {
             const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.);
             const double Kp = kfac * (a0prev + aprev1 / 2.);
             // Kelvin condition typedefs.jl:249-251:  K0 + g*K1 - Kp + g = 0
-            const double g = -(K0 - Kp) / (K1 + 1.0);
+            double g = -(K0 - Kp) / (K1 + 1.0);
+            if (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) {
+                // nlsolve(not_in_place(kelv), [-0.01]) (solvers.jl:199): soln.zero is the trust-region iterate;
+                // the reference is left in the state of the last finite-difference probe g - eps
+                double xs[1] = {-0.01};
+                auto f1 = [&](const double *x, double *r) { r[0] = K0 + x[0] * K1 - Kp + x[0]; };
+                dev_nlsolve_tr<1>(f1, xs);
+                g = xs[0];
+            }
             sc[8] = g;
-            // state the reference is left in: at the root (exact) or at NLsolve's last
-            // finite-difference probe g - eps
             sc[9] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) ? g - eps_fd * fmax(1.0, fabs(g)) : g;
         }
         __syncthreads();
@@ -309,8 +316,21 @@ __device__ void step_solve(const LdvmDev &d) {
                 const double m11 = K1 + 1., m12 = K2 + 1., m21 = a01, m22 = a02;
                 const double r1 = Kp - K0, r2 = lesp_cond - a00;
                 const double det = m11 * m22 - m12 * m21;
-                const double g1 = (r1 * m22 - m12 * r2) / det;
-                const double g2 = (m11 * r2 - r1 * m21) / det;
+                double g1 = (r1 * m22 - m12 * r2) / det;
+                double g2 = (m11 * r2 - r1 * m21) / det;
+                if (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) {
+                    // nlsolve(not_in_place(kelvkutta), [-0.01; 0.01]) (solvers.jl:216).  The LESP target follows the
+                    // sign of A0 at every iterate (typedefs.jl:340-344): two self-consistent roots, the iteration picks.
+                    double xs[2] = {-0.01, 0.01};
+                    const double lc = d.lespcrit;
+                    auto f2 = [&](const double *x, double *r) {
+                        const double a0x = a00 + a01 * x[0] + a02 * x[1];
+                        r[0] = K0 + K1 * x[0] + K2 * x[1] - Kp + x[0] + x[1];
+                        r[1] = a0x - (a0x > 0 ? lc : -lc);
+                    };
+                    dev_nlsolve_tr<2>(f2, xs);
+                    g1 = xs[0]; g2 = xs[1];
+                }
                 sc[8] = g1; sc[14] = g2;
                 sc[9] = g1;
                 sc[15] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) ? g2 - eps_fd * fmax(1.0, fabs(g2)) : g2;
