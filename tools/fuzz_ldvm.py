@@ -91,7 +91,7 @@ def main(ncase=NCASE, seed=SEED):
         cs = make_case(rng)
         driver, surf, fld, delv, mode, nsteps, dtstar, lesp = (cs[k] for k in ("driver", "surf", "fld", "delv", "mode", "nsteps", "dtstar", "lesp"))
         om = oracle_history(cs)
-        if not np.all(np.isfinite(om)) or np.max(np.abs(om[:, 4])) > 5.0 or np.max(np.abs(om[:, 5])) > 50.0:
+        if not np.all(np.isfinite(om)) or np.max(np.abs(om[:, 4])) > 5.0 or np.max(np.abs(om[2:, 5])) > 50.0:
             # the random motion / structure drove the model out of its range (a vortex on top of a bound point, a
             # numerically unstable explicit fluid-structure coupling with saw-tooth loads growing every step):
             # round-off is amplified without bound, on the CPU as on the GPU
@@ -123,5 +123,44 @@ def main(ncase=NCASE, seed=SEED):
     return 1 if bad else 0
 
 
+def main_multi(ncase=NCASE // 3, seed=SEED):
+    """multi-surface ldvm(::Vector{TwoDSurf}) (solvers.jl:270-445): 2-4 plates at random stations with random
+    pitch / plunge motions and LESP thresholds, exact-root mode, against the multi-surface oracle"""
+    rng = np.random.default_rng(seed + 1000)
+    worst, bad = 0.0, 0
+    for case in range(ncase):
+        ns = int(rng.integers(2, 5))
+        ndiv, naterm = int(rng.choice([70, 40])), int(rng.choice([35, 20]))
+        surfs, x0 = [], 0.0
+        for q in range(ns):
+            kin = uf.KinemDef(motion(rng, int(rng.choice([0, 1, 2, 3])), 0.3), motion(rng, int(rng.choice([0, 0, 1])), 0.1), uf.ConstDef(1.0))
+            surfs.append(uf.TwoDSurf("FlatPlate", float(rng.choice([0.0, 0.25, 0.5])), kin, [float(rng.choice([0.1, 0.2, 10.0]))],
+                                     ndiv=ndiv, naterm=naterm, initpos=(x0, float(rng.uniform(-0.3, 0.3)))))
+            x0 += rng.uniform(1.3, 2.5)
+        fld = uf.TwoDFlowField()
+        nsteps, dtstar = int(rng.integers(40, 80)), float(rng.choice([0.015, 0.01]))
+        tabs = np.stack([uf.kinematics_table(sf, fld, nsteps, dtstar) for sf in surfs], axis=1)
+        om = O.MultiSim(copy.deepcopy(surfs), copy.deepcopy(fld)).run(tabs, dtstar)
+        if not np.all(np.isfinite(om)) or np.max(np.abs(om[2:, 1:])) > 50.0:      # (rows 0-1: impulsive-start spike)
+            why = "NaN (zero-core placeholder LEV on a bound point, calcs.jl:446)" if not np.all(np.isfinite(om)) else "blows up"
+            print(f"multi case {case:3d} skipped: oracle history {why}", flush=True)
+            continue
+        gm, s2, f2 = uf.ldvm(surfs, fld, nsteps, dtstar, write_summary=False)
+        a0cols = om[:, 4::7]
+        lesps = np.array([sf.lespcrit[0] for sf in surfs])
+        shed = np.cumsum(np.sum(np.abs(np.abs(a0cols) - lesps[None, :]) < 1e-9, axis=1))
+        cut = int(np.searchsorted(shed, 25, side="right")) if shed[-1] > 25 else nsteps
+        err = float(np.max(np.abs(gm[:cut] - om[:cut]))) / max(1.0, float(np.max(np.abs(om[:cut, 1:]))))
+        worst = max(worst, err)
+        bad += err > TOL
+        print(f"multi case {case:3d} nsurf {ns} ndiv {ndiv} steps {nsteps} cmp {cut} ntev {len(f2.tev)} nlev {len(f2.lev)} err {err:.2e}"
+              f"{'' if err <= TOL else '  <-- FAIL'}", flush=True)
+    print(f"{ncase} multi-surface cases, worst relative history error {worst:.2e}, {bad} above tolerance ({TOL})")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    if os.environ.get("FUZZ_MULTI", "1") != "0":
+        rc |= main_multi()
+    sys.exit(rc)
