@@ -159,8 +159,39 @@ def main_multi(ncase=NCASE // 3, seed=SEED):
     return 1 if bad else 0
 
 
+def main_lve(ncase=NCASE // 10, seed=SEED):
+    """LVE panel solver (src/lowOrder2D/LVE.jl): random pitch / plunge motions, pivots, LESP thresholds and panel counts
+    against the LVE oracle"""
+    rng = np.random.default_rng(seed + 2000)
+    worst, bad = 0.0, 0
+    for case in range(ncase):
+        kin = uf.KinemDef(motion(rng, int(rng.choice([0, 1, 3])), 0.35), motion(rng, int(rng.choice([0, 0, 2])), 0.1), uf.ConstDef(1.0))
+        lesp, ndiv = float(rng.choice([0.15, 0.25, 10.0])), int(rng.choice([70, 40, 100]))
+        pvt = float(rng.choice([0.0, 0.25, 0.5]))
+        surf = uf.TwoDSurf("FlatPlate", pvt, kin, [lesp], rho=float(rng.choice([1.0, 0.04])), ndiv=ndiv)
+        ifr = uf.TwoDSurf("FlatPlate", pvt, kin, [lesp], ndiv=ndiv, camberType="linear")
+        n, dtstar = int(rng.integers(40, 110)), float(rng.choice([0.015, 0.01]))
+        tab = uf.lve_table(surf, n, dtstar)
+        om = O.LveSim(copy.deepcopy(surf), ifr).run(tab, n, dtstar)
+        if not np.all(np.isfinite(om)) or np.max(np.abs(om[2:, 4:])) > 50.0:
+            print(f"lve case {case:3d} skipped: oracle history blows up", flush=True)
+            continue
+        frames, ifr_field, gm, th, lh = uf.LVE(surf, uf.TwoDFlowField(), n, dtstar)
+        cut = n if len(ifr_field.lev) <= 25 else int(np.searchsorted(np.cumsum(np.isin(tab[1:n + 1, 0], lh[:, 0])), 25, side="right"))
+        err = float(np.max(np.abs(gm[:cut] - om[:cut]))) / max(1.0, float(np.max(np.abs(om[:cut, 4:]))))
+        worst = max(worst, err)
+        bad += err > TOL
+        print(f"lve case {case:3d} ndiv {ndiv} pvt {pvt} lesp {lesp} steps {n} cmp {cut} ntev {len(ifr_field.tev)} nlev {len(ifr_field.lev)} err {err:.2e}"
+              f"{'' if err <= TOL else '  <-- FAIL'}", flush=True)
+    print(f"{ncase} LVE cases, worst relative history error {worst:.2e}, {bad} above tolerance ({TOL})")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
+    if os.environ.get("FUZZ_ONLY") == "lve":
+        sys.exit(main_lve())
     rc = main()
+    rc |= main_lve()
     if os.environ.get("FUZZ_MULTI", "1") != "0":
         rc |= main_multi()
     sys.exit(rc)
