@@ -136,10 +136,7 @@ __device__ void mstep_solve(const LdvmDev &d) {
             d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
         }
         __syncthreads();
-        for (int n = warp; n <= na; n += nwarps) {
-            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-            if (lane == 0) aterm[n] = v;
-        }
+        block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
         __syncthreads();
         if (tid == 0) {
             const double a0 = -aterm[0] / urefpi;
@@ -276,10 +273,7 @@ __device__ void mstep_solve(const LdvmDev &d) {
             __syncthreads();
         }
         // final Fourier coefficients of this surface from its final downwash
-        for (int n = warp; n <= na; n += nwarps) {
-            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-            if (lane == 0) aterm[n] = v;
-        }
+        block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
         __syncthreads();
         if (tid == 0) {
             const double a0 = -aterm[0] / urefpi;

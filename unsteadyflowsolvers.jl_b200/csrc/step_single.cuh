@@ -103,6 +103,24 @@ __device__ __forceinline__ double warp_trapz_cos(const double *y, const double *
     return acc * 0.5;
 }
 
+// All integrals n = 0..na of one downwash at once: 4 consecutive lanes per integral (64 integrals per pass of a
+// 256-thread block), each lane a strided quarter of the panels, two xor-shuffles to combine.  One short pass
+// instead of ceil((na+1)/8) dependent warp-wide passes.
+__device__ __forceinline__ void block_trapz_cos_all(const double *y, const double *dth, const double *costab, int nd, int na, double *out) {
+    const int sub = threadIdx.x & 3, grp = threadIdx.x >> 2, ngrp = blockDim.x >> 2;
+    for (int n0 = 0; n0 <= na; n0 += ngrp) {
+        const int n = n0 + grp;
+        double acc = 0.0;
+        if (n <= na) {
+            const double *cr = costab + (long long)n * nd;
+            for (int i = 1 + sub; i < nd; i += 4) acc += dth[i] * (y[i] * cr[i] + y[i - 1] * cr[i - 1]);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (n <= na && sub == 0) out[n] = acc * 0.5;
+    }
+}
+
 // unit-strength induced velocity of one vortex at (xv,zv) on bound point i, calcs.jl:469-473
 __device__ __forceinline__ void unit_influence(double xv, double zv, double vc4, double bx, double bz, double *u, double *w) {
     const double xdist = xv - bx, zdist = zv - bz;
@@ -246,10 +264,7 @@ __device__ void step_solve(const LdvmDev &d) {
         // all A_n integrals of this downwash at once: A0..A3 feed update_a2a3adot (:2-12) /
         // update_atermdot (:14-24); when no LEV is shed they are also the final coefficients
         // (update_a2toan :66-72 recomputes the same numbers), so phase H is skipped then
-        for (int n = warp; n <= na; n += nwarps) {
-            const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-            if (lane == 0) aterm[n] = v;
-        }
+        block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
         __syncthreads();
         if (tid == 0) {
             const double a0 = -aterm[0] / urefpi;
@@ -348,10 +363,7 @@ __device__ void step_solve(const LdvmDev &d) {
         // ---- H: all Fourier coefficients from the final downwash (update_a0anda1 :57-63,
         //         update_a2toan :66-72); only the LEV branch changed the downwash since phase F ---
         if (lev_shed) {
-            for (int n = warp; n <= na; n += nwarps) {
-                const double v = warp_trapz_cos(dw, dth, d.costab + n * nd, nd);
-                if (lane == 0) aterm[n] = v;
-            }
+            block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
             __syncthreads();
         }
         if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
@@ -369,11 +381,8 @@ __device__ void step_solve(const LdvmDev &d) {
         __syncthreads();
         // integrals of T1, T2 against cos(n theta), n = 0..na  -> uL (T1), wL (T2) reused as storage
         double *c1 = uL, *c2 = wL, *c3 = uT;
-        for (int n = warp; n <= na; n += nwarps) {
-            const double v1 = warp_trapz_cos(T1, dth, d.costab + n * nd, nd);
-            const double v2 = warp_trapz_cos(T2, dth, d.costab + n * nd, nd);
-            if (lane == 0) { c1[n] = v1; c2[n] = v2; }
-        }
+        block_trapz_cos_all(T1, dth, d.costab, nd, na, c1);
+        block_trapz_cos_all(T2, dth, d.costab, nd, na, c2);
         __syncthreads();
         if (tid == 0) {
             // I = trapz(T.*(cos(theta)-1)) = c[1] - c[0]  (algebraically; :511, :535)
@@ -417,10 +426,7 @@ __device__ void step_solve(const LdvmDev &d) {
                 T3[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
             }
             __syncthreads();
-            for (int n = warp; n <= na; n += nwarps) {
-                const double v3 = warp_trapz_cos(T3, dth, d.costab + n * nd, nd);
-                if (lane == 0) c3[n] = v3;
-            }
+            block_trapz_cos_all(T3, dth, d.costab, nd, na, c3);
             __syncthreads();
             if (tid == 0) {
                 const double I1 = sc[0], J1 = sc[1], I2 = sc[2], J2 = sc[3], sig_prev = sc[4];
