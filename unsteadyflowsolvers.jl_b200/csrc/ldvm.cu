@@ -32,7 +32,29 @@
 namespace unsflow {
 
 __global__ void __launch_bounds__(kSolveThreads) k_step_head(const LdvmDev d) { step_head(d); }
-__global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d) { step_solve(d); }
+// shared-memory copy of the cos / sin tables, filled by TMA bulk copies issued by one thread at kernel entry
+__device__ __forceinline__ void tabs_to_smem(const LdvmDev &d, double *dst, uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        const uint32_t bytes = (uint32_t)(sizeof(double) * 2 * (d.naterm + 1) * d.ndiv);
+        mbar_expect_tx(bar, bytes);
+        for (uint32_t o = 0; o < bytes; o += 16384)
+            tma_load_1d(reinterpret_cast<char *>(dst) + o, reinterpret_cast<const char *>(d.costab) + o, min(16384u, bytes - o), bar);
+    }
+    __syncthreads();   // the initialised barrier is visible to every waiter
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d, int tabs_in_smem) {
+    extern __shared__ __align__(128) double tab_s[];
+    __shared__ __align__(8) uint64_t tab_bar;
+    if (tabs_in_smem) {
+        tabs_to_smem(d, tab_s, &tab_bar);
+        step_solve(d, tab_s, tab_s + (d.naterm + 1) * d.ndiv, &tab_bar);
+    } else {
+        step_solve(d, d.costab, d.sintab, nullptr);
+    }
+}
 
 __global__ void __launch_bounds__(kSolveThreads) k_mstep_head(const LdvmDev d) { mstep_head(d); }
 __global__ void __launch_bounds__(kSolveThreads) k_mstep_solve(const LdvmDev d) { mstep_solve(d); }
@@ -67,7 +89,7 @@ __global__ void __launch_bounds__(kSolveThreads, 3) k_ensemble(const LdvmDev *me
             if (threadIdx.x == 0) d.S2 = S2;
             __syncthreads();
         }
-        step_solve(d);
+        step_solve(d, d.costab, d.sintab, nullptr);
         __syncthreads();
         ens_rollup(d, ens_smem, tot);
     }
@@ -500,7 +522,13 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     }
     if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * h->ndiv, st>>>(h->dev);
     else if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
-    else k_step_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
+    else {
+        // tables in shared memory when they fit beside the kernel's static arrays (default 70 x 35: 40 KB)
+        const size_t tab_bytes = sizeof(double) * 2 * (size_t)(h->naterm + 1) * h->ndiv;
+        const int in_smem = tab_bytes <= 160 * 1024;
+        if (in_smem) UF_CUDA(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+        k_step_solve<<<1, kSolveThreads, in_smem ? tab_bytes : 0, st>>>(h->dev, in_smem);
+    }
     h->launches++;
     // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
     const bool sym = h->uniform && nwake_ub >= sym_threshold();

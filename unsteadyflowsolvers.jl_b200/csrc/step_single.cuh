@@ -5,6 +5,7 @@
 
 namespace unsflow {
 
+
 // ---------------------------------------------------------------------------------------------
 // k_step_head
 // ---------------------------------------------------------------------------------------------
@@ -161,7 +162,10 @@ __device__ void dev_spalart(const LdvmDev &d, long long *begin, long long end, d
     }
 }
 
-__device__ void step_solve(const LdvmDev &d) {
+// costab / sintab: the [(naterm+1)][ndiv] cos(n theta) / sin(n theta) tables -- d.costab / d.sintab in global memory, or
+// a shared-memory copy that a TMA bulk copy started at kernel entry is still filling (tab_bar != nullptr: wait on it
+// before the first table read; the copy overlaps the partial-plane sums of phase A)
+__device__ void step_solve(const LdvmDev &d, const double *costab, const double *sintab, uint64_t *tab_bar) {
     StepState *s = d.st;
     const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm;
     __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
@@ -191,20 +195,24 @@ __device__ void step_solve(const LdvmDev &d) {
             uind[i] = d.uind[i];
             wind[i] = d.wind[i];
         } else {
+            // masked batches of 16 independent loads (one L2 latency per batch); additions stay in plane order
             double su = 0.0, sw = 0.0;
-            int k = 0;
-            for (; k + 8 <= d.S2; k += 8) {
-                double bu[8], bw[8];
+            for (int k = 0; k < d.S2; k += 16) {
+                double bu[16], bw[16];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { bu[q] = d.p2u[(long long)(k + q) * d.p2stride + i]; bw[q] = d.p2w[(long long)(k + q) * d.p2stride + i]; }
+                for (int q = 0; q < 16; q++) {
+                    const bool ok = k + q < d.S2;
+                    bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
+                    bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
+                }
 #pragma unroll
-                for (int q = 0; q < 8; q++) { su += bu[q]; sw += bw[q]; }
+                for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
             }
-            for (; k < d.S2; k++) { su += d.p2u[(long long)k * d.p2stride + i]; sw += d.p2w[(long long)k * d.p2stride + i]; }
             uind[i] = su * kInvTwoPi;
             wind[i] = sw * kInvTwoPi;
         }
     }
+    if (tab_bar) mbar_wait(tab_bar, 0);
     __syncthreads();
 
     // location of the TEV shed this step
@@ -229,7 +237,7 @@ __device__ void step_solve(const LdvmDev &d) {
         __syncthreads();
         // ---- D: A0, A1 as affine functions of the TEV strength --------------------------------
         for (int q = warp; q < 4; q += nwarps) {
-            const double v = warp_trapz_cos((q & 2) ? dw1 : dw, dth, d.costab + (q & 1) * nd, nd);
+            const double v = warp_trapz_cos((q & 2) ? dw1 : dw, dth, costab + (q & 1) * nd, nd);
             if (lane == 0) sc[q] = v;
         }
         __syncthreads();
@@ -264,7 +272,7 @@ __device__ void step_solve(const LdvmDev &d) {
         // all A_n integrals of this downwash at once: A0..A3 feed update_a2a3adot (:2-12) /
         // update_atermdot (:14-24); when no LEV is shed they are also the final coefficients
         // (update_a2toan :66-72 recomputes the same numbers), so phase H is skipped then
-        block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
+        block_trapz_cos_all(dw, dth, costab, nd, na, aterm);
         __syncthreads();
         if (tid == 0) {
             const double a0 = -aterm[0] / urefpi;
@@ -316,7 +324,7 @@ __device__ void step_solve(const LdvmDev &d) {
             }
             __syncthreads();
             for (int q = warp; q < 6; q += nwarps) {
-                const double v = warp_trapz_cos(q < 2 ? dw : (q < 4 ? dw1 : dw2), dth, d.costab + (q & 1) * nd, nd);
+                const double v = warp_trapz_cos(q < 2 ? dw : (q < 4 ? dw1 : dw2), dth, costab + (q & 1) * nd, nd);
                 if (lane == 0) sc[q] = v;
             }
             __syncthreads();
@@ -363,7 +371,7 @@ __device__ void step_solve(const LdvmDev &d) {
         // ---- H: all Fourier coefficients from the final downwash (update_a0anda1 :57-63,
         //         update_a2toan :66-72); only the LEV branch changed the downwash since phase F ---
         if (lev_shed) {
-            block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
+            block_trapz_cos_all(dw, dth, costab, nd, na, aterm);
             __syncthreads();
         }
         if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
@@ -381,8 +389,8 @@ __device__ void step_solve(const LdvmDev &d) {
         __syncthreads();
         // integrals of T1, T2 against cos(n theta), n = 0..na  -> uL (T1), wL (T2) reused as storage
         double *c1 = uL, *c2 = wL, *c3 = uT;
-        block_trapz_cos_all(T1, dth, d.costab, nd, na, c1);
-        block_trapz_cos_all(T2, dth, d.costab, nd, na, c2);
+        block_trapz_cos_all(T1, dth, costab, nd, na, c1);
+        block_trapz_cos_all(T2, dth, costab, nd, na, c2);
         __syncthreads();
         if (tid == 0) {
             // I = trapz(T.*(cos(theta)-1)) = c[1] - c[0]  (algebraically; :511, :535)
@@ -426,7 +434,7 @@ __device__ void step_solve(const LdvmDev &d) {
                 T3[i] = (d.cam_slope[i] * zdist + xdist) / (kTwoPi * sqrt(distsq * distsq + d.vc4_new));
             }
             __syncthreads();
-            block_trapz_cos_all(T3, dth, d.costab, nd, na, c3);
+            block_trapz_cos_all(T3, dth, costab, nd, na, c3);
             __syncthreads();
             if (tid == 0) {
                 const double I1 = sc[0], J1 = sc[1], I2 = sc[2], J2 = sc[3], sig_prev = sc[4];
@@ -480,10 +488,10 @@ __device__ void step_solve(const LdvmDev &d) {
     // ---- I: update_bv, calcs.jl:204-219 -------------------------------------------------------
     const double a0 = sc[10];
     for (int ib = tid; ib < nd; ib += blockDim.x) {
-        double g = (a0 * (1 + d.costab[nd + ib]));
-        const double sth = d.sintab[nd + ib];
+        double g = (a0 * (1 + costab[nd + ib]));
+        const double sth = sintab[nd + ib];
 #pragma unroll 7
-        for (int ia = 1; ia <= na; ia++) g = g + aterm[ia] * d.sintab[ia * nd + ib] * sth;
+        for (int ia = 1; ia <= na; ia++) g = g + aterm[ia] * sintab[ia * nd + ib] * sth;
         gam[ib] = g * d.uref * d.c;
     }
     __syncthreads();
