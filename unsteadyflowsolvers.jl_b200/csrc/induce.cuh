@@ -182,20 +182,16 @@ __global__ void __launch_bounds__(256) k_induce_finish(const FinishArgs a) {
     }
     if (i < 0) return;
     double su = 0.0, sw = 0.0;
-    int s = 0;
-    for (; s + 8 <= a.S; s += 8) {      // batches of independent loads; the additions stay in plane order
-        double bu[8], bw[8];
+    for (int s = 0; s < a.S; s += 16) {   // masked batches of 16 independent loads; the additions stay in plane order
+        double bu[16], bw[16];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            bu[k] = a.pu[(long long)(s + k) * a.tstride + i];
-            bw[k] = a.pw[(long long)(s + k) * a.tstride + i];
+        for (int k = 0; k < 16; k++) {
+            const bool ok = s + k < a.S;
+            bu[k] = ok ? a.pu[(long long)(s + k) * a.tstride + i] : 0.0;
+            bw[k] = ok ? a.pw[(long long)(s + k) * a.tstride + i] : 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { su += bu[k]; sw += bw[k]; }
-    }
-    for (; s < a.S; s++) {
-        su += a.pu[(long long)s * a.tstride + i];
-        sw += a.pw[(long long)s * a.tstride + i];
+        for (int k = 0; k < 16; k++) { su += bu[k]; sw += bw[k]; }
     }
     if (a.raw) { a.vx[i] = su; a.vz[i] = sw; return; }
     double vx = su * kInvTwoPi, vz = sw * kInvTwoPi;
