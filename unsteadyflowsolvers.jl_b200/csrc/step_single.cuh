@@ -44,9 +44,19 @@ __device__ void dev_update_kinem2dof(const LdvmDev &d, StepState *s) {
 }
 
 __device__ void step_head(const LdvmDev &d) {
+    // Three independent chains of dependent global loads run side by side (each costs two L2 round trips):
+    // thread 0: step counter -> kinematics row;  thread 32: wake counts -> newest TEV;  all threads: geometry.
     StepState *s = d.st;
-    const int tid = threadIdx.x;
-    __shared__ double sh_kin[6];
+    const int tid = threadIdx.x, nd = d.ndiv;      // nd <= kNdMax == blockDim.x: one bound point per thread
+    __shared__ double sh_kin[6], sh_last[2], sh_te[2];
+    __shared__ long long sh_be[2];
+    double bx = 0.0, bz = 0.0, xi = 0.0, ci = 0.0;
+    if (tid < nd) { bx = d.bnd_x[tid]; bz = d.bnd_z[tid]; xi = d.x[tid]; ci = d.cam[tid]; }
+    if (tid == 32 % blockDim.x && d.driver != UNSFLOW_DRIVER_LDVMLIN) {
+        const long long b = s->wake.begin[0], e = s->wake.end[0];
+        sh_be[0] = b; sh_be[1] = e;
+        if (e > b) { sh_last[0] = d.wx[e - 1]; sh_last[1] = d.wz[e - 1]; }
+    }
     if (tid == 0) {
         const long long row = s->step < d.kin_rows ? s->step : d.kin_rows - 1;
         const double *r = d.kin + 9 * row;
@@ -66,22 +76,24 @@ __device__ void step_head(const LdvmDev &d) {
     double sa, ca;
     sincos(alpha, &sa, &ca);
     // update_boundpos, calcs.jl:453-459
-    for (int i = tid; i < d.ndiv; i += blockDim.x) {
-        d.bnd_x[i] = d.bnd_x[i] + d.dt * ((d.pvt * d.c - d.x[i]) * sa * alphadot - u + d.cam[i] * ca * alphadot);
-        d.bnd_z[i] = d.bnd_z[i] + d.dt * (hdot + (d.pvt * d.c - d.x[i]) * ca * alphadot - d.cam[i] * sa * alphadot);
+    if (tid < nd) {
+        bx = bx + d.dt * ((d.pvt * d.c - xi) * sa * alphadot - u + ci * ca * alphadot);
+        bz = bz + d.dt * (hdot + (d.pvt * d.c - xi) * ca * alphadot - ci * sa * alphadot);
+        d.bnd_x[tid] = bx;
+        d.bnd_z[tid] = bz;
+        if (tid == nd - 1) { sh_te[0] = bx; sh_te[1] = bz; }
     }
     __syncthreads();
     if (tid == 0 && d.driver != UNSFLOW_DRIVER_LDVMLIN) {
         // place_tev, calcs.jl:375-387
-        const long long b = s->wake.begin[0], e = s->wake.end[0];
-        const int nd = d.ndiv;
+        const long long b = sh_be[0], e = sh_be[1];
         double xloc, zloc;
         if (e == b) {
-            xloc = d.bnd_x[nd - 1] + 0.5 * u * d.dt;
-            zloc = d.bnd_z[nd - 1];
+            xloc = sh_te[0] + 0.5 * u * d.dt;
+            zloc = sh_te[1];
         } else {
-            xloc = d.bnd_x[nd - 1] + (1. / 3.) * (d.wx[e - 1] - d.bnd_x[nd - 1]);
-            zloc = d.bnd_z[nd - 1] + (1. / 3.) * (d.wz[e - 1] - d.bnd_z[nd - 1]);
+            xloc = sh_te[0] + (1. / 3.) * (sh_last[0] - sh_te[0]);
+            zloc = sh_te[1] + (1. / 3.) * (sh_last[1] - sh_te[1]);
         }
         d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0; d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new;
         d.wvx[e] = 0.0; d.wvz[e] = 0.0;
