@@ -30,7 +30,7 @@ def trapz(y, x):
 
 
 class NpLdvm:
-    """State = plain numpy arrays; drivers: ldvm (two_dof=None) and ldvm2DOF."""
+    """State = plain numpy arrays; drivers: ldvm, ldvm2DOF (k2 / sp set), ldvmLin, lautat."""
 
     def __init__(self, surf, fld):
         s = surf
@@ -109,11 +109,13 @@ class NpLdvm:
                 self.fam[fam] = v[:, 1:].copy()
                 return
 
-    def step(self, dt, row, delvort=None):
-        """one iteration of solvers.jl:178-257 (ldvm) / :697-778 (ldvm2DOF)"""
+    def step(self, dt, row, delvort=None, lautat=False):
+        """one iteration of solvers.jl:178-257 (ldvm) / :697-778 (ldvm2DOF) / :47-100 (lautat: no update_externalvel,
+        no update_indbound -- surf.uind only ever accumulates each step's own new TEV -- and no LEV branch)"""
         two = self.k2 is not None
         t = row[0]
-        self.fs = [row[7], row[8]]
+        if not lautat:
+            self.fs = [row[7], row[8]]
         if two:
             self.kinem2dof(dt)
         else:
@@ -130,7 +132,12 @@ class NpLdvm:
             zt = self.bnd_z[-1] + (tev[1, -1] - self.bnd_z[-1]) / 3.0
         vc = 0.02 * self.c
         w = self.wake()
-        ub, wb = induce(w[0], w[1], w[2], w[3], self.bnd_x, self.bnd_z)                                            # calcs.jl:35-38
+        if lautat:
+            if not hasattr(self, "uind_keep"):
+                self.uind_keep, self.wind_keep = np.zeros(self.nd), np.zeros(self.nd)
+            ub, wb = self.uind_keep, self.wind_keep
+        else:
+            ub, wb = induce(w[0], w[1], w[2], w[3], self.bnd_x, self.bnd_z)                                        # calcs.jl:35-38
         one = np.ones(1)
         uT, wT = induce(np.array([xt]), np.array([zt]), one, vc * one, self.bnd_x, self.bnd_z)
         kf = self.uref * self.c * math.pi
@@ -149,7 +156,9 @@ class NpLdvm:
         self.adot[:nrate] = (at_pre - self.aprev[:nrate]) / dt
         ui, wi = ub + gt * uT, wb + gt * wT
         gl = None
-        if abs(a0) > self.lespcrit:                                                                                # solvers.jl:208
+        if lautat:
+            self.uind_keep, self.wind_keep = ui, wi
+        if abs(a0) > self.lespcrit and not lautat:                                                                 # solvers.jl:208
             lev = self.fam[1]
             if self.levflag == 0:                                                                                  # calcs.jl:409-426
                 xl = self.bnd_x[0] + 0.5 * (u - ald * math.sin(al) * pc + ui[0]) * dt
@@ -170,7 +179,7 @@ class NpLdvm:
             a0 = self.fourier(dw, 0)
             self.fam[1] = np.concatenate([lev, np.array([[xl], [zl], [gl], [vc]])], axis=1)
             self.levflag = 1
-        else:
+        elif not lautat:
             self.levflag = 0
         self.fam[0] = np.concatenate([tev, np.array([[xt], [zt], [gt], [vc]])], axis=1)
         self.aterm = np.array([self.fourier(dw, n) for n in range(1, self.na + 1)])                                # calcs.jl:66-72
@@ -178,6 +187,11 @@ class NpLdvm:
         self.a0prev = a0
         nprev = self.na if two else 3
         self.aprev[:nprev] = self.aterm[:nprev]
+        return self._tail(dt, t, ui, wi, delvort)
+
+    def _tail(self, dt, t, ui, wi, delvort):
+        """update_bv, controlVortCount, wakeroll, calc_forces and the mat row (common to all drivers)"""
+        a0, al, u, hd = self.a0, self.kin[0], self.kin[4], self.kin[3]
         n_ = np.arange(1, self.na + 1)
         gam = (a0 * (1 + np.cos(self.theta)) + (self.aterm[None, :] * np.sin(n_[None, :] * self.theta[:, None])
                                                  * np.sin(self.theta)[:, None]).sum(axis=1)) * self.uref * self.c     # calcs.jl:204-212
@@ -217,5 +231,73 @@ class NpLdvm:
         self.cl, self.cm = cl, cm
         return [t, al, self.kin[1], u, a0, cl, cd, cm]
 
-    def run(self, table, dt, delvort=None):
-        return np.array([self.step(dt, row, delvort) for row in table])
+    def step_lin(self, dt, row, delvort=None):
+        """one iteration of ldvmLin, solvers.jl:488-644: linearised closed-form shedding through the integrals
+        I1, J1 (downwash without this step's vortices), I2, J2 (unit TEV), I3, J3 (unit LEV)"""
+        t = row[0]
+        self.fs = [row[7], row[8]]
+        self.kin = list(row[1:7])
+        al, h, ald, hd, u, _ = self.kin
+        pc = self.pvt * self.c
+        self.bnd_x = self.bnd_x + dt * ((pc - self.x) * math.sin(al) * ald - u + self.cam * math.cos(al) * ald)
+        self.bnd_z = self.bnd_z + dt * (hd + (pc - self.x) * math.cos(al) * ald - self.cam * math.sin(al) * ald)
+        w = self.wake()
+        ui, wi = induce(w[0], w[1], w[2], w[3], self.bnd_x, self.bnd_z)                                            # :502
+        T1 = self.downwash(ui, wi)                                                                                 # :505-510
+        cm1 = np.cos(self.theta) - 1.0
+        I1 = self.c * trapz(T1 * cm1, self.theta)
+        J1 = -trapz(T1, self.theta) / (self.uref * math.pi)
+        tev, vc = self.fam[0], 0.02 * self.c
+        if tev.shape[1] == 0:                                                                                      # :515-523
+            xt, zt = self.bnd_x[-1] + 0.5 * u * dt, self.bnd_z[-1]
+        else:
+            xt = self.bnd_x[-1] + (tev[0, -1] - self.bnd_x[-1]) / 3.0
+            zt = self.bnd_z[-1] + (tev[1, -1] - self.bnd_z[-1]) / 3.0
+
+        def unit(xv, zv):                                                                                          # :525-530
+            xd, zd = self.bnd_x - xv, self.bnd_z - zv
+            dsq = xd * xd + zd * zd
+            return (self.cam_slope * zd + xd) / (2 * math.pi * np.sqrt(dsq ** 2 + vc ** 4))
+        T2 = unit(xt, zt)
+        sig_prev = -self.uref * self.c * math.pi * (self.a0prev + self.aprev[0] / 2.0)                             # :533
+        I2 = trapz(T2 * cm1, self.theta)
+        J2 = -trapz(T2, self.theta) / (math.pi * self.uref)
+        gt = -(I1 + sig_prev) / (1 + I2)                                                                           # :538
+        a0 = J1 + J2 * gt
+        c1 = np.array([trapz(T1 * np.cos(n * self.theta), self.theta) for n in range(1, self.na + 1)])
+        c2 = np.array([trapz(T2 * np.cos(n * self.theta), self.theta) for n in range(1, self.na + 1)])
+        self.aterm = 2.0 * (c1 + gt * c2) / (math.pi * self.uref)                                                  # :542-544
+        self.a0dot = (a0 - self.a0prev) / dt                                                                       # :547-550
+        self.adot = (self.aterm - self.aprev) / dt
+        if abs(a0) > self.lespcrit:                                                                                # :553
+            lesp = self.lespcrit if a0 >= 0.0 else -self.lespcrit
+            lev = self.fam[1]
+            if self.levflag == 0:
+                xl = self.bnd_x[0] + 0.5 * (u - ald * math.sin(al) * pc + ui[0]) * dt
+                zl = self.bnd_z[0] + 0.5 * (-ald * math.cos(al) * pc - hd + wi[0]) * dt
+            else:
+                xl = self.bnd_x[0] + (lev[0, -1] - self.bnd_x[0]) / 3.0
+                zl = self.bnd_z[0] + (lev[1, -1] - self.bnd_z[0]) / 3.0
+            T3 = unit(xl, zl)
+            I3 = trapz(T3 * cm1, self.theta)
+            J3 = -trapz(T3, self.theta) / (math.pi * self.uref)
+            det = J3 * (I2 + 1.0) - J2 * (I3 + 1.0)                                                                # :581-584
+            gt = (-J3 * (I1 + sig_prev) + (I3 + 1) * (J1 - lesp)) / det
+            gl = (J2 * (I1 + sig_prev) - (I2 + 1) * (J1 - lesp)) / det
+            a0 = J1 + J2 * gt + J3 * gl
+            c3 = np.array([trapz(T3 * np.cos(n * self.theta), self.theta) for n in range(1, self.na + 1)])
+            self.aterm = 2.0 * (c1 + gt * c2 + gl * c3) / (math.pi * self.uref)
+            self.fam[1] = np.concatenate([lev, np.array([[xl], [zl], [gl], [vc]])], axis=1)
+            self.levflag = 1
+        else:
+            self.levflag = 0
+        self.fam[0] = np.concatenate([tev, np.array([[xt], [zt], [gt], [vc]])], axis=1)
+        self.a0 = a0
+        self.a0prev = a0                                                                                           # :607-610
+        self.aprev[:3] = self.aterm[:3]
+        return self._tail(dt, t, ui, wi, delvort)
+
+    def run(self, table, dt, delvort=None, driver="ldvm"):
+        if driver == "ldvmLin":
+            return np.array([self.step_lin(dt, row, delvort) for row in table])
+        return np.array([self.step(dt, row, delvort, lautat=(driver == "lautat")) for row in table])

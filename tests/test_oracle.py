@@ -10,6 +10,7 @@ import math
 import os
 
 import numpy as np
+import pytest
 
 from cases import c1_surf, c1r_surf
 
@@ -218,3 +219,22 @@ def test_c_oracle_against_independent_numpy_restatement(oracle, uf):
     nm = npm.run(tab, 0.015, delvort=(30, 10.0, 1e-6))
     assert npm.fam[0].shape[1] == len(sim.get_vorts(0)["x"]) < n
     assert np.max(np.abs(cm - nm)) < 1e-10
+
+
+@pytest.mark.parametrize("driver", ["ldvmLin", "lautat"])
+def test_c_oracle_ldvmlin_and_lautat_against_numpy_restatement(oracle, uf, driver):
+    """the reference's only tested driver (ldvmLin, test/ldvmLinTest.jl) and lautat, C oracle vs the independent
+    numpy restatement: attached flow (config C1) and a LEV-shedding ramp (C1r)"""
+    from cases import c1_surf, c1r_surf
+    from oracle.np_restatement import NpLdvm
+    code = {"ldvmLin": oracle.DRIVER_LDVMLIN, "lautat": oracle.DRIVER_LAUTAT}[driver]
+    for mk, n in ((c1_surf, 150), (c1r_surf, 120)):
+        r = mk(uf)
+        surf, fld, dtstar = r[0], r[1], r[3]
+        tab = uf.kinematics_table(surf, fld, n, dtstar, external=(driver != "lautat"))
+        cm = oracle.Sim(surf, fld).run(code, tab, dtstar)
+        npm = NpLdvm(surf, fld)
+        nm = npm.run(tab, dtstar, driver=driver)
+        assert np.max(np.abs(cm - nm)) < 1e-10, (driver, mk.__name__, float(np.max(np.abs(cm - nm))))
+        if driver == "ldvmLin" and mk is c1r_surf:
+            assert npm.fam[1].shape[1] > 5
