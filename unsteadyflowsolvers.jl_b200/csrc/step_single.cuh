@@ -293,11 +293,14 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
             lev_shed = (!lautat && fabs(a0) > d.lespcrit) ? 1 : 0;   // solvers.jl:208
         }
         {
+            // scale every coefficient now (in place; thread 0 only reads the raw aterm[0]): without a LEV these
+            // are already the final values and the barrier of phase H is saved
             const int nrate = twodof ? na : 3;
-            for (int n = tid + 1; n <= nrate; n += blockDim.x) {
+            for (int n = tid + 1; n <= na; n += blockDim.x) {
                 const double an = 2. * aterm[n] / urefpi;
+                aterm[n] = an;
                 d.aterm[n - 1] = an;
-                d.adot[n - 1] = (an - d.aprev[n - 1]) / d.dt;     // calcs.jl:8-10 / :20-22
+                if (n <= nrate) d.adot[n - 1] = (an - d.aprev[n - 1]) / d.dt;     // calcs.jl:8-10 / :20-22
             }
         }
         __syncthreads();
@@ -385,10 +388,10 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
         if (lev_shed) {
             block_trapz_cos_all(dw, dth, costab, nd, na, aterm);
             __syncthreads();
+            if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
+            for (int n = tid + 1; n <= na; n += blockDim.x) d.aterm[n - 1] = aterm[n] = 2. * aterm[n] / urefpi;
+            __syncthreads();
         }
-        if (tid == 0) { sc[10] = -aterm[0] / urefpi; }
-        for (int n = tid + 1; n <= na; n += blockDim.x) d.aterm[n - 1] = aterm[n] = 2. * aterm[n] / urefpi;
-        __syncthreads();
     } else {
         // =========================== ldvmLin, solvers.jl:505-613 =================================
         double *T1 = dw, *T2 = dw1, *T3 = dw2;
