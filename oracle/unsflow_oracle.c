@@ -245,6 +245,7 @@ typedef struct {
     double t;
     double cl, cd, cm;   /* carried between steps by ldvm2DOF, solvers.jl:692-693,765 */
     long nfev;           /* functor evaluations (diagnostic) */
+    int lesp_force;      /* exact-root mode: LESP branch fixed to the sign of the A0 that triggered shedding (0 = per evaluation) */
 } o_sim;
 
 /* simpleTrapz, src/utils.jl:105-115 */
@@ -548,6 +549,7 @@ static void kelvinkutta_functor(o_sim *m, const double v_iter[2], double val[2])
     val[0] = s->uref * s->c * O_PI * (s->a0 + s->aterm[0] / 2.)
              - s->uref * s->c * O_PI * (s->a0prev + s->aprev[0] / 2.) + lt->s + ll->s;  /* :336-338 */
     double lesp_cond = (s->a0 > 0) ? s->lespcrit : -s->lespcrit;          /* :340-344 */
+    if (m->lesp_force) lesp_cond = m->lesp_force * s->lespcrit;          /* exact-root mode, see root_solve */
     val[1] = s->a0 - lesp_cond;                                           /* :345 */
 }
 
@@ -560,7 +562,11 @@ static void kelvinkutta_functor(o_sim *m, const double v_iter[2], double val[2])
  *      build the exact Jacobian by unit differences of the functor, take a Newton step,
  *      repeat until the step no longer changes the iterate, and finish with ONE functor
  *      evaluation at the root so the functor's side effects (uind, wind, downwash, a0, a1)
- *      correspond to the returned strengths.
+ *      correspond to the returned strengths.  The Kelvin-Kutta system has TWO self-consistent roots
+ *      (A0 = +LESPcrit and A0 = -LESPcrit, typedefs.jl:340-344 switches the target on the sign of A0 at
+ *      every evaluation); "exact" means the root on the branch of the A0 that triggered the shedding
+ *      (the drivers pin the sign through lesp_force for the duration of the solve).  Which root NLsolve
+ *      reaches depends on its iterates: that is mode 1.
  *
  *  mode 1 "nlsolve": restatement of NLsolve 4.x defaults as published -- method
  *      :trust_region (Powell dogleg, Nocedal & Wright alg. 4.1/11.5), factor = 1.0,
@@ -749,7 +755,9 @@ static void step_ldvm(o_sim *m, int two_dof, double dt, const double *row, int m
     if (fabs(lesp) > s->lespcrit) {                                      /* :208 */
         place_lev(s, f, dt);                                             /* :212 */
         double x2[2] = { -0.01, 0.01 };
+        m->lesp_force = (mode == 0) ? (lesp > 0 ? 1 : -1) : 0;
         root_solve(m, mode, fun2, 2, x2);                                /* :215-216 */
+        m->lesp_force = 0;
         f->tev.v[f->tev.n - 1].s = x2[0];                                /* :217 */
         f->lev.v[f->lev.n - 1].s = x2[1];
         s->levflag = 1;                                                  /* :220 */
@@ -1065,6 +1073,7 @@ typedef struct {
     long nfev;
     int shed[O_NMAX];   /* shed_ind (0-based surface indices) */
     int nshed;
+    int lesp_force[O_NMAX];   /* exact-root mode: per-surface LESP branch fixed to the triggering A0's sign (0 = per evaluation) */
 } o_msim;
 
 /* place_tev(surf::Vector{TwoDSurf}, field, dt), calcs.jl:389-406 */
@@ -1173,7 +1182,8 @@ static void mult_functor(o_msim *m, const double *v_iter, double *val, int with_
         if (with_lev && in_shed(m, i)) {
             val[i] = kelvin_val(s) + tevs + m->f.lev.v[m->f.lev.n - ns + i].s;
             levcount += 1;
-            const double lesp_cond = (s->a0 > 0) ? s->lespcrit : -s->lespcrit;
+            double lesp_cond = (s->a0 > 0) ? s->lespcrit : -s->lespcrit;
+            if (m->lesp_force[i]) lesp_cond = m->lesp_force[i] * s->lespcrit;
             val[levcount - 1 + ns] = s->a0 - lesp_cond;
         } else {
             val[i] = kelvin_val(s) + tevs;
@@ -1249,7 +1259,9 @@ static void step_ldvm_multi(o_msim *m, double dt, const double *kin, int mode,
     if (m->nshed > 0) {                                                  /* :365-390 */
         place_lev_multi(m, dt);
         for (int i = 0; i < ns + m->nshed; i++) x[i] = -0.01;            /* :372 */
+        for (int i = 0; i < ns; i++) m->lesp_force[i] = (mode == 0) ? (m->s[i].a0 > 0 ? 1 : -1) : 0;
         root_solve(m, mode, mfun2, ns + m->nshed, x);
+        for (int i = 0; i < ns; i++) m->lesp_force[i] = 0;
         /* strengths: the functor has already stored the iterate in the vortices; the driver's
          * own assignment block (:374-390) re-stores soln.zero for the index patterns it handles */
         int lc = 0;
