@@ -526,10 +526,12 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         // tables in shared memory when they fit beside the kernel's static arrays (default 70 x 35: 40 KB)
         const size_t tab_bytes = sizeof(double) * 2 * (size_t)(h->naterm + 1) * h->ndiv;
         const int in_smem = tab_bytes <= 160 * 1024;
-        static size_t attr_bytes = 0;      // the attribute only ever needs to grow
-        if (in_smem && tab_bytes > attr_bytes) {
+        static size_t attr_bytes[64] = {0};      // per device; the attribute only ever needs to grow
+        int dev = 0;
+        UF_CUDA(cudaGetDevice(&dev));
+        if (in_smem && tab_bytes > attr_bytes[dev & 63]) {
             UF_CUDA(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-            attr_bytes = tab_bytes;
+            attr_bytes[dev & 63] = tab_bytes;
         }
         k_step_solve<<<1, kSolveThreads, in_smem ? tab_bytes : 0, st>>>(h->dev, in_smem);
     }
