@@ -114,11 +114,13 @@ long long sym_threshold() {
 
 template <int R, int O>
 static int launch_sym_one(const SymArgs &a, int ctas, cudaStream_t st) {
-    static bool attr_set = false;
+    static bool attr_set[64] = {false};      // per device (a process may drive several through unsflow_set_device)
     const size_t smem = sym_smem_bytes(R);
-    if (!attr_set) {
+    int dev = 0;
+    UF_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
         UF_CUDA(cudaFuncSetAttribute(k_induce_sym<R, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     k_induce_sym<R, O><<<ctas, kThreads, smem, st>>>(a);
     UF_CUDA(cudaGetLastError());
