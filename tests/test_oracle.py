@@ -238,3 +238,28 @@ def test_c_oracle_ldvmlin_and_lautat_against_numpy_restatement(oracle, uf, drive
         assert np.max(np.abs(cm - nm)) < 1e-10, (driver, mk.__name__, float(np.max(np.abs(cm - nm))))
         if driver == "ldvmLin" and mk is c1r_surf:
             assert npm.fam[1].shape[1] > 5
+
+
+def test_exact_mode_two_root_step_found_by_the_fuzz_sweep(oracle, uf):
+    """tools/fuzz_ldvm.py, seed 7, case 196: at step 55 the Kelvin-Kutta system (LESP target switching on the sign of
+    A0, typedefs.jl:340-344) has two self-consistent roots and a Newton iteration started at [-0.01, 0.01] settles
+    on A0 = -LESPcrit although the shedding was triggered by A0 > +LESPcrit.  Exact-root mode is defined as the root on
+    the branch of the triggering A0: the C oracle (sign pinned during the solve) must agree with the independent
+    numpy restatement (closed form on that branch) through and past that step."""
+    import importlib.util
+    from oracle.np_restatement import NpLdvm
+    spec = importlib.util.spec_from_file_location("fuzz_ldvm", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_ldvm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(7)
+    for _ in range(197):
+        cs = mod.make_case(rng)
+    assert cs["driver"] == oracle.DRIVER_LDVM and cs["mode"] == 0 and isinstance(cs["delv"], uf.delSpalart)
+    om = mod.oracle_history(cs)
+    surf, fld, delv = cs["surf"], cs["fld"], cs["delv"]
+    dt = cs["dtstar"] * surf.c / surf.uref
+    tab = uf.kinematics_table(surf, fld, cs["nsteps"], dt)
+    nm = NpLdvm(surf, fld).run(tab, dt, delvort=(delv.limit, delv.dist, delv.tol))
+    a0 = om[:, 4]
+    assert np.any(np.abs(a0 - cs["lesp"]) < 1e-12) and np.any(np.abs(a0 + cs["lesp"]) < 1e-12)     # sheds on both branches
+    assert np.max(np.abs(om - nm)) < 1e-9
