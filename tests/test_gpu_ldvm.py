@@ -516,3 +516,22 @@ def test_randomised_configurations_against_oracle(gpu_lib, uf, oracle):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main(ncase=16, seed=7) == 0
+
+
+def test_nlsolve_mode_reproduces_the_branch_taken_by_the_trust_region_iteration(gpu_lib, uf, oracle):
+    """tools/fuzz_ldvm.py, seed 11, case 229 (ldvm2DOF, NLsolve mode): on the second step the emulated NLsolve iteration
+    settles on A0 = -LESPcrit although A0 > +LESPcrit triggered the shedding.  The device runs the same iteration
+    (nlsolve_dev.cuh), so it must follow -- a closed form on the triggering branch is off by 2 LESPcrit there."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_ldvm", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_ldvm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(11)
+    for _ in range(230):
+        cs = mod.make_case(rng)
+    assert cs["driver"] == oracle.DRIVER_LDVM2DOF and cs["mode"] == 1
+    om = mod.oracle_history(cs)
+    assert om[0, 4] > 0 and om[1, 4] < 0 and abs(abs(om[1, 4]) - cs["lesp"]) < 1e-4          # the branch flip
+    gm, _, _ = uf.ldvm2DOF(cs["surf"], cs["fld"], cs["strpar"], copy.deepcopy(cs["kin0"]), cs["nsteps"], cs["dtstar"], 0, 0, 1000.0,
+                           cs["delv"], write_summary=False, solve_mode=1)
+    assert np.max(np.abs(gm[:30] - om[:30])) < 1e-8
