@@ -255,6 +255,10 @@ int unsflow_bench_sweep(int64_t n, int ndiv, int reps, float *ms_sweep, float *m
 int unsflow_rsqrt_probe(int64_t nsamples, double qmin, double qmax, double *max_rel_seed,
                         double *max_rel_newton, double *max_rel_cubic);
 
+/* maximum relative error of ONE refinement variant over the same sweep, against a double-double truth:
+ * order 2 = bias-centred Newton (FAST), 3 = Halley in FP64, 4/5/6 = Halley with the e^2 term in FP32 */
+int unsflow_rsqrt_probe_order(int order, int64_t nsamples, double qmin, double qmax, double *max_rel);
+
 #ifdef __cplusplus
 }
 #endif

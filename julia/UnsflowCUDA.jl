@@ -144,7 +144,7 @@ function kinematics_table(surf::TwoDSurf, curfield::TwoDFlowField, nsteps, dt, t
 end
 
 function run_driver(driver::Integer, surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64, dtstar::Float64, startflag,
-                    writeflag, writeInterval, delvort; maxwrite = 50, nround = 6, solve_mode = 0, strpar = nothing, kinem = nothing)
+                    writeflag, writeInterval, delvort; maxwrite = 50, nround = 6, solve_mode = 1, strpar = nothing, kinem = nothing)
     startflag == 0 || throw("invalid start flag, should be 0 or 1")        # solvers.jl:157 (restart is broken upstream)
     t = 0.0
     dt = dtstar * surf.c / surf.uref                                       # solvers.jl:161
@@ -231,12 +231,12 @@ end
 
 "ldvm(surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite, nround)  replaces solvers.jl:144-268"
 ldvm(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0, writeflag = 0,
-     writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+     writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 1) =
     run_driver(0, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround, solve_mode = solve_mode)
 
 "ldvm2DOF(surf, curfield, strpar, kinem, ...)  replaces solvers.jl:657-788"
 ldvm2DOF(surf::TwoDSurf, curfield::TwoDFlowField, strpar::TwoDOFPar, kinem::KinemPar2DOF, nsteps::Int64 = 500, dtstar::Float64 = 0.015,
-         startflag = 0, writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+         startflag = 0, writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 1) =
     run_driver(1, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround,
                solve_mode = solve_mode, strpar = strpar, kinem = kinem)
 
@@ -247,7 +247,7 @@ ldvmLin(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Fl
 
 "lautat(...)  replaces solvers.jl:42-142 (wakerollup = 1)"
 lautat(surf::TwoDSurf, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0, writeflag = 0,
-       writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0) =
+       writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 1) =
     run_driver(3, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort; maxwrite = maxwrite, nround = nround, solve_mode = solve_mode)
 
 # ---- multi-surface ldvm(surf::Vector{TwoDSurf}, ...)  replaces solvers.jl:270-445 -------------------
@@ -261,7 +261,7 @@ function csurf(surf::TwoDSurf, bv::SoA)
 end
 
 function ldvm(surf::Vector{TwoDSurf}, curfield::TwoDFlowField, nsteps::Int64 = 500, dtstar::Float64 = 0.015, startflag = 0,
-              writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 0)
+              writeflag = 0, writeInterval = 1000., delvort = delNone(); maxwrite = 50, nround = 6, solve_mode = 1)
     startflag == 0 || throw("invalid start flag, should be 0 or 1")
     nsurf = length(surf)
     dt = dtstar * minimum(map(q -> q.c / q.uref, surf))                     # solvers.jl:289
@@ -390,7 +390,7 @@ function member_tables(surfs::Vector{TwoDSurf}, nsteps, dt; twodof = false)
     tabs
 end
 
-function ldvm_batch(surfs::Vector{TwoDSurf}, nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 0)
+function ldvm_batch(surfs::Vector{TwoDSurf}, nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 1)
     surf = surfs[1]; M = length(surfs); dt = dtstar * surf.c / surf.uref
     tabs = member_tables(surfs, nsteps, dt)
     lesp = [sf.lespcrit[1] for sf in surfs]
@@ -407,7 +407,7 @@ end
 
 # ldvm2DOF members: strpars[m]::TwoDOFPar, kinems[m]::KinemPar2DOF (mutated to the final state)
 function ldvm2DOF_batch(surfs::Vector{TwoDSurf}, strpars::Vector{TwoDOFPar}, kinems::Vector{KinemPar2DOF},
-                        nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 0)
+                        nsteps::Int64 = 500, dtstar::Float64 = 0.015, delvort = delNone(); solve_mode = 1)
     surf = surfs[1]; M = length(surfs); dt = dtstar * surf.c / surf.uref
     tabs = member_tables(surfs, nsteps, dt; twodof = true)
     lesp = [sf.lespcrit[1] for sf in surfs]

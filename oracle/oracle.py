@@ -144,6 +144,10 @@ def unpack_surf(p, nd, na):
 
 
 DRIVER_LDVM, DRIVER_LDVM2DOF, DRIVER_LDVMLIN, DRIVER_LAUTAT = 0, 1, 2, 3
+# shedding-solve mode: 0 = state at the exact root, 1 = restatement of the reference's NLsolve mechanics
+# (solvers.jl:199,216; the default, like the product's DEFAULT_SOLVE_MODE)
+SOLVER_EXACT, SOLVER_NLSOLVE = 0, 1
+DEFAULT_SOLVER_MODE = SOLVER_NLSOLVE
 
 
 class Sim:
@@ -214,7 +218,8 @@ class Sim:
     def set_forces(self, cl, cd, cm):
         lib().o_sim_set_forces(self.h, C.c_double(cl), C.c_double(cd), C.c_double(cm))
 
-    def run(self, driver, table, dt, solver_mode=0, delvort=(0, 0, 0.0, 0.0)):
+    def run(self, driver, table, dt, solver_mode=None, delvort=(0, 0, 0.0, 0.0)):
+        solver_mode = DEFAULT_SOLVER_MODE if solver_mode is None else solver_mode
         table = _f(table)
         n = table.shape[0]
         mat = np.zeros((n, 8))
@@ -275,8 +280,9 @@ class MultiSim:
         except Exception:
             pass
 
-    def run(self, tables, dt, solver_mode=0, delvort=(0, 0, 0.0, 0.0)):
+    def run(self, tables, dt, solver_mode=None, delvort=(0, 0, 0.0, 0.0)):
         """tables: nsteps x nsurf x 9"""
+        solver_mode = DEFAULT_SOLVER_MODE if solver_mode is None else solver_mode
         tables = _f(tables)
         n = tables.shape[0]
         mat = np.zeros((n, 1 + 7 * self.ns))

@@ -16,6 +16,9 @@ from cases import c1_surf, c1r_surf, c2_surf, c5_2dof
 pytestmark = pytest.mark.gpu
 HTOL = 1e-8
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# shedding-solve modes (include/unsflow.h UNSFLOW_SOLVE_*; same codes in the oracle): the reference-signature entry
+# points default to NLSOLVE (the reference's mechanics), EXACT is the opt-in -- the core histories are checked in both
+BOTH_MODES = pytest.mark.parametrize("mode", [0, 1], ids=["exact", "nlsolve"])
 
 
 def _oracle_run(oracle, uf, surf, fld, driver, nsteps, dtstar, **kw):
@@ -25,7 +28,7 @@ def _oracle_run(oracle, uf, surf, fld, driver, nsteps, dtstar, **kw):
     sim = oracle.Sim(surf, fld)
     if "twodof" in kw:
         sim.set_2dof(kw["twodof"][0].as_array(), kw["twodof"][1].as_array())
-    mat = sim.run(driver, tab, dt, solver_mode=kw.get("solver_mode", 0), delvort=kw.get("delvort", (0, 0, 0.0, 0.0)))
+    mat = sim.run(driver, tab, dt, solver_mode=kw.get("solver_mode", None), delvort=kw.get("delvort", (0, 0, 0.0, 0.0)))
     return mat, sim
 
 
@@ -45,19 +48,20 @@ def _cmp_state(surf, fld, sim, tol=1e-9):
             assert np.all(v.vc == o["vc"])
 
 
-def test_c1_ldvm_history_and_final_state(gpu_lib, uf, oracle, tmp_path, monkeypatch):
+@BOTH_MODES
+def test_c1_ldvm_history_and_final_state(gpu_lib, uf, oracle, tmp_path, monkeypatch, mode):
     """config C1 = test/ldvmLinTest.jl through ldvm: 468 steps, N -> 468, attached flow"""
     monkeypatch.chdir(tmp_path)
     surf, fld, nsteps, dtstar = c1_surf(uf)
-    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, nsteps, dtstar)
-    mat, surf, fld = uf.ldvm(surf, fld, nsteps, dtstar, 0, 0, 0.7, uf.delNone())
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, nsteps, dtstar, solver_mode=mode)
+    mat, surf, fld = uf.ldvm(surf, fld, nsteps, dtstar, 0, 0, 0.7, uf.delNone(), solve_mode=mode)
     assert mat.shape == (nsteps, 8)
     assert np.max(np.abs(mat - omat)) <= HTOL
     _cmp_state(surf, fld, sim)
     # the reference's own assertion (test/ldvmLinTest.jl:33-36)
     assert abs(2 * math.pi * 5 * math.pi / 180 - mat[-1, 5]) < 0.5 * 2 * math.pi * 5 * math.pi / 180
     gold = json.load(open(os.path.join(GOLD, "c1_ldvm_probe.json")))
-    for row in gold["rows"]:
+    for row in gold["rows"] if mode == 0 else []:      # the probe values are exact-root ones
         assert abs(mat[row["step"] - 1, 5] - row["cl"]) <= HTOL and abs(mat[row["step"] - 1, 7] - row["cm"]) <= HTOL
     # resultsSummary written like solvers.jl:261-264
     txt = open("resultsSummary").read().splitlines()
@@ -73,11 +77,12 @@ def test_c1_ldvmlin_and_lautat(gpu_lib, uf, oracle):
         _cmp_state(surf, fld, sim)
 
 
-def test_c1r_lev_shedding_free_running_150_steps(gpu_lib, uf, oracle):
+@BOTH_MODES
+def test_c1r_lev_shedding_free_running_150_steps(gpu_lib, uf, oracle, mode):
     surf, fld, _, dtstar = c1r_surf(uf)
     n = 150
-    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
-    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar, solver_mode=mode)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False, solve_mode=mode)
     assert len(fld.lev) > 10
     assert np.max(np.abs(mat - omat)) <= HTOL
     _cmp_state(surf, fld, sim, tol=1e-8)
@@ -90,7 +95,7 @@ def test_c1r_teacher_forced_late_steps(gpu_lib, uf, oracle):
     k0, m = 300, 5
     tab = uf.kinematics_table(surf, fld, k0 + m, dt)
     sim = oracle.Sim(surf, fld)
-    sim.run(oracle.DRIVER_LDVM, tab[:k0], dt)
+    sim.run(oracle.DRIVER_LDVM, tab[:k0], dt, solver_mode=oracle.SOLVER_EXACT)
     # transplant the oracle state into host-mirror objects
     s = sim.get_surf()
     for name in ("bnd_x", "bnd_z", "uind", "wind", "downwash", "aterm", "adot", "aprev"):
@@ -102,7 +107,7 @@ def test_c1r_teacher_forced_late_steps(gpu_lib, uf, oracle):
     for fam, v in enumerate((fld.tev, fld.lev, fld.extv)):
         o = sim.get_vorts(fam)
         v.assign(o["x"], o["z"], o["s"], o["vc"], o["vx"], o["vz"])
-    omat = sim.run(oracle.DRIVER_LDVM, tab[k0:], dt)
+    omat = sim.run(oracle.DRIVER_LDVM, tab[k0:], dt, solver_mode=oracle.SOLVER_EXACT)
     cabi = uf._cabi
     from unsflow_b200.solvers import LdvmHandle, _opts
     h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dt, m, uf.delNone(), cabi.SOLVE_EXACT))
@@ -124,11 +129,12 @@ def test_nlsolve_emulation_mode(gpu_lib, uf, oracle):
     assert np.max(np.abs(mat - omat)) <= 1e-7     # the emulated trust region stops at ftol = 1e-8
 
 
-def test_c2_pitch_plunge(gpu_lib, uf, oracle):
+@BOTH_MODES
+def test_c2_pitch_plunge(gpu_lib, uf, oracle, mode):
     surf, fld, dtstar = c2_surf(uf)
     n = 100
-    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
-    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar, solver_mode=mode)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False, solve_mode=mode)
     assert np.max(np.abs(mat - omat)) <= HTOL
     _cmp_state(surf, fld, sim, tol=1e-7)      # LEV shedding: round-off grows
 
@@ -491,19 +497,20 @@ def test_error_paths_on_device(gpu_lib, uf):
         uf.ldvm([a, b], uf.TwoDFlowField(), 2, dtstar, write_summary=False)
 
 
-def test_500_step_attached_history(gpu_lib, uf, oracle):
+@BOTH_MODES
+def test_500_step_attached_history(gpu_lib, uf, oracle, mode):
     """north_star criterion verbatim: Cl/Cd/Cm histories <= 1e-8 over the first 500 steps (attached
     flow: pitch-plunge below the LESP threshold, so round-off does not amplify)"""
     kin = uf.KinemDef(uf.SinDef(2 * math.pi / 180, 4 * math.pi / 180, 0.3, 0.0), uf.CosDef(0.0, 0.05, 0.3, 0.0), uf.ConstDef(1.0))
     surf = uf.TwoDSurf("FlatPlate", 0.3, kin, [5.0])
     fld = uf.TwoDFlowField()
     n, dtstar = 500, 0.015
-    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
-    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar, solver_mode=mode)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False, solve_mode=mode)
     assert len(fld.lev) == 0 and len(fld.tev) == n
     err = np.max(np.abs(mat[:, 5:8] - omat[:, 5:8]))
     assert err <= HTOL, err
-    assert err < 1e-11            # in practice round-off level
+    assert mode == 1 or err < 1e-11            # in practice round-off level
     _cmp_state(surf, fld, sim)
 
 

@@ -59,7 +59,7 @@ def test_reference_ldvmlin_test_bound(oracle, uf):
     cl_expected = 2 * math.pi * 5.0 * math.pi / 180
     assert abs(cl_expected - mat[-1, 5]) < 0.5 * cl_expected
     # ldvm (exact mode) agrees with the closed-form linearised solver to ~1e-5 at t* = 7
-    mat2 = oracle.Sim(surf, fld).run(oracle.DRIVER_LDVM, tab, dtstar)
+    mat2 = oracle.Sim(surf, fld).run(oracle.DRIVER_LDVM, tab, dtstar, solver_mode=oracle.SOLVER_EXACT)
     assert abs(mat2[-1, 5] - mat[-1, 5]) < 2e-5
     assert abs(mat2[0, 5] - mat[0, 5]) / mat[0, 5] < 2e-3
 
@@ -69,7 +69,7 @@ def test_golden_c1_probe(oracle, uf):
     surf, fld, nsteps, dtstar = c1_surf(uf)
     tab = uf.kinematics_table(surf, fld, nsteps, dtstar)
     sim = oracle.Sim(surf, fld)
-    mat = sim.run(oracle.DRIVER_LDVM, tab, dtstar)
+    mat = sim.run(oracle.DRIVER_LDVM, tab, dtstar, solver_mode=oracle.SOLVER_EXACT)   # the probe values are exact-root ones
     for row in gold["rows"]:
         k = row["step"] - 1
         got = mat[k]
@@ -89,7 +89,7 @@ def test_kelvin_invariant(oracle, uf):
     tab = uf.kinematics_table(surf, fld, 200, dtstar)
     sim = oracle.Sim(surf, fld)
     for k in range(0, 200, 40):
-        sim.run(oracle.DRIVER_LDVM, tab[k:k + 40], dtstar)
+        sim.run(oracle.DRIVER_LDVM, tab[k:k + 40], dtstar, solver_mode=oracle.SOLVER_EXACT)   # the identities hold at the root
         s = sim.get_surf()
         tot = sim.get_vorts(0)["s"].sum() + sim.get_vorts(1)["s"].sum()
         assert abs(tot + s["uref"] * s["c"] * math.pi * (s["a0"] + s["aterm"][0] / 2)) < 1e-12
@@ -150,13 +150,13 @@ def test_multi_surface_oracle_consistency(oracle, uf):
         return uf.TwoDSurf("FlatPlate", 0.25, kin, [lesp], initpos=(x0, 0.0))
     fld, dt = uf.TwoDFlowField(), 0.012
     tab1 = uf.kinematics_table(mk(0.0, 0.0, 0.12), fld, 30, dt)
-    m1 = oracle.MultiSim([mk(0.0, 0.0, 0.12)], fld).run(tab1[:, None, :], dt)
-    ms = oracle.Sim(mk(0.0, 0.0, 0.12), fld).run(oracle.DRIVER_LDVM, tab1, dt)
+    m1 = oracle.MultiSim([mk(0.0, 0.0, 0.12)], fld).run(tab1[:, None, :], dt, solver_mode=oracle.SOLVER_EXACT)
+    ms = oracle.Sim(mk(0.0, 0.0, 0.12), fld).run(oracle.DRIVER_LDVM, tab1, dt, solver_mode=oracle.SOLVER_EXACT)
     assert np.max(np.abs(m1 - ms)) < 1e-12
     surfs = [mk(0.0, 0.0, 0.12), mk(1.5, 1.0, 0.2)]
     tabs = np.stack([uf.kinematics_table(s, fld, 120, dt) for s in surfs], axis=1)
     sim = oracle.MultiSim(surfs, fld)
-    mat = sim.run(tabs, dt)
+    mat = sim.run(tabs, dt, solver_mode=oracle.SOLVER_EXACT)
     lev = sim.get_vorts(1)
     assert np.all(np.isfinite(mat)) and np.sum(lev["vc"] == 0) > 0 and np.sum(lev["vc"] > 0) > 0
     assert len(sim.get_vorts(0)["x"]) == 240
@@ -200,7 +200,7 @@ def test_c_oracle_against_independent_numpy_restatement(oracle, uf):
     surf, fld, _, dtstar = c1r_surf(uf)
     n = 110
     tab = uf.kinematics_table(surf, fld, n, dtstar)
-    cm = oracle.Sim(surf, fld).run(oracle.DRIVER_LDVM, tab, dtstar)
+    cm = oracle.Sim(surf, fld).run(oracle.DRIVER_LDVM, tab, dtstar, solver_mode=oracle.SOLVER_EXACT)   # the numpy restatement solves in closed form
     npm = NpLdvm(surf, fld)
     nm = npm.run(tab, dtstar)
     assert npm.fam[1].shape[1] > 5                      # LEVs were shed
@@ -211,7 +211,7 @@ def test_c_oracle_against_independent_numpy_restatement(oracle, uf):
     tab = uf.kinematics_table(surf, fld, n, 0.015, two_dof=True)
     sim = oracle.Sim(surf, fld)
     sim.set_2dof(strpar.as_array(), kin0.as_array())
-    cm = sim.run(oracle.DRIVER_LDVM2DOF, tab, 0.015, delvort=(1, 30, 10.0, 1e-6))
+    cm = sim.run(oracle.DRIVER_LDVM2DOF, tab, 0.015, solver_mode=oracle.SOLVER_EXACT, delvort=(1, 30, 10.0, 1e-6))
     npm = NpLdvm(surf, fld)
     npm.k2 = {k: getattr(kin0, k) for k in kin0.FIELDS}
     npm.sp = dict(zip(("x_alpha", "r_alpha", "kappa", "w_alpha", "w_h", "w_alphadot", "w_hdot", "cubic_h_1", "cubic_h_3",
@@ -232,7 +232,7 @@ def test_c_oracle_ldvmlin_and_lautat_against_numpy_restatement(oracle, uf, drive
         r = mk(uf)
         surf, fld, dtstar = r[0], r[1], r[3]
         tab = uf.kinematics_table(surf, fld, n, dtstar, external=(driver != "lautat"))
-        cm = oracle.Sim(surf, fld).run(code, tab, dtstar)
+        cm = oracle.Sim(surf, fld).run(code, tab, dtstar, solver_mode=oracle.SOLVER_EXACT)
         npm = NpLdvm(surf, fld)
         nm = npm.run(tab, dtstar, driver=driver)
         assert np.max(np.abs(cm - nm)) < 1e-10, (driver, mk.__name__, float(np.max(np.abs(cm - nm))))

@@ -121,6 +121,7 @@ def lib():
         "unsflow_bench_sweep": [i64, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)],
         "unsflow_fp64_peak": [d, d],
         "unsflow_rsqrt_probe": [i64, C.c_double, C.c_double, d, d, d],
+        "unsflow_rsqrt_probe_order": [C.c_int, i64, C.c_double, C.c_double, d],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)

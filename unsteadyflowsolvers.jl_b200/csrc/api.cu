@@ -39,7 +39,7 @@ int rsqrt_order() {
     static int order = [] {
         const char *e = getenv("UNSFLOW_RSQRT_ORDER");
         int o = e ? atoi(e) : 3;
-        return (o == 2) ? 2 : 3;
+        return (o == 2 || (o >= 4 && o <= 6)) ? o : 3;
     }();
     return order;
 }
@@ -148,7 +148,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     // few targets against many sources (update_indbound): dedicated sweep kernel
     const bool sweep = !sym && !self_targets && nt <= 256 && ns >= 2048 && sweep_supported((int)nt);
     if (sweep) plan.S = (int)std::max<int64_t>(1, std::min<int64_t>((ns + kTS - 1) / kTS + ng, 256));
-    const int64_t npart = sym ? (int64_t)ctas * 2 * tot : 2 * (int64_t)plan.S * ntp;
+    const int64_t npart = sym ? sym_plane_doubles(ctas, tot) : 2 * (int64_t)plan.S * ntp;
     if (d_part.ensure(npart)) return 2;
     if (d_out.ensure(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
 
@@ -161,7 +161,6 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     a.pu = d_part.p; a.pw = d_part.p + (int64_t)plan.S * ntp;
     a.tstride = ntp;
     if (sym) {
-        UF_CUDA(cudaMemsetAsync(d_part.p, 0, sizeof(double) * (size_t)npart, st));
         SymArgs sa;
         sa.x = a.sx; sa.z = a.sz; sa.g = a.sg;
         sa.reg = d_reg.p; sa.nreg = 1; sa.bv_reg = ng > 1 ? 1 : -1;
@@ -176,7 +175,6 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     FinishArgs f;
     memset(&f, 0, sizeof(f));
     f.pu = a.pu; f.pw = a.pw; f.tstride = ntp; f.S = plan.S;
-    if (sym) { f.pu = d_part.p; f.pw = d_part.p + tot; f.tstride = 2 * tot; f.S = ctas; }
     f.treg = d_reg.p + 1; f.ntreg = 1;
     f.vx = d_out.p; f.vz = d_out.p + ntp;
     f.fs = nullptr; f.fs_u = fs_u; f.fs_w = fs_w;
@@ -191,7 +189,18 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
         UF_CUDA(cudaMemcpyAsync(f.x, d_tx, sizeof(double) * nt, cudaMemcpyDeviceToDevice, st));
         UF_CUDA(cudaMemcpyAsync(f.z, d_tz, sizeof(double) * nt, cudaMemcpyDeviceToDevice, st));
     }
-    if (int rc = launch_induce_finish(f, nt, st)) return rc;
+    if (sym) {
+        // targets = source group 0 = [0, nt) in slab indexing, so the outputs can be indexed the same way
+        SymFinishArgs sf;
+        memset(&sf, 0, sizeof(sf));
+        sf.P = d_part.p; sf.n = tot; sf.ctas = ctas; sf.R = symR;
+        sf.reg = d_reg.p; sf.nreg = 1;
+        sf.vx = f.vx; sf.vz = f.vz; sf.x = f.x; sf.z = f.z;
+        sf.fs_u = fs_u; sf.fs_w = fs_w; sf.dt = f.dt; sf.accumulate = accumulate;
+        if (int rc = launch_sym_finish(sf, nt, st)) return rc;
+    } else {
+        if (int rc = launch_induce_finish(f, nt, st)) return rc;
+    }
     if (nt > 0) {
         UF_CUDA(cudaMemcpyAsync(u_inout, f.vx, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
         UF_CUDA(cudaMemcpyAsync(w_inout, f.vz, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
@@ -240,6 +249,21 @@ __global__ void k_rsqrt_probe(long long n, double lqmin, double lqstep, double *
     atomic_max_pos(&mx[0], e0);
     atomic_max_pos(&mx[1], e2);
     atomic_max_pos(&mx[2], e3);
+}
+
+template <int ORDER>
+__global__ void k_rsqrt_probe_order(long long n, double lqmin, double lqstep, double *mx) {
+    double e = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double q = exp(lqmin + lqstep * (double)i);
+        // truth in double-double: one Newton correction of the IEEE value with an exact residual
+        const double t0 = 1.0 / sqrt(q);
+        const double r = fma(-q * t0, t0, 1.0) - fma(q, t0, -(q * t0)) * t0;     // 1 - q t0^2 to ~1e-32
+        const double truth_corr = 0.5 * t0 * r;                                     // truth = t0 + truth_corr
+        const double y = rsqrt_full<ORDER>(q);
+        e = fmax(e, fabs((y - t0) - truth_corr) / t0);
+    }
+    atomic_max_pos(&mx[0], e);
 }
 
 }  // namespace unsflow
@@ -434,6 +458,27 @@ int unsflow_rsqrt_probe(int64_t nsamples, double qmin, double qmax, double *e_se
     if (e_seed) *e_seed = h[0];
     if (e_newton) *e_newton = h[1];
     if (e_cubic) *e_cubic = h[2];
+    return 0;
+}
+
+int unsflow_rsqrt_probe_order(int order, int64_t nsamples, double qmin, double qmax, double *max_rel) {
+    UF_CHECK(nsamples > 1 && qmin > 0 && qmax > qmin && max_rel, "unsflow_rsqrt_probe_order: bad arguments");
+    UF_CHECK(order >= 2 && order <= 6, "unsflow_rsqrt_probe_order: order must be in [2, 6]");
+    if (int rc = require_device()) return rc;
+    DevBuf<double> mx;
+    if (mx.alloc(1)) return 2;
+    UF_CUDA(cudaMemset(mx.p, 0, sizeof(double)));
+    const double l0 = log(qmin), step = (log(qmax) - l0) / (double)(nsamples - 1);
+    const int grid = sm_count() * 4;
+    switch (order) {
+        case 2: k_rsqrt_probe_order<2><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        case 3: k_rsqrt_probe_order<3><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        case 4: k_rsqrt_probe_order<4><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        case 5: k_rsqrt_probe_order<5><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        default: k_rsqrt_probe_order<6><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+    }
+    UF_CUDA(cudaGetLastError());
+    UF_CUDA(cudaMemcpy(max_rel, mx.p, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -70,6 +70,33 @@ __device__ __forceinline__ double rsqrt_full(double q) {
         const double s = q * y0;
         const double c = fma(s, yh, 1.5 + 6.4e-13);
         return y0 * c;
+    } else if (ORDER == 4 || ORDER == 5 || ORDER == 6) {
+        // Halley step with its second-order term in FP32: y = y0*(1 + e/2 + 3e^2/8).  |e| <= 2e-6, so
+        // 3e^2/8 <= 1.5e-12 needs a relative accuracy of only ~1e-4 to stay below 1e-16 of y: e is rounded
+        // to float (or its top 20 mantissa bits are re-packed as a float by integer ops), squared and
+        // scaled on the FP32 pipe and widened again -- 4 FP64-pipe instructions instead of 5, same
+        // 2.7e-16 accuracy class as ORDER 3 (unsflow_rsqrt_probe reports all of them).
+        const double s = q * y0;
+        const double e = fma(-s, y0, 1.0);
+        float ef;
+        if (ORDER == 4) {
+            ef = __double2float_rn(e);                                   // F2F.F32.F64
+        } else {
+            // |e| as a float from the high word: rebias the exponent (1023 -> 127), keep 20 mantissa bits;
+            // |e| < 2^-126 is clamped to 0 (its square is irrelevant)
+            const int a = max(__double2hiint(e) & 0x7fffffff, 0x38100000);
+            ef = __int_as_float((a - 0x38000000) << 3);
+        }
+        const float e2f = (ef * ef) * 0.375f;
+        double e2;
+        if (ORDER == 6) {
+            // float -> double by integer ops (e2f >= 0; 0 maps to 2^-896, harmless)
+            e2 = __hiloint2double((int)((unsigned)__float_as_int(e2f) >> 3) + 0x38000000, 0);
+        } else {
+            e2 = (double)e2f;                                            // F2F.F64.F32
+        }
+        const double pe = fma(e, 0.5, e2);
+        return fma(y0, pe, y0);
     } else {
         const double s = q * y0;
         const double e = fma(-s, y0, 1.0);

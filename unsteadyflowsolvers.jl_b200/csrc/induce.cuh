@@ -52,10 +52,10 @@ struct FinishArgs {
     double *x, *z;          // positions to convect (may be null)
     const double *fs;       // device pointer to (u_inf, w_inf) or null
     double fs_u, fs_w;      // by-value free stream (added when fs == null)
-    const double *dtp;      // unused (reserved)
     double dt;              // 0 -> no convection
     int accumulate;         // 1: vx += result (mutual_ind semantics)
     int raw;                // 1: store the plain plane sum only (no 1/2pi, free stream, convection)
+    int packed;             // 1: the partials are indexed by the live-target ordinal (regions back to back), not by slab index
 };
 
 
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) k_induce_direct(const InduceArgs a) 
 __global__ void __launch_bounds__(256) k_induce_finish(const FinishArgs a) {
     const Regions treg = *a.treg;
     long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ord = lin;
     long long i = -1;
     for (int r = 0; r < a.ntreg; r++) {
         const long long n = treg.end[r] > treg.begin[r] ? treg.end[r] - treg.begin[r] : 0;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(256) k_induce_finish(const FinishArgs a) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const bool ok = s + k < a.S;
-            bu[k] = ok ? a.pu[(long long)(s + k) * a.tstride + i] : 0.0;
-            bw[k] = ok ? a.pw[(long long)(s + k) * a.tstride + i] : 0.0;
+            bu[k] = ok ? a.pu[(long long)(s + k) * a.tstride + (a.packed ? ord : i)] : 0.0;
+            bw[k] = ok ? a.pw[(long long)(s + k) * a.tstride + (a.packed ? ord : i)] : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < 16; k++) { su += bu[k]; sw += bw[k]; }

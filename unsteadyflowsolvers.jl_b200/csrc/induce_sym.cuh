@@ -19,8 +19,10 @@
 //   * per pair: 16 FP64-pipe instructions for 2 interactions (+2 per R pairs for the
 //     shared-memory accumulator) = 8.25 per interaction instead of 13;
 //   * diagonal tiles (I == J) and the bound-vortex sources are one-sided (13 per interaction);
-//   * every CTA accumulates into its own partial plane P[c][2][n]; k_induce_finish adds the
-//     planes in a fixed order -> bit-reproducible, no floating-point atomics.
+//   * every CTA accumulates into its own partial plane P[c][2][n]; it first zeroes the blocks of that
+//     plane it is going to touch and records them (SymTouch: two ranges of block indices), so that
+//     k_sym_finish adds, in a fixed order, only the planes that hold something for a given block --
+//     bit-reproducible, no floating-point atomics, no whole-plane memset / read.
 #pragma once
 #include "induce.cuh"
 
@@ -36,9 +38,35 @@ struct SymArgs {
     int nreg;
     int bv_reg;                  // index of the bound-vortex region in *reg (one-sided sources) or -1
     double vc4;
-    double *P;                   // [C][2][n] partial planes (pu then pw per CTA)
+    double *P;                   // [C][2][n] partial planes (pu then pw per CTA), then C SymTouch records
     long long n;                 // plane length
     int rank, nranks;            // split of the tile list over GPUs
+};
+
+// blocks (indices into the list of TB-wide blocks of the live regions) whose plane entries CTA c wrote:
+// [a0, a1) U [b0, b1); everything else in its plane is stale and must not be read
+struct SymTouch {
+    long long a0, a1, b0, b1;
+};
+// doubles to allocate for `ctas` planes of length n plus the touch records
+inline long long sym_plane_doubles(int ctas, long long n) { return (long long)ctas * 2 * n + (long long)ctas * (long long)(sizeof(SymTouch) / sizeof(double)); }
+
+// sum of the planes that touched each block + 1/2pi, free stream, convection (or the raw sum)
+struct SymFinishArgs {
+    const double *P;             // planes + touch records written by k_induce_sym
+    long long n;                 // plane length
+    int ctas, R;                 // number of planes, rows per thread of the launch that wrote them
+    const Regions *reg;          // same regions / nreg as the SymArgs
+    int nreg;
+    double *vx, *vz;             // outputs (absolute indexing, or packed when `packed`)
+    double *x, *z;               // positions to convect (may be null)
+    const double *fs;            // device pointer to (u_inf, w_inf) or null
+    double fs_u, fs_w;
+    double dt;                   // 0 -> no convection
+    int accumulate;              // 1: vx += result (mutual_ind semantics)
+    int raw;                     // 1: store the plain plane sum only
+    int packed;                  // raw only: outputs indexed by the live-target ordinal (regions back to back), vz at vx + packed_stride
+    long long packed_stride;
 };
 
 // contiguous share [begin, end) of `total` work items owned by `part` of `nparts` (ranks, then CTAs)
@@ -56,6 +84,7 @@ long long sym_threshold();                               // free vortices from w
 int sym_ctas(int R);                    // persistent CTAs = resident CTAs per SM x SMs (= number of partial planes)
 int sym_ctas_max();
 int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st);
+int launch_sym_finish(const SymFinishArgs &a, long long ntargets_ub, cudaStream_t st);
 
 #if defined(__CUDACC__) && defined(UNSFLOW_INDUCE_KERNELS)
 
@@ -88,7 +117,19 @@ __device__ __forceinline__ int sym_block_live(const Regions &rg, int nreg, long 
 // row-major upper triangle incl. diagonal: row I starts at I*nb - I*(I-1)/2
 __device__ __forceinline__ long long sym_row_offset(long long I, long long nb) { return I * nb - I * (I - 1) / 2; }
 
-template <int R, int ORDER>
+// VAR (experiments, bit mask): 1 = two partial chains per column accumulator, 2 = step loop unrolled by two
+// (I, J) of tile t in the row-major upper-triangle list of nb blocks
+__device__ __forceinline__ void sym_tile_coords(long long t, long long nb, long long *Io, long long *Jo) {
+    long long I = (long long)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
+    if (I < 0) I = 0;
+    if (I > nb - 1) I = nb - 1;
+    while (I > 0 && sym_row_offset(I, nb) > t) I--;
+    while (I + 1 < nb && sym_row_offset(I + 1, nb) <= t) I++;
+    *Io = I;
+    *Jo = I + (t - sym_row_offset(I, nb));
+}
+
+template <int R, int ORDER, int VAR = 0>
 __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_induce_sym(const SymArgs a) {
     constexpr int TB = kThreads * R, kChunk = TB / (kThreads / 32);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -106,18 +147,36 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
     split_range(W * kSymSub, a.rank, a.nranks, &r0, &r1);
     split_range(r1 - r0, blockIdx.x, gridDim.x, &c0, &c1);
     const long long u0 = r0 + c0, u1 = r0 + c1;
-    if (u0 >= u1) return;
+    SymTouch *touch = reinterpret_cast<SymTouch *>(a.P + (long long)gridDim.x * 2 * a.n) + blockIdx.x;
+    if (u0 >= u1) {
+        if (tid == 0) *touch = SymTouch{0, 0, 0, 0};
+        return;
+    }
     const long long t0 = u0 / kSymSub, t1 = (u1 + kSymSub - 1) / kSymSub;
 
-    // (I, J) of tile t0
-    long long I = (long long)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t0)) * 0.5);
-    if (I < 0) I = 0;
-    while (I > 0 && sym_row_offset(I, nb) > t0) I--;
-    while (I + 1 < nb && sym_row_offset(I + 1, nb) <= t0) I++;
-    long long J = I + (t0 - sym_row_offset(I, nb));
+    long long I, J, I1, J1;
+    sym_tile_coords(t0, nb, &I, &J);
+    sym_tile_coords(t1 - 1, nb, &I1, &J1);
 
     double *Pu = a.P + (long long)blockIdx.x * 2 * a.n;
     double *Pw = Pu + a.n;
+    {
+        // blocks this CTA will write: one row -> that row block and its column range; several rows -> every
+        // block from the first row on.  Zero them (the planes are never memset as a whole) and publish the ranges.
+        SymTouch tc;
+        if (I1 > I) tc = SymTouch{I, nb, 0, 0};
+        else tc = SymTouch{I, I + 1, J, J1 + 1};
+        if (tid == 0) *touch = tc;
+        for (int part = 0; part < 2; part++) {
+            const long long kb = part ? tc.b0 : tc.a0, ke = part ? tc.b1 : tc.a1;
+            for (long long k = kb; k < ke; k++) {
+                if (part && k >= tc.a0 && k < tc.a1) continue;
+                const long long e0 = sym_block_start<TB>(reg, a.nreg, k);
+                double2 *pu2 = reinterpret_cast<double2 *>(Pu + e0), *pw2 = reinterpret_cast<double2 *>(Pw + e0);
+                for (int c = tid; c < TB / 2; c += kThreads) { pu2[c] = make_double2(0.0, 0.0); pw2[c] = make_double2(0.0, 0.0); }
+            }
+        }
+    }
 
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
@@ -274,11 +333,11 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                 // accumulator read-modify-write of step s (column data is read-only in a tile)
                 int j = base + ((sb + lane) & (kChunk - 1));
                 double xj = sx[j], zj = sz[j], gj = sg[j];
-#pragma unroll 1
+#pragma unroll(VAR & 2 ? 2 : 1)
                 for (int s = sb; s < se; s++) {
                     const int jn = base + ((s + 1 + lane) & (kChunk - 1));
                     const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
-                    double cu = 0.0, cw = 0.0;
+                    double cu = 0.0, cw = 0.0, cu2 = 0.0, cw2 = 0.0;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const double dx = xj - tx[r], dz = zj - tz[r];
@@ -287,10 +346,16 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                         const double t1v = y * dz, t2v = y * dx;
                         u[r] = fma(-gj, t1v, u[r]);
                         w[r] = fma(gj, t2v, w[r]);
-                        cu = fma(tg[r], t1v, cu);
-                        cw = fma(-tg[r], t2v, cw);
+                        if ((VAR & 1) && (r & 1)) {
+                            cu2 = fma(tg[r], t1v, cu2);
+                            cw2 = fma(-tg[r], t2v, cw2);
+                        } else {
+                            cu = fma(tg[r], t1v, cu);
+                            cw = fma(-tg[r], t2v, cw);
+                        }
                     }
                     double2 acc = s_acc[j];
+                    if (VAR & 1) { cu += cu2; cw += cw2; }
                     acc.x += cu;
                     acc.y += cw;
                     s_acc[j] = acc;
@@ -331,6 +396,87 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             Pu[i] += u[r];
             Pw[i] += w[r];
         }
+    }
+}
+
+// One CTA = kThreads consecutive entries of one block.  The planes that touched the block are found from the
+// SymTouch records (ballot per warp -> ordered list in shared memory) and added in ascending plane order.
+template <int R>
+__global__ void __launch_bounds__(kThreads) k_sym_finish(const SymFinishArgs a) {
+    constexpr int TB = kThreads * R;
+    __shared__ unsigned s_mask[16];      // up to 512 planes
+    __shared__ short s_list[512];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Regions reg = *a.reg;
+    const long long X = blockIdx.x / R;
+    long long nb = 0;
+    for (int r = 0; r < a.nreg; r++) nb += sym_blocks_in<TB>(reg.begin[r], reg.end[r]);
+    if (X >= nb) return;
+    const SymTouch *touch = reinterpret_cast<const SymTouch *>(a.P + (long long)a.ctas * 2 * a.n);
+    for (int c0 = warp * 32; c0 < a.ctas; c0 += kThreads) {
+        const int c = c0 + lane;
+        bool in = false;
+        if (c < a.ctas) {
+            const SymTouch t = touch[c];
+            in = (X >= t.a0 && X < t.a1) || (X >= t.b0 && X < t.b1);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_mask[c0 >> 5] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = 0;
+        for (int wd = 0; wd * 32 < a.ctas; wd++) {
+            unsigned m = s_mask[wd];
+            while (m) { const int b = __ffs(m) - 1; m &= m - 1; s_list[cnt++] = (short)(wd * 32 + b); }
+        }
+        s_cnt = cnt;
+    }
+    __syncthreads();
+    // which region does block X belong to, and which entry is mine?
+    long long k = X, i = -1, ord = 0;
+    for (int r = 0; r < a.nreg; r++) {
+        const long long nbr = sym_blocks_in<TB>(reg.begin[r], reg.end[r]);
+        if (k < nbr) {
+            i = (reg.begin[r] / TB + k) * TB + (long long)(blockIdx.x % R) * kThreads + tid;
+            if (i < reg.begin[r] || i >= reg.end[r]) return;
+            ord += i - reg.begin[r];
+            break;
+        }
+        k -= nbr;
+        ord += reg.end[r] > reg.begin[r] ? reg.end[r] - reg.begin[r] : 0;
+    }
+    if (i < 0) return;
+    const int cnt = s_cnt;
+    double su = 0.0, sw = 0.0;
+    for (int s = 0; s < cnt; s += 16) {   // masked batches of 16 independent loads; the additions stay in plane order
+        double bu[16], bw[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const bool ok = s + q < cnt;
+            const long long off = ok ? (long long)s_list[s + q] * 2 * a.n + i : 0;
+            bu[q] = ok ? a.P[off] : 0.0;
+            bw[q] = ok ? a.P[off + a.n] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
+    }
+    if (a.raw) {
+        if (a.packed) { a.vx[ord] = su; a.vx[a.packed_stride + ord] = sw; }
+        else { a.vx[i] = su; a.vz[i] = sw; }
+        return;
+    }
+    double vx = su * kInvTwoPi, vz = sw * kInvTwoPi;
+    const double fu = a.fs ? a.fs[0] : a.fs_u, fw = a.fs ? a.fs[1] : a.fs_w;
+    vx += fu;
+    vz += fw;
+    if (a.accumulate) { vx += a.vx[i]; vz += a.vz[i]; }
+    a.vx[i] = vx;
+    a.vz[i] = vz;
+    if (a.dt != 0.0 && a.x) {
+        a.x[i] += a.dt * vx;
+        a.z[i] += a.dt * vz;
     }
 }
 

@@ -549,56 +549,48 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         const int symR = sym_rows_per_thread(nwake_ub, h->nranks);
         UF_CHECK(h->planes.p != nullptr, "internal: pair-tile planes not allocated before the step was enqueued");
         h->ctas = sym_ctas(symR);
-        // zero the live column ranges of every plane (TEV, LEV, EXTV slabs)
-        const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
-        const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
-        for (int r = 0; r < 3; r++) {
-            const int64_t b = lo[r], e = std::min(round_up(hi[r], kSymTB), tot);
-            if (e > b)
-                UF_CUDA(cudaMemset2DAsync(h->planes.p + b, sizeof(double) * tot, 0, sizeof(double) * (e - b), (size_t)h->ctas * 2, st));
-        }
         SymArgs sa;
         sa.x = h->dev.wx; sa.z = h->dev.wz; sa.g = h->dev.wg;
         sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
         sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = h->rank; sa.nranks = h->nranks;
         if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
-    } else {
-        if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
-    }
-    FinishArgs f;
-    memset(&f, 0, sizeof(f));
-    f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
-    if (sym) { f.pu = h->planes.p; f.pw = h->planes.p + tot; f.tstride = 2 * tot; f.S = h->ctas; }
-    f.treg = &h->st.p->wake; f.ntreg = 3;
-    f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
-    f.fs = h->st.p->fs; f.dt = h->opts.dt;
-    if (sym && h->nranks > 1) {
+        // sum of the planes that touched each block (+ 1/2pi, free stream, explicit Euler when single-rank)
+        SymFinishArgs fs;
+        memset(&fs, 0, sizeof(fs));
+        fs.P = h->planes.p; fs.n = tot; fs.ctas = h->ctas; fs.R = symR;
+        fs.reg = &h->st.p->wake; fs.nreg = 3;
+        fs.vx = h->dev.wvx; fs.vz = h->dev.wvz; fs.x = h->dev.wx; fs.z = h->dev.wz;
+        fs.fs = h->st.p->fs; fs.dt = h->opts.dt;
+        if (h->nranks == 1) {
+            if (int rc = launch_sym_finish(fs, nwake_ub, st)) return rc;
+            h->launches += 2;
+            return 0;
+        }
         // every rank holds the partial velocities of ITS share of the pair tiles for all vortices:
-        // plain plane sums -> NCCL all-reduce over the live slab ranges -> 1/2pi, free stream, convection.
-        // The all-reduce returns identical bits on every rank, so the replicated state stays in lockstep.
-        FinishArgs fr = f;
-        fr.raw = 1; fr.vx = h->vsum.p; fr.vz = h->vsum.p + tot;
-        if (int rc = launch_induce_finish(fr, nwake_ub, st)) return rc;
+        // plain plane sums, packed [u | w] by live-vortex ordinal -> ONE NCCL all-reduce -> 1/2pi, free stream,
+        // convection.  The all-reduce returns identical bits on every rank, so the replicated state stays in lockstep.
+        fs.raw = 1; fs.packed = 1; fs.packed_stride = nwake_ub; fs.vx = h->vsum.p;
+        if (int rc = launch_sym_finish(fs, nwake_ub, st)) return rc;
         const NcclApi *nc = nccl_api();
         if (!nc) return 4;
-        const int64_t lo[3] = {h->off_t, h->off_l, h->off_e};
-        const int64_t hi[3] = {h->off_t + ntev_ub, h->off_l + nlev_ub, h->off_e + h->nextv};
-        if (nc->GroupStart() != ncclSuccess) { set_error("ncclGroupStart failed"); return 4; }
-        for (int r = 0; r < 3; r++) {
-            const int64_t cnt = std::min(hi[r], tot) - lo[r];
-            if (cnt <= 0) continue;
-            for (int c = 0; c < 2; c++) {
-                double *p = h->vsum.p + c * tot + lo[r];
-                if (nc->AllReduce(p, p, (size_t)cnt, ncclDouble, ncclSum, h->comm, st) != ncclSuccess) { set_error("ncclAllReduce failed"); return 4; }
-            }
-        }
-        if (nc->GroupEnd() != ncclSuccess) { set_error("ncclGroupEnd failed"); return 4; }
-        FinishArgs f2 = f;
-        f2.pu = h->vsum.p; f2.pw = h->vsum.p + tot; f2.tstride = 0; f2.S = 1;
+        if (nc->AllReduce(h->vsum.p, h->vsum.p, (size_t)(2 * nwake_ub), ncclDouble, ncclSum, h->comm, st) != ncclSuccess) { set_error("ncclAllReduce failed"); return 4; }
+        FinishArgs f2;
+        memset(&f2, 0, sizeof(f2));
+        f2.pu = h->vsum.p; f2.pw = h->vsum.p + nwake_ub; f2.tstride = 0; f2.S = 1; f2.packed = 1;
+        f2.treg = &h->st.p->wake; f2.ntreg = 3;
+        f2.vx = h->dev.wvx; f2.vz = h->dev.wvz; f2.x = h->dev.wx; f2.z = h->dev.wz;
+        f2.fs = h->st.p->fs; f2.dt = h->opts.dt;
         if (int rc = launch_induce_finish(f2, nwake_ub, st)) return rc;
         h->launches += 3;
         return 0;
     }
+    if (int rc = launch_induce_direct(a, p1, h->uniform, order, st)) return rc;
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.pu = a.pu; f.pw = a.pw; f.tstride = tot; f.S = p1.S;
+    f.treg = &h->st.p->wake; f.ntreg = 3;
+    f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
+    f.fs = h->st.p->fs; f.dt = h->opts.dt;
     if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
     h->launches += 2;
     return 0;
@@ -607,7 +599,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
 // partial planes of the pair-tile kernel, allocated on first need and OUTSIDE stream capture
 static int ensure_planes(unsflow_ldvm *h, int64_t nwake_ub) {
     if (h->planes.p || !h->uniform || nwake_ub < sym_threshold()) return 0;
-    return h->planes.alloc((int64_t)sym_ctas(sym_rows_per_thread(nwake_ub, h->nranks)) * 2 * h->tot) ? 2 : 0;
+    return h->planes.alloc(sym_plane_doubles(sym_ctas(sym_rows_per_thread(nwake_ub, h->nranks)), h->tot)) ? 2 : 0;
 }
 
 static void poll_readback(unsflow_ldvm *h) {
@@ -820,7 +812,14 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     // per-member slabs: [TEV | LEV | EXTV(empty) | BV]
     const int64_t cap_t = round_up(nsteps + 1, 8), cap_l = round_up(nsteps + 1, 8), cap_e = 8, bvp = round_up(nd - 1, 8);
     const int64_t off_l = cap_t, off_e = off_l + cap_l, off_b = off_e + cap_e, tot = off_b + bvp;
-    const int64_t nsurf = 9 * nd + 3 * na, ndp = round_up(nd, 8), np2 = 2 * 4 * ndp;
+    const size_t ens_dyn = sizeof(double) * 5 * (size_t)tot;
+    UF_CHECK(ens_dyn <= 180 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 180 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
+    // the member kernels use the scalar core radius 0.02c of every reference-created vortex (calcs.jl:385,423)
+    for (int64_t i = 0; i < nd - 1; i++)
+        UF_CHECK(sf->bv.vc && sf->bv.vc[i] == 0.02 * sf->c, "unsflow_ldvm_batch_run: surf.bv[%lld].vc must be 0.02c (uniform core radius)", (long long)i);
+    const int64_t nsurf = 9 * nd + 3 * na, ndp = round_up(nd, 8);
+    const int64_t ens_groups = std::max(1, kSolveThreads / nd);      // source groups of ens_sweep = partial planes it writes
+    const int64_t np2 = 2 * ens_groups * ndp;
     DevBuf<StepState> st;
     DevBuf<LdvmDev> devs;
     DevBuf<double> surf, tabs, wake, kin, mat, p2;
@@ -883,7 +882,7 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
         d.wx = wp; d.wz = wp + tot; d.wg = wp + 2 * tot; d.wvc4 = wp + 3 * tot; d.wvc = wp + 4 * tot; d.wvx = wp + 5 * tot; d.wvz = wp + 6 * tot;
         d.kin = kin.p + m * nsteps * 9; d.kin_rows = nsteps;
         d.mat = mat.p + m * nsteps * 8;
-        d.p2u = p2.p + m * np2; d.p2w = p2.p + m * np2 + 4 * ndp; d.p2stride = ndp; d.S2 = 1;
+        d.p2u = p2.p + m * np2; d.p2w = p2.p + m * np2 + ens_groups * ndp; d.p2stride = ndp; d.S2 = 1;
     }
     UF_CUDA(cudaMemcpyAsync(st.p, hst.data(), sizeof(StepState) * M, cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemcpyAsync(devs.p, hd.data(), sizeof(LdvmDev) * M, cudaMemcpyHostToDevice, stream));
@@ -897,12 +896,10 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
         UF_CUDA(cudaMemcpyAsync(surf.p + have * nsurf, surf.p, sizeof(double) * nsurf * cnt, cudaMemcpyDeviceToDevice, stream));
         UF_CUDA(cudaMemcpyAsync(wake.p + have * 7 * tot, wake.p, sizeof(double) * 7 * tot * cnt, cudaMemcpyDeviceToDevice, stream));
     }
-    cudaEvent_t e0, e1;
-    UF_CUDA(cudaEventCreate(&e0));
-    UF_CUDA(cudaEventCreate(&e1));
+    DevEvent ev0, ev1;
+    if (ev0.create() || ev1.create()) return 2;
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     UF_CUDA(cudaEventRecord(e0, stream));
-    const size_t ens_dyn = sizeof(double) * 5 * (size_t)tot;
-    UF_CHECK(ens_dyn <= 180 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 180 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
     UF_CUDA(cudaFuncSetAttribute(k_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
     k_ensemble<<<(unsigned)M, kSolveThreads, ens_dyn, stream>>>(devs.p, nsteps, tot);
     UF_CUDA(cudaGetLastError());
@@ -912,8 +909,6 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     UF_CUDA(cudaMemcpyAsync(hst.data(), st.p, sizeof(StepState) * M, cudaMemcpyDeviceToHost, stream));
     UF_CUDA(cudaStreamSynchronize(stream));
     UF_CUDA(cudaEventElapsedTime(&g_batch_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     for (int64_t m = 0; m < M; m++) {
         double *mo = mat_out + m * nsteps * 8;
         const double *mi = &hm[(size_t)(m * nsteps * 8)];

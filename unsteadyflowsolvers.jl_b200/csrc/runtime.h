@@ -1,6 +1,7 @@
 // runtime.h -- small host-side runtime pieces shared by the .cu files.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace unsflow {
 
@@ -43,6 +44,58 @@ struct DevBuf {
     int zero(cudaStream_t st = 0) {
         cudaError_t e = cudaMemsetAsync(p, 0, sizeof(T) * (size_t)n, st);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e)); return 2; }
+        return 0;
+    }
+};
+
+// Page-locks caller buffers that are handed to a handle again and again (device-resident wake: upload /
+// download of the same host arrays every step), so the copies run as DMA at PCIe speed instead of through the
+// driver's pageable staging path.  A registration is kept until the handle dies or the range is seen with a
+// different size; a failed registration is not an error (the copy falls back to the pageable path).
+// UNSFLOW_NO_HOST_REGISTER=1 disables it.
+struct HostPinCache {
+    struct Ent { const void *p; size_t bytes; };
+    Ent ent[16];
+    int n = 0;
+    HostPinCache() = default;
+    HostPinCache(const HostPinCache &) = delete;
+    HostPinCache &operator=(const HostPinCache &) = delete;
+    ~HostPinCache() { clear(); }
+    void clear() {
+        for (int i = 0; i < n; i++) cudaHostUnregister(const_cast<void *>(ent[i].p));
+        n = 0;
+        (void)cudaGetLastError();
+    }
+    void pin(const void *p, size_t bytes) {
+        static const bool off = [] { const char *e = getenv("UNSFLOW_NO_HOST_REGISTER"); return e && atoi(e) != 0; }();
+        if (off || !p || bytes < (1u << 16)) return;
+        const char *b = static_cast<const char *>(p), *e = b + bytes;
+        for (int i = 0; i < n; i++) {
+            const char *eb = static_cast<const char *>(ent[i].p), *ee = eb + ent[i].bytes;
+            if (eb == b && ee == e) return;                      // already pinned
+            if (b < ee && eb < e) {                              // overlaps an older registration: replace it
+                cudaHostUnregister(const_cast<void *>(ent[i].p));
+                ent[i] = ent[--n];
+                i--;
+            }
+        }
+        if (n == 16) { cudaHostUnregister(const_cast<void *>(ent[0].p)); ent[0] = ent[--n]; }
+        if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) ent[n++] = Ent{p, bytes};
+        (void)cudaGetLastError();
+    }
+};
+
+// RAII CUDA event (early error returns must not leak it)
+struct DevEvent {
+    cudaEvent_t e = nullptr;
+    DevEvent() = default;
+    DevEvent(const DevEvent &) = delete;
+    DevEvent &operator=(const DevEvent &) = delete;
+    ~DevEvent() { if (e) cudaEventDestroy(e); }
+    int create() {
+        if (e) return 0;
+        cudaError_t r = cudaEventCreate(&e);
+        if (r != cudaSuccess) { set_error("cudaEventCreate failed: %s", cudaGetErrorString(r)); e = nullptr; return 2; }
         return 0;
     }
 };

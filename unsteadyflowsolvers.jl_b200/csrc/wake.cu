@@ -58,10 +58,15 @@ struct unsflow_wake {
     int rank = 0, nranks = 1, variant = UNSFLOW_KERNEL_DIRECT;
     bool uniform = true;
     double vc4u = 1.0;
+    bool have_vc = false, have_bvc = false, uni_w = true, uni_b = true;
+    double vc0_w = 0.0, vc0_b = 0.0;   // first core radius of the wake / bound slab (the uniform value when uni_*)
+    DevBuf<int> flag;      // device flag of the uniformity test
+    HostPinCache pins;     // page-locked caller buffers (upload / download every step)
     DevBuf<double> src;    // [x | z | g | vc4], each `tot`
     DevBuf<double> vel;    // [vx | vz], each npad
     DevBuf<double> part;   // [pu | pw], each S*npad
-    DevBuf<double> planes; // symmetric kernel: [ctas][2][tot]
+    DevBuf<double> planes; // symmetric kernel: [ctas][2][tot] + touch records
+    DevBuf<double> vsum;   // symmetric kernel on several ranks: packed plane sums [u(n) | w(n)] for the all-reduce
     int ctas = 0, symR = 4;
     bool want_sym = false;
     DevBuf<Regions> reg;   // [0] sources, [1] my targets
@@ -74,6 +79,23 @@ struct unsflow_wake {
     ncclComm_t comm = nullptr;
     static constexpr int kMaxTimed = 64;
 };
+
+namespace unsflow {
+// v[i] <- v[i]^4 with the host's operation order ((vc*vc)*vc)*vc (multiplies only: nothing to contract);
+// *flag is cleared when an entry differs from v0
+__global__ void k_vc4_inplace(double *v, long long n, double v0, int *flag) {
+    bool same = true;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double c = v[i];
+        same = same && c == v0;
+        v[i] = __dmul_rn(__dmul_rn(__dmul_rn(c, c), c), c);
+    }
+    if (!same) *flag = 0;
+}
+__global__ void k_fill(double *v, long long n, double val) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] = val;
+}
+}  // namespace unsflow
 
 // target slice of the direct kernel: equal slices (NCCL all-gather needs equal counts)
 static int64_t slice_len(int64_t n, int nranks) { return round_up((n + nranks - 1) / nranks, 2); }
@@ -126,15 +148,18 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     cudaEventCreate(&w->ev1);
     w->kev.resize(2 * unsflow_wake::kMaxTimed);
     for (auto &e : w->kev) cudaEventCreate(&e);
-    if (w->src.alloc(4 * w->tot) || w->vel.alloc(2 * w->npad) || w->reg.alloc(2)) return fail(2);
+    if (w->src.alloc(4 * w->tot) || w->vel.alloc(2 * w->npad) || w->reg.alloc(2) || w->flag.alloc(1)) return fail(2);
     const int64_t my_t = std::max<int64_t>(0, std::min(n, (rank + 1) * w->slice) - rank * w->slice);
     w->plan = plan_induce(my_t, 1, n + nbv, 2, sm_count(), 64);
     if (w->part.alloc(2 * (int64_t)w->plan.S * w->npad)) return fail(2);
     w->want_sym = variant == UNSFLOW_KERNEL_SYMMETRIC || (variant == UNSFLOW_KERNEL_AUTO && n >= sym_threshold());
     w->symR = sym_rows_per_thread(n, nranks);
     w->ctas = sym_ctas(w->symR);
-    if (w->want_sym && w->planes.alloc((int64_t)w->ctas * 2 * w->tot)) return fail(2);
+    if (w->want_sym && w->planes.alloc(sym_plane_doubles(w->ctas, w->tot))) return fail(2);
+    if (w->want_sym && nranks > 1 && w->vsum.alloc(2 * n)) return fail(2);
     if (w->src.zero(w->st) || w->vel.zero(w->st)) return fail(2);
+    // dead / padding entries: strength 0, finite position, vc^4 = 1 > 0
+    k_fill<<<sm_count() * 2, 256, 0, w->st>>>(w->src.p + 3 * w->tot, w->tot, 1.0);
     Regions h[2];
     memset(h, 0, sizeof(h));
     h[0].begin[0] = 0; h[0].end[0] = n;
@@ -142,7 +167,7 @@ int unsflow_wake_create(unsflow_wake **out, int64_t n, int64_t nbv, int rank, in
     h[1].begin[0] = rank * w->slice; h[1].end[0] = rank * w->slice + my_t;
     if (cudaMemcpyAsync(w->reg.p, h, sizeof(h), cudaMemcpyHostToDevice, w->st) != cudaSuccess) { set_error("region upload failed"); return fail(2); }
     if (nranks > 1) {
-        UF_CHECK(uid != nullptr, "unsflow_wake_create: nccl_unique_id required when nranks > 1");
+        if (uid == nullptr) { set_error("unsflow_wake_create: nccl_unique_id required when nranks > 1"); return fail(1); }
         const NcclApi *nc = nccl_api();
         if (!nc) return fail(4);
         ncclUniqueId id;
@@ -162,23 +187,31 @@ int unsflow_wake_upload(unsflow_wake *w, const double *x, const double *z, const
     const int64_t tot = w->tot;
     auto up = [&](int arr, int64_t off, const double *h, int64_t cnt) -> int {
         if (!h || cnt == 0) return 0;
+        w->pins.pin(h, sizeof(double) * cnt);
         UF_CUDA(cudaMemcpyAsync(base + arr * tot + off, h, sizeof(double) * cnt, cudaMemcpyHostToDevice, w->st));
         return 0;
     };
     if (up(0, 0, x, w->n) || up(1, 0, z, w->n) || up(2, 0, s, w->n)) return 2;
     if (up(0, w->npad, bx, w->nbv) || up(1, w->npad, bz, w->nbv) || up(2, w->npad, bs, w->nbv)) return 2;
-    if (vc || bvc) {
-        // vc^4 on the host; padding keeps vc4 = 1 (> 0) so dead entries stay finite
-        std::vector<double> v4((size_t)tot, 1.0);
-        bool uni = true;
-        double v0 = vc ? vc[0] : (bvc ? bvc[0] : 1.0);
-        for (int64_t i = 0; vc && i < w->n; i++) { v4[i] = vc[i] * vc[i] * vc[i] * vc[i]; uni = uni && vc[i] == v0; }
-        for (int64_t i = 0; bvc && i < w->nbv; i++) { v4[w->npad + i] = bvc[i] * bvc[i] * bvc[i] * bvc[i]; uni = uni && bvc[i] == v0; }
-        UF_CUDA(cudaMemcpyAsync(base + 3 * tot, v4.data(), sizeof(double) * tot, cudaMemcpyHostToDevice, w->st));
+    // core radii: only the sub-range that was passed is rewritten; vc -> vc^4 and the uniformity test run on the device
+    auto up_vc = [&](int64_t off, const double *h, int64_t cnt, bool *have, bool *uni, double *v0) -> int {
+        if (!h || cnt == 0) return 0;
+        if (up(3, off, h, cnt)) return 2;
+        int one = 1;
+        UF_CUDA(cudaMemcpyAsync(w->flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, w->st));
+        k_vc4_inplace<<<sm_count() * 2, 256, 0, w->st>>>(base + 3 * tot + off, cnt, h[0], w->flag.p);
+        UF_CUDA(cudaGetLastError());
+        int f = 0;
+        UF_CUDA(cudaMemcpyAsync(&f, w->flag.p, sizeof(int), cudaMemcpyDeviceToHost, w->st));
         UF_CUDA(cudaStreamSynchronize(w->st));
-        w->uniform = uni;
-        w->vc4u = v0 * v0 * v0 * v0;
-    }
+        *have = true; *uni = f != 0; *v0 = h[0];
+        return 0;
+    };
+    if (up_vc(0, vc, w->n, &w->have_vc, &w->uni_w, &w->vc0_w)) return 2;
+    if (up_vc(w->npad, bvc, w->nbv, &w->have_bvc, &w->uni_b, &w->vc0_b)) return 2;
+    w->uniform = w->uni_w && (w->nbv == 0 || (w->uni_b && (!w->have_vc || !w->have_bvc || w->vc0_b == w->vc0_w)));
+    const double v0 = w->have_vc ? w->vc0_w : w->vc0_b;
+    w->vc4u = v0 * v0 * v0 * v0;
     UF_CUDA(cudaStreamSynchronize(w->st));
     return 0;
 }
@@ -186,11 +219,14 @@ int unsflow_wake_upload(unsflow_wake *w, const double *x, const double *z, const
 int unsflow_wake_download(unsflow_wake *w, double *x, double *z, double *vx, double *vz) {
     UF_CHECK(w != nullptr, "unsflow_wake_download: null handle");
     const int64_t n = w->n;
-    if (x) UF_CUDA(cudaMemcpyAsync(x, w->src.p, sizeof(double) * n, cudaMemcpyDeviceToHost, w->st));
-    if (z) UF_CUDA(cudaMemcpyAsync(z, w->src.p + w->tot, sizeof(double) * n, cudaMemcpyDeviceToHost, w->st));
-    // velocities exist only for this rank's target slice; other entries are whatever was there
-    if (vx) UF_CUDA(cudaMemcpyAsync(vx, w->vel.p, sizeof(double) * n, cudaMemcpyDeviceToHost, w->st));
-    if (vz) UF_CUDA(cudaMemcpyAsync(vz, w->vel.p + w->npad, sizeof(double) * n, cudaMemcpyDeviceToHost, w->st));
+    auto down = [&](double *h, const double *d) -> int {
+        if (!h) return 0;
+        w->pins.pin(h, sizeof(double) * n);
+        UF_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, w->st));
+        return 0;
+    };
+    // velocities exist only for this rank's target slice (direct variant); other entries are whatever was there
+    if (down(x, w->src.p) || down(z, w->src.p + w->tot) || down(vx, w->vel.p) || down(vz, w->vel.p + w->npad)) return 2;
     UF_CUDA(cudaStreamSynchronize(w->st));
     return 0;
 }
@@ -198,6 +234,7 @@ int unsflow_wake_download(unsflow_wake *w, double *x, double *z, double *vx, dou
 int unsflow_wake_step(unsflow_wake *w, int64_t nsteps, double u_inf, double w_inf, double dt) {
     UF_CHECK(w != nullptr, "unsflow_wake_step: null handle");
     UF_CHECK(nsteps >= 0, "unsflow_wake_step: negative nsteps");
+    UF_CHECK(w->have_vc && (w->nbv == 0 || w->have_bvc), "unsflow_wake_step: core radii were never uploaded (pass vc%s to unsflow_wake_upload first)", w->nbv ? " and bv_vc" : "");
     const int64_t tot = w->tot, npad = w->npad;
     InduceArgs a;
     a.sx = w->src.p; a.sz = w->src.p + tot; a.sg = w->src.p + 2 * tot; a.svc4 = w->src.p + 3 * tot;
@@ -231,26 +268,26 @@ int unsflow_wake_step(unsflow_wake *w, int64_t nsteps, double u_inf, double w_in
         if (timed) UF_CUDA(cudaEventRecord(w->kev[2 * is], w->st));
         if (sym) {
             // every rank evaluates its share of the unordered pair tiles for ALL vortices
-            UF_CUDA(cudaMemsetAsync(w->planes.p, 0, sizeof(double) * (size_t)w->ctas * 2 * tot, w->st));
             if (int rc = launch_induce_sym(sa, w->symR, rsqrt_order(), w->st)) return rc;
             if (timed) { UF_CUDA(cudaEventRecord(w->kev[2 * is + 1], w->st)); w->ktimed = (int)is + 1; }
-            FinishArgs fsym = f;
-            fsym.pu = w->planes.p; fsym.pw = w->planes.p + tot; fsym.tstride = 2 * tot; fsym.S = w->ctas;
-            fsym.treg = w->reg.p; fsym.ntreg = 1;          // all n free vortices
+            SymFinishArgs fs;
+            memset(&fs, 0, sizeof(fs));
+            fs.P = w->planes.p; fs.n = tot; fs.ctas = w->ctas; fs.R = w->symR;
+            fs.reg = w->reg.p; fs.nreg = 1;          // all n free vortices
+            fs.vx = w->vel.p; fs.vz = w->vel.p + npad; fs.x = w->src.p; fs.z = w->src.p + tot;
+            fs.fs_u = u_inf; fs.fs_w = w_inf; fs.dt = dt;
             if (w->nranks == 1) {
-                if (int rc = launch_induce_finish(fsym, w->n, w->st)) return rc;
+                if (int rc = launch_sym_finish(fs, w->n, w->st)) return rc;
                 w->launches += 2;
             } else {
-                fsym.raw = 1;
-                if (int rc = launch_induce_finish(fsym, w->n, w->st)) return rc;
+                // plain sums of this rank's planes, packed [u | w] -> ONE all-reduce -> 1/2pi, free stream, convection
+                fs.raw = 1; fs.packed = 1; fs.packed_stride = w->n; fs.vx = w->vsum.p;
+                if (int rc = launch_sym_finish(fs, w->n, w->st)) return rc;
                 const NcclApi *nc = nccl_api();
                 if (!nc) return 4;
-                UF_NCCL(nc->GroupStart());
-                UF_NCCL(nc->AllReduce(w->vel.p, w->vel.p, (size_t)w->n, ncclDouble, ncclSum, w->comm, w->st));
-                UF_NCCL(nc->AllReduce(w->vel.p + npad, w->vel.p + npad, (size_t)w->n, ncclDouble, ncclSum, w->comm, w->st));
-                UF_NCCL(nc->GroupEnd());
+                UF_NCCL(nc->AllReduce(w->vsum.p, w->vsum.p, (size_t)(2 * w->n), ncclDouble, ncclSum, w->comm, w->st));
                 FinishArgs f2 = f;
-                f2.pu = w->vel.p; f2.pw = w->vel.p + npad; f2.tstride = 0; f2.S = 1;
+                f2.pu = w->vsum.p; f2.pw = w->vsum.p + w->n; f2.tstride = 0; f2.S = 1; f2.packed = 1;
                 f2.treg = w->reg.p; f2.ntreg = 1;
                 if (int rc = launch_induce_finish(f2, w->n, w->st)) return rc;
                 w->launches += 3;

@@ -155,7 +155,16 @@ class LdvmHandle:
             v.assign(*arrs)
 
 
+# Shedding-solve mode of the reference-signature entry points when the caller does not choose one:
+# the restatement of the reference's own mechanics (NLsolve trust-region iteration on the mutating
+# functors, state left at its last finite-difference probe, solvers.jl:199,216 / typedefs.jl:236-247).
+# SOLVE_EXACT (state at the exact root) is the opt-in; the two differ by |dCl| ~ 8e-3 on config C1.
+DEFAULT_SOLVE_MODE = cabi.SOLVE_NLSOLVE
+
+
 def _opts(driver, dt, nsteps, delvort, solve_mode):
+    if solve_mode is None:
+        solve_mode = DEFAULT_SOLVE_MODE
     o = cabi.Opts()
     o.driver, o.solve_mode, o.device = driver, solve_mode, -1
     if isinstance(delvort, delSpalart):
@@ -240,7 +249,7 @@ def _run(driver, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInte
 
 
 def ldvm(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
-         maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+         maxwrite=50, nround=6, solve_mode=None, write_summary=True):
     """ldvm(surf::TwoDSurf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval, delvort;
     maxwrite, nround) -> (mat, surf, curfield), solvers.jl:144-268.  Passing a list of TwoDSurf
     selects the multi-surface method ldvm(surf::Vector{TwoDSurf}, ...) of solvers.jl:270-445
@@ -250,7 +259,7 @@ def ldvm(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, wri
 
 
 def ldvm2DOF(surf, curfield, strpar, kinem, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0,
-             delvort=None, *, maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+             delvort=None, *, maxwrite=50, nround=6, solve_mode=None, write_summary=True):
     """ldvm2DOF(surf, curfield, strpar::TwoDOFPar, kinem::KinemPar2DOF, ...), solvers.jl:657-788"""
     return _run(cabi.DRIVER_LDVM2DOF, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
                 delvort or delNone(), maxwrite, nround, solve_mode, strpar=strpar, kinem=kinem,
@@ -265,13 +274,13 @@ def ldvmLin(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, 
 
 
 def lautat(surf, curfield, nsteps=500, dtstar=0.015, startflag=0, writeflag=0, writeInterval=1000.0, delvort=None, *,
-           maxwrite=50, nround=6, solve_mode=cabi.SOLVE_EXACT, write_summary=True):
+           maxwrite=50, nround=6, solve_mode=None, write_summary=True):
     """lautat(...), solvers.jl:42-142 (wakerollup=1)"""
     return _run(cabi.DRIVER_LAUTAT, surf, curfield, nsteps, dtstar, startflag, writeflag, writeInterval,
                 delvort or delNone(), maxwrite, nround, solve_mode, write_summary=write_summary)
 
 
-def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM, delvort=None, solve_mode=cabi.SOLVE_EXACT):
+def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM, delvort=None, solve_mode=None):
     """Batched ensemble of independent LDVM runs (BASELINE config 3): one thread-block per member
     runs the whole `for istep` loop of solvers.jl:178-257 on the GPU.  All members share the
     geometry / initial state of `surf` (empty wake); member m follows tables[m] (nsteps x 9, see
@@ -298,7 +307,7 @@ def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM,
     return np.ascontiguousarray(mats.transpose(0, 2, 1)), ntev, nlev, ms.value
 
 
-def ldvm2DOF_batch(surf, tables, lespcrit, strpars, kinems, dtstar=0.015, *, delvort=None, solve_mode=cabi.SOLVE_EXACT):
+def ldvm2DOF_batch(surf, tables, lespcrit, strpars, kinems, dtstar=0.015, *, delvort=None, solve_mode=None):
     """Ensemble of independent ldvm2DOF runs (solvers.jl:657-788), e.g. a sweep over structural
     parameters: member m uses TwoDOFPar strpars[m], starts from KinemPar2DOF kinems[m] and follows
     tables[m] (kinematics_table(..., two_dof=True): only t and the external velocities are read).
