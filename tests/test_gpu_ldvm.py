@@ -542,3 +542,60 @@ def test_nlsolve_mode_reproduces_the_branch_taken_by_the_trust_region_iteration(
     gm, _, _ = uf.ldvm2DOF(cs["surf"], cs["fld"], cs["strpar"], copy.deepcopy(cs["kin0"]), cs["nsteps"], cs["dtstar"], 0, 0, 1000.0,
                            cs["delv"], write_summary=False, solve_mode=1)
     assert np.max(np.abs(gm[:30] - om[:30])) < 1e-8
+
+
+def _seed_wake(uf, oracle, fld, ntev, nlev, shift=0.5):
+    """free vortices of S-wake(ntev + nlev) behind the plate, split over the TEV and LEV families"""
+    x, z, g, vc = oracle.s_wake(ntev + nlev)
+    fld.tev = uf.VortList.from_arrays(x[:ntev] + shift, z[:ntev], g[:ntev], vc[:ntev])
+    if nlev:
+        fld.lev = uf.VortList.from_arrays(x[ntev:] + shift, z[ntev:], g[ntev:], vc[ntev:])
+
+
+def _cmp_wake(fld, sim, ptol=1e-12, vtol=1e-12):
+    for fam, v in enumerate((fld.tev, fld.lev)):
+        o = sim.get_vorts(fam)
+        assert len(v) == len(o["x"]), (fam, len(v), len(o["x"]))
+        if not len(v):
+            continue
+        vs = max(np.max(np.abs(o["vx"])), np.max(np.abs(o["vz"])))
+        assert np.max(np.abs(v.x - o["x"])) <= ptol * max(1.0, np.max(np.abs(o["x"]))), fam
+        assert np.max(np.abs(v.z - o["z"])) <= ptol, fam
+        assert np.max(np.abs(v.s[:-3] - o["s"][:-3])) <= 1e-16 and np.max(np.abs(v.s - o["s"])) <= 1e-9, fam     # old strengths are copies / merged sums
+        assert np.max(np.abs(v.vx - o["vx"])) <= vtol * vs and np.max(np.abs(v.vz - o["vz"])) <= vtol * vs, fam
+
+
+@pytest.mark.parametrize("ntev,nlev", [(52000, 6000), (60000, 0)])
+def test_stepper_pair_tile_kernel_teacher_forced_against_the_oracle(gpu_lib, uf, oracle, ntev, nlev):
+    """>= 5e4 free vortices: the stepper's roll-up runs on the symmetric pair-tile kernel (sparse partial planes,
+    k_sym_finish).  Two ldvm steps from the same pre-seeded state on the GPU and on the CPU oracle (whose mutual_ind is
+    the reference's sequential i<j loop, calcs.jl:491-510): histories, wake positions and convection velocities"""
+    surf, fld, dtstar = c2_surf(uf)
+    _seed_wake(uf, oracle, fld, ntev, nlev)
+    n = 2
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM, n, dtstar)
+    mat, surf, fld = uf.ldvm(surf, fld, n, dtstar, write_summary=False)
+    assert len(fld.tev) == ntev + n
+    assert np.max(np.abs(mat - omat)) <= HTOL
+    _cmp_wake(fld, sim)
+    _cmp_state(surf, fld, sim, tol=1e-9)
+
+
+def test_c5_2dof_spalart_merging_on_a_large_wake_against_the_oracle(gpu_lib, uf, oracle):
+    """config C5 at scale: ldvm2DOF (structural Adams-Bashforth feedback, calcs.jl:604-650) with delSpalart merging
+    (calcs.jl:541-602) active from step 1 on a 5.5e4-vortex wake (both families above the limit), three steps against
+    the oracle: every merge decision (counts), the merged strengths / centroids, histories and the 2DOF state"""
+    surf, fld, strpar, kin0 = c5_2dof(uf)
+    ntev, nlev, n = 50000, 5000, 3
+    _seed_wake(uf, oracle, fld, ntev, nlev)
+    dv = uf.delSpalart(4000, 10.0, 1e-6)
+    k_or = copy.deepcopy(kin0)
+    omat, sim = _oracle_run(oracle, uf, copy.deepcopy(surf), copy.deepcopy(fld), oracle.DRIVER_LDVM2DOF, n, 0.015,
+                            twodof=(strpar, k_or), delvort=(1, dv.limit, dv.dist, dv.tol))
+    mat, surf, fld = uf.ldvm2DOF(surf, fld, strpar, kin0, n, 0.015, 0, 0, 1000.0, dv, write_summary=False)
+    o_t, o_l = sim.get_vorts(0), sim.get_vorts(1)
+    assert len(o_t["x"]) < ntev + n and len(o_l["x"]) < nlev + n          # the oracle merged in both families
+    assert np.max(np.abs(mat - omat)) <= HTOL
+    _cmp_wake(fld, sim)
+    _cmp_state(surf, fld, sim, tol=1e-9)
+    assert np.max(np.abs(kin0.as_array() - sim.get_2dof())) < 1e-10

@@ -304,9 +304,7 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
             }
         }
         __syncthreads();
-        if (lautat && tid == 0) {   // lautat saves a0prev/aprev BEFORE update_a2toan (solvers.jl:98-101)
-            // (values are identical either way: a0..a3 do not change afterwards)
-        }
+        // (lautat saves a0prev/aprev BEFORE update_a2toan, solvers.jl:98-101: same values, a0..a3 do not change afterwards)
         if (lev_shed) {
             // ---- G: place_lev (calcs.jl:409-426) + Kelvin-Kutta 2x2 (typedefs.jl:313-348) ------
             if (tid == 0) {
