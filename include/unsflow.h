@@ -256,7 +256,8 @@ int unsflow_rsqrt_probe(int64_t nsamples, double qmin, double qmax, double *max_
                         double *max_rel_newton, double *max_rel_cubic);
 
 /* maximum relative error of ONE refinement variant over the same sweep, against a double-double truth:
- * order 2 = bias-centred Newton (FAST), 3 = Halley in FP64, 4/5/6 = Halley with the e^2 term in FP32 */
+ * order 2 = bias-centred Newton (FAST), 3 = Halley in FP64, 4/5/6 = Halley with the e^2 term in FP32 (measured
+ * slower: kept as experiments), 7 = Halley in FP64 on a seed whose low word is donated by a dying register */
 int unsflow_rsqrt_probe_order(int order, int64_t nsamples, double qmin, double qmax, double *max_rel);
 
 #ifdef __cplusplus

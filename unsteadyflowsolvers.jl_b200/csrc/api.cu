@@ -260,7 +260,9 @@ __global__ void k_rsqrt_probe_order(long long n, double lqmin, double lqstep, do
         const double t0 = 1.0 / sqrt(q);
         const double r = fma(-q * t0, t0, 1.0) - fma(q, t0, -(q * t0)) * t0;     // 1 - q t0^2 to ~1e-32
         const double truth_corr = 0.5 * t0 * r;                                     // truth = t0 + truth_corr
-        const double y = rsqrt_full<ORDER>(q);
+        // ORDER 7: the cubic step on a seed whose low word is donated by another register (rsqrt_seed_lo); the donor
+        // here is an unrelated value with all low bits set / random
+        const double y = ORDER == 7 ? rsqrt_full_lo<3>(q, __hiloint2double(0x3ff00000, (int)(i * 2654435761u) | 0x80000001), 0.375) : rsqrt_full<ORDER == 7 ? 3 : ORDER>(q);
         e = fmax(e, fabs((y - t0) - truth_corr) / t0);
     }
     atomic_max_pos(&mx[0], e);
@@ -463,7 +465,7 @@ int unsflow_rsqrt_probe(int64_t nsamples, double qmin, double qmax, double *e_se
 
 int unsflow_rsqrt_probe_order(int order, int64_t nsamples, double qmin, double qmax, double *max_rel) {
     UF_CHECK(nsamples > 1 && qmin > 0 && qmax > qmin && max_rel, "unsflow_rsqrt_probe_order: bad arguments");
-    UF_CHECK(order >= 2 && order <= 6, "unsflow_rsqrt_probe_order: order must be in [2, 6]");
+    UF_CHECK(order >= 2 && order <= 7, "unsflow_rsqrt_probe_order: order must be in [2, 7]");
     if (int rc = require_device()) return rc;
     DevBuf<double> mx;
     if (mx.alloc(1)) return 2;
@@ -475,7 +477,8 @@ int unsflow_rsqrt_probe_order(int order, int64_t nsamples, double qmin, double q
         case 3: k_rsqrt_probe_order<3><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
         case 4: k_rsqrt_probe_order<4><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
         case 5: k_rsqrt_probe_order<5><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
-        default: k_rsqrt_probe_order<6><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        case 6: k_rsqrt_probe_order<6><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
+        default: k_rsqrt_probe_order<7><<<grid, 256>>>(nsamples, l0, step, mx.p); break;
     }
     UF_CUDA(cudaGetLastError());
     UF_CUDA(cudaMemcpy(max_rel, mx.p, sizeof(double), cudaMemcpyDeviceToHost));

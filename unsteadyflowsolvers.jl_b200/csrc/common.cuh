@@ -60,6 +60,47 @@ __device__ __forceinline__ double rsqrt_seed(double q) {
     return y;
 }
 
+// Same seed, but the low word of the result is taken from `donor` instead of being zeroed.  MUFU.RSQ64H only
+// writes the high word; PTX's rsqrt.approx.ftz.f64 adds a MOV of 0 into the low one.  The refinement does not care
+// what the low 32 mantissa bits of the seed are (they move it by < 2^-20 relative, like the seed's own error), so
+// a register that dies here anyway (d^2 after q = d^4 + vc^4) donates them and the MOV disappears: the induction
+// loops are issue-bound (a DFMA takes two issue slots, every other instruction one), so each one removed counts.
+// Deterministic: the donor is data, not leftover register content.
+__device__ __forceinline__ double rsqrt_seed_lo(double q, double donor) {
+    double y;
+    asm("{\n"
+        ".reg .f64 t;\n"
+        ".reg .b32 tlo, thi, dlo, dhi;\n"
+        "rsqrt.approx.ftz.f64 t, %1;\n"
+        "mov.b64 {tlo, thi}, t;\n"
+        "mov.b64 {dlo, dhi}, %2;\n"
+        "mov.b64 %0, {dlo, thi};\n"
+        "}\n"
+        : "=d"(y)
+        : "d"(q), "d"(donor));
+    return y;
+}
+
+// 1/sqrt(q), seed low word donated by `donor` (see rsqrt_seed_lo); k375 = 0.375 held in a (uniform) register by
+// the caller so that the compiler does not rematerialise the constant inside the loop
+template <int ORDER>
+__device__ __forceinline__ double rsqrt_full_lo(double q, double donor, double k375) {
+    const double y0 = rsqrt_seed_lo(q, donor);
+    if (ORDER == 3) {
+        const double s = q * y0;
+        const double e = fma(-s, y0, 1.0);
+        const double p = fma(k375, e, 0.5);
+        const double pe = p * e;
+        return fma(y0, pe, y0);
+    } else {
+        const int hi = (__double2hiint(y0) - 0x00100000) ^ 0x80000000;
+        const double yh = __hiloint2double(hi, __double2loint(y0));
+        const double s = q * y0;
+        const double c = fma(s, yh, 1.5 + 6.4e-13);
+        return y0 * c;
+    }
+}
+
 template <int ORDER>
 __device__ __forceinline__ double rsqrt_full(double q) {
     const double y0 = rsqrt_seed(q);

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
     double tx[R], tz[R], tg[R], u[R], w[R];
     long long rowI = -1, row_start = 0;
     const double vc4 = a.vc4;
+    const double k375 = fma(vc4, 0.0, 0.375);   // 0.375 as a run-time value: stays in a (uniform) register instead of two MOVs per use
 
     for (long long t = t0; t < t1; t++) {
         const int k = (int)(t - t0), stage = k & 1;
@@ -329,20 +330,15 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             // one phase: warp w works on column chunk (w + p) mod 8, steps [sb, se) of the lane rotation
             auto run_phase = [&](const int p, const int sb, const int se) {
                 const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
-                // software pipeline: the column read for step s+1 is issued before the
-                // accumulator read-modify-write of step s (column data is read-only in a tile)
-                int j = base + ((sb + lane) & (kChunk - 1));
-                double xj = sx[j], zj = sz[j], gj = sg[j];
-#pragma unroll(VAR & 2 ? 2 : 1)
-                for (int s = sb; s < se; s++) {
-                    const int jn = base + ((s + 1 + lane) & (kChunk - 1));
-                    const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
+                // one step of the lane rotation: column j (already in registers) against the R rows
+                auto step = [&](const int j, const double xj, const double zj, const double gj) {
                     double cu = 0.0, cw = 0.0, cu2 = 0.0, cw2 = 0.0;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const double dx = xj - tx[r], dz = zj - tz[r];
                         const double d2 = fma(dz, dz, dx * dx);
-                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                        const double q = fma(d2, d2, vc4);
+                        const double y = (VAR & 4) ? rsqrt_full_lo<ORDER>(q, d2, k375) : rsqrt_full<ORDER>(q);
                         const double t1v = y * dz, t2v = y * dx;
                         u[r] = fma(-gj, t1v, u[r]);
                         w[r] = fma(gj, t2v, w[r]);
@@ -360,7 +356,31 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     acc.y += cw;
                     s_acc[j] = acc;
                     __syncwarp();   // lane l+1 wrote column j+1 in this step; lane l reads it next step
-                    j = jn; xj = xn; zj = zn; gj = gn;
+                };
+                // software pipeline: the column read for step s+1 is issued before the
+                // accumulator read-modify-write of step s (column data is read-only in a tile)
+                int j = base + ((sb + lane) & (kChunk - 1));
+                double xj = sx[j], zj = sz[j], gj = sg[j];
+                if (VAR & 4) {
+                    // two steps per trip with ping-pong column registers: no loop-carried register copies
+                    // (se - sb is even: phases are cut in units of kUnit steps)
+#pragma unroll 1
+                    for (int s = sb; s < se; s += 2) {
+                        const int jb = base + ((s + 1 + lane) & (kChunk - 1));
+                        const double xb = sx[jb], zb = sz[jb], gb = sg[jb];
+                        step(j, xj, zj, gj);
+                        j = base + ((s + 2 + lane) & (kChunk - 1));
+                        xj = sx[j]; zj = sz[j]; gj = sg[j];
+                        step(jb, xb, zb, gb);
+                    }
+                } else {
+#pragma unroll(VAR & 2 ? 2 : 1)
+                    for (int s = sb; s < se; s++) {
+                        const int jn = base + ((s + 1 + lane) & (kChunk - 1));
+                        const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
+                        step(j, xj, zj, gj);
+                        j = jn; xj = xn; zj = zn; gj = gn;
+                    }
                 }
                 __syncthreads();
             };
