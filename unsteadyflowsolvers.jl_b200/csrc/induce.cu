@@ -169,6 +169,7 @@ int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st) {
             case 32: return launch_sym_one<8, 3, 2>(a, ctas, st);
             case 33: return launch_sym_one<8, 3, 3>(a, ctas, st);
             case 34: return launch_sym_one<8, 3, 4>(a, ctas, st);
+            case 38: return launch_sym_one<8, 3, 8>(a, ctas, st);
             case 40: return launch_sym_one<8, 4, 0>(a, ctas, st);
             case 60: return launch_sym_one<8, 6, 0>(a, ctas, st);
             default: break;

@@ -328,7 +328,52 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
             __syncthreads();
             // one phase: warp w works on column chunk (w + p) mod 8, steps [sb, se) of the lane rotation
+            // VAR & 8: every lane works on TWO columns per step (one in each half of the warp's chunk): 2R independent
+            // pair chains per warp instead of R, half as many steps per phase
+            constexpr int kSteps = (VAR & 8) ? kChunk / 2 : kChunk;
+            auto run_phase2 = [&](const int p, const int sb, const int se) {
+                const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
+                int ja = base + ((sb + lane) & (kSteps - 1));
+                double xa = sx[ja], za = sz[ja], ga = sg[ja], xb = sx[ja + kSteps], zb = sz[ja + kSteps], gb = sg[ja + kSteps];
+#pragma unroll 1
+                for (int s = sb; s < se; s++) {
+                    const int jn = base + ((s + 1 + lane) & (kSteps - 1));
+                    const double xan = sx[jn], zan = sz[jn], gan = sg[jn], xbn = sx[jn + kSteps], zbn = sz[jn + kSteps], gbn = sg[jn + kSteps];
+                    double cua = 0.0, cwa = 0.0, cub = 0.0, cwb = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        {
+                            const double dx = xa - tx[r], dz = za - tz[r];
+                            const double d2 = fma(dz, dz, dx * dx);
+                            const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                            const double t1v = y * dz, t2v = y * dx;
+                            u[r] = fma(-ga, t1v, u[r]);
+                            w[r] = fma(ga, t2v, w[r]);
+                            cua = fma(tg[r], t1v, cua);
+                            cwa = fma(-tg[r], t2v, cwa);
+                        }
+                        {
+                            const double dx = xb - tx[r], dz = zb - tz[r];
+                            const double d2 = fma(dz, dz, dx * dx);
+                            const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                            const double t1v = y * dz, t2v = y * dx;
+                            u[r] = fma(-gb, t1v, u[r]);
+                            w[r] = fma(gb, t2v, w[r]);
+                            cub = fma(tg[r], t1v, cub);
+                            cwb = fma(-tg[r], t2v, cwb);
+                        }
+                    }
+                    double2 acca = s_acc[ja], accb = s_acc[ja + kSteps];
+                    acca.x += cua; acca.y += cwa; accb.x += cub; accb.y += cwb;
+                    s_acc[ja] = acca;
+                    s_acc[ja + kSteps] = accb;
+                    __syncwarp();
+                    ja = jn; xa = xan; za = zan; ga = gan; xb = xbn; zb = zbn; gb = gbn;
+                }
+                __syncthreads();
+            };
             auto run_phase = [&](const int p, const int sb, const int se) {
+                if (VAR & 8) { run_phase2(p, sb, se); return; }
                 const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
                 // one step of the lane rotation: column j (already in registers) against the R rows
                 auto step = [&](const int j, const double xj, const double zj, const double gj) {
@@ -387,14 +432,14 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             if (pb == 0 && pe == kSymSub) {
                 // whole tile (the common case): compile-time loop bounds
 #pragma unroll 1
-                for (int p = 0; p < kThreads / 32; p++) run_phase(p, 0, kChunk);
+                for (int p = 0; p < kThreads / 32; p++) run_phase(p, 0, kSteps);
             } else {
                 // first / last tile of this CTA's share: a unit = kUnit consecutive steps of the
                 // (phase, step) sequence of the tile
-                constexpr int kUnit = (kThreads / 32) * kChunk / kSymSub;
+                constexpr int kUnit = (kThreads / 32) * kSteps / kSymSub;
                 const int gs0 = pb * kUnit, gs1 = pe * kUnit;
-                for (int p = gs0 / kChunk; p * kChunk < gs1; p++)
-                    run_phase(p, max(gs0 - p * kChunk, 0), min(gs1 - p * kChunk, kChunk));
+                for (int p = gs0 / kSteps; p * kSteps < gs1; p++)
+                    run_phase(p, max(gs0 - p * kSteps, 0), min(gs1 - p * kSteps, kSteps));
             }
             // flush the column accumulators into this CTA's private plane
             const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);

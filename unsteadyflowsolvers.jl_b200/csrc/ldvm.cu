@@ -46,13 +46,15 @@ __device__ __forceinline__ void tabs_to_smem(const LdvmDev &d, double *dst, uint
 }
 
 __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d, int tabs_in_smem) {
-    extern __shared__ __align__(128) double tab_s[];
+    // dynamic shared memory: [step_solve workspace | cos / sin tables (optional)]
+    extern __shared__ __align__(128) double solve_dyn[];
     __shared__ __align__(8) uint64_t tab_bar;
+    double *tab_s = solve_dyn + (solve_ws_doubles(d.ndiv, d.naterm) + 15) / 16 * 16;
     if (tabs_in_smem) {
         tabs_to_smem(d, tab_s, &tab_bar);
-        step_solve(d, tab_s, tab_s + (d.naterm + 1) * d.ndiv, &tab_bar);
+        step_solve(d, tab_s, tab_s + (d.naterm + 1) * d.ndiv, &tab_bar, solve_dyn);
     } else {
-        step_solve(d, d.costab, d.sintab, nullptr);
+        step_solve(d, d.costab, d.sintab, nullptr, solve_dyn);
     }
 }
 
@@ -66,37 +68,74 @@ __global__ void __launch_bounds__(kSolveThreads) k_lve_solve(const LdvmDev d) {
     lve_solve(d, lve_dyn);
 }
 
-__global__ void __launch_bounds__(kSolveThreads, 3) k_ensemble(const LdvmDev *members, long long nsteps, long long tot) {
-    extern __shared__ __align__(16) double ens_smem[];      // [5][tot]: x, z, g, vx, vz of this member
+// OCC = member CTAs per SM the register budget is cut for (3: 85 registers, 2: 128)
+template <int OCC>
+__global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a) {
+    extern __shared__ __align__(16) double ens_smem[];
     __shared__ LdvmDev d;
-    const LdvmDev *g = members + blockIdx.x;
-    for (long long k = threadIdx.x; k < tot; k += blockDim.x) {
-        ens_smem[k] = g->wx[k]; ens_smem[tot + k] = g->wz[k]; ens_smem[2 * tot + k] = g->wg[k];
-        ens_smem[3 * tot + k] = g->wvx[k]; ens_smem[4 * tot + k] = g->wvz[k];
-    }
-    if (threadIdx.x == 0) {
-        d = *g;
-        d.wx = ens_smem; d.wz = ens_smem + tot; d.wg = ens_smem + 2 * tot; d.wvx = ens_smem + 3 * tot; d.wvz = ens_smem + 4 * tot;
-    }
-    __syncthreads();
-    double *p2u = const_cast<double *>(d.p2u), *p2w = const_cast<double *>(d.p2w);
-    for (long long is = 0; is < nsteps; is++) {
-        step_head(d);
+    __shared__ StepState sst;
+    __shared__ int s_member;
+    const int tid = threadIdx.x, nd = a.proto.ndiv, na = a.proto.naterm;
+    const long long tot = a.tot, ndp = (nd + 7) / 8 * 8, nap = (na + 7) / 8 * 8;
+    // layout: [x | z | g | vx | vz](tot each) [bnd_x | bnd_z | uind | wind | downwash](ndp each) [aterm | adot | aprev](nap each)
+    //         [p2u | p2w](groups * ndp each) [solve workspace]
+    double *wk = ens_smem, *sm_surf = wk + 5 * tot, *sm_at = sm_surf + 5 * ndp, *sm_p2 = sm_at + 3 * nap;
+    double *ws = sm_p2 + 2 * (long long)a.groups * ndp;
+    long long prof[5] = {0, 0, 0, 0, 0};
+    for (;;) {
+        long long c0 = clock64();
+        __syncthreads();                                  // everyone is done with the previous member's shared state
+        if (tid == 0) s_member = atomicAdd(a.next, 1);
         __syncthreads();
-        if (d.driver != UNSFLOW_DRIVER_LAUTAT) {
-            int S2;
-            ens_sweep(d, p2u, p2w, &S2, ens_smem, tot);
-            if (threadIdx.x == 0) d.S2 = S2;
-            __syncthreads();
+        const int slot = s_member;
+        if (slot >= a.M) break;
+        const long long m = a.order[slot];
+        // ---- member set-up: empty wake, bound vortices and surface state from the shared image ----
+        for (long long k = tid; k < 5 * tot; k += blockDim.x) wk[k] = 0.0;
+        __syncthreads();
+        for (int k = tid; k < nd; k += blockDim.x)
+            for (int q = 0; q < 5; q++) sm_surf[q * ndp + k] = a.img[q * nd + k];
+        for (int k = tid; k < na; k += blockDim.x)
+            for (int q = 0; q < 3; q++) sm_at[q * nap + k] = a.img[5 * nd + q * na + k];
+        for (int k = tid; k < nd - 1; k += blockDim.x)
+            for (int q = 0; q < 3; q++) wk[q * tot + a.off_b + k] = a.img[5 * nd + 3 * na + q * (nd - 1) + k];
+        if (tid == 0) {
+            sst = a.st[m];
+            d = a.proto;
+            d.st = &sst;
+            d.lespcrit = a.lespcrit ? a.lespcrit[m] : a.proto.lespcrit;
+            d.bnd_x = sm_surf; d.bnd_z = sm_surf + ndp; d.uind = sm_surf + 2 * ndp; d.wind = sm_surf + 3 * ndp; d.downwash = sm_surf + 4 * ndp;
+            d.aterm = sm_at; d.adot = sm_at + nap; d.aprev = sm_at + 2 * nap;
+            d.wx = wk; d.wz = wk + tot; d.wg = wk + 2 * tot; d.wvx = wk + 3 * tot; d.wvz = wk + 4 * tot;
+            d.wvc4 = nullptr; d.wvc = nullptr;             // scalar core radius (d.vc4_new)
+            d.kin = a.kin + m * a.nsteps * 9; d.kin_rows = a.nsteps;
+            d.mat = a.mat + m * a.nsteps * 8;
+            d.p2u = sm_p2; d.p2w = sm_p2 + (long long)a.groups * ndp; d.p2stride = ndp; d.S2 = 1;
         }
-        step_solve(d, d.costab, d.sintab, nullptr);
         __syncthreads();
-        ens_rollup(d, ens_smem, tot);
+        long long c1 = clock64();
+        prof[4] += c1 - c0;
+        for (long long is = 0; is < a.nsteps; is++) {
+            step_head(d);
+            __syncthreads();
+            c0 = clock64(); prof[0] += c0 - c1;
+            if (d.driver != UNSFLOW_DRIVER_LAUTAT) {
+                int S2;
+                ens_sweep(d, sm_p2, sm_p2 + (long long)a.groups * ndp, &S2, wk, tot);
+                if (tid == 0) d.S2 = S2;
+                __syncthreads();
+            }
+            c1 = clock64(); prof[1] += c1 - c0;
+            step_solve(d, d.costab, d.sintab, nullptr, ws);
+            __syncthreads();
+            c0 = clock64(); prof[2] += c0 - c1;
+            ens_rollup(d, wk, tot);
+            c1 = clock64(); prof[3] += c1 - c0;
+        }
+        if (tid == 0) a.st[m] = sst;
     }
-    for (long long k = threadIdx.x; k < tot; k += blockDim.x) {
-        g->wx[k] = ens_smem[k]; g->wz[k] = ens_smem[tot + k]; g->wg[k] = ens_smem[2 * tot + k];
-        g->wvx[k] = ens_smem[3 * tot + k]; g->wvz[k] = ens_smem[4 * tot + k];
-    }
+    if (a.prof && tid == 0)
+        for (int q = 0; q < 5; q++) a.prof[(long long)blockIdx.x * 8 + q] = prof[q];
 }
 
 }  // namespace unsflow
@@ -523,17 +562,19 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * h->ndiv, st>>>(h->dev);
     else if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
     else {
-        // tables in shared memory when they fit beside the kernel's static arrays (default 70 x 35: 40 KB)
+        // tables in shared memory when they fit beside the workspace (default 70 x 35: 40 KB)
         const size_t tab_bytes = sizeof(double) * 2 * (size_t)(h->naterm + 1) * h->ndiv;
+        const size_t ws_bytes = sizeof(double) * (size_t)((solve_ws_doubles(h->ndiv, h->naterm) + 15) / 16 * 16);
         const int in_smem = tab_bytes <= 160 * 1024;
+        const size_t dyn = ws_bytes + (in_smem ? tab_bytes : 0);
         static size_t attr_bytes[64] = {0};      // per device; the attribute only ever needs to grow
         int dev = 0;
         UF_CUDA(cudaGetDevice(&dev));
-        if (in_smem && tab_bytes > attr_bytes[dev & 63]) {
-            UF_CUDA(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-            attr_bytes[dev & 63] = tab_bytes;
+        if (dyn > attr_bytes[dev & 63]) {
+            UF_CUDA(cudaFuncSetAttribute(k_step_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            attr_bytes[dev & 63] = dyn;
         }
-        k_step_solve<<<1, kSolveThreads, in_smem ? tab_bytes : 0, st>>>(h->dev, in_smem);
+        k_step_solve<<<1, kSolveThreads, dyn, st>>>(h->dev, in_smem);
     }
     h->launches++;
     // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
@@ -791,6 +832,7 @@ int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {
 }  // extern "C"
 
 // shared body of the two ensemble entry points; strpar/kinem2dof non-null <=> ldvm2DOF members
+static thread_local std::vector<long long> g_batch_prof;   // per-CTA phase cycle sums of the last run (UNSFLOW_ENS_PROFILE=1)
 static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
                           const double *tables, const double *lespcrit, const double *strpar, const double *kinem2dof,
                           double *mat_out, double *kinem2dof_out, int64_t *ntev_out, int64_t *nlev_out) {
@@ -804,36 +846,46 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
                  "unsflow_ldvm_batch_run: prescribed-motion drivers only (ldvm, ldvmLin, lautat); use unsflow_ldvm2dof_batch_run for ldvm2DOF");
     }
     UF_CHECK(op->dt > 0, "unsflow_ldvm_batch_run: dt must be > 0");
+    UF_CHECK(op->solve_mode == 0 || op->solve_mode == 1, "unsflow_ldvm_batch_run: bad solve_mode %d", op->solve_mode);
     UF_CHECK(sf->bv.n == sf->ndiv - 1, "unsflow_ldvm_batch_run: surf.bv must hold ndiv-1 vortices");
-    if (int rc = require_device()) return rc;
-    if (op->device >= 0) UF_CUDA(cudaSetDevice(op->device));
+    UF_CHECK(sf->theta && sf->x && sf->cam && sf->cam_slope && sf->bnd_x && sf->bnd_z && sf->uind && sf->wind && sf->downwash &&
+                 sf->aterm && sf->adot && sf->aprev && sf->bv.x && sf->bv.z && sf->bv.s && sf->bv.vc,
+             "unsflow_ldvm_batch_run: null surf array");
     const int nd = sf->ndiv, na = sf->naterm;
     const int64_t M = nmember;
-    // per-member slabs: [TEV | LEV | EXTV(empty) | BV]
+    // per-member slabs (shared memory): [TEV | LEV | EXTV(empty) | BV]
     const int64_t cap_t = round_up(nsteps + 1, 8), cap_l = round_up(nsteps + 1, 8), cap_e = 8, bvp = round_up(nd - 1, 8);
     const int64_t off_l = cap_t, off_e = off_l + cap_l, off_b = off_e + cap_e, tot = off_b + bvp;
-    const size_t ens_dyn = sizeof(double) * 5 * (size_t)tot;
-    UF_CHECK(ens_dyn <= 180 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 180 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
+    const int groups = std::max(1, kSolveThreads / nd);      // source groups of ens_sweep = partial planes it writes
+    const size_t ens_dyn = sizeof(double) * (size_t)ens_smem_doubles(nd, na, tot, groups);
+    UF_CHECK(ens_dyn <= 200 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 200 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
     // the member kernels use the scalar core radius 0.02c of every reference-created vortex (calcs.jl:385,423)
     for (int64_t i = 0; i < nd - 1; i++)
-        UF_CHECK(sf->bv.vc && sf->bv.vc[i] == 0.02 * sf->c, "unsflow_ldvm_batch_run: surf.bv[%lld].vc must be 0.02c (uniform core radius)", (long long)i);
-    const int64_t nsurf = 9 * nd + 3 * na, ndp = round_up(nd, 8);
-    const int64_t ens_groups = std::max(1, kSolveThreads / nd);      // source groups of ens_sweep = partial planes it writes
-    const int64_t np2 = 2 * ens_groups * ndp;
+        UF_CHECK(sf->bv.vc[i] == 0.02 * sf->c, "unsflow_ldvm_batch_run: surf.bv[%lld].vc must be 0.02c (uniform core radius)", (long long)i);
+    if (int rc = require_device()) return rc;
+    if (op->device >= 0) UF_CUDA(cudaSetDevice(op->device));
+    const int64_t ngeo = 4 * nd, nimg = 5 * nd + 3 * na + 3 * (nd - 1);
     DevBuf<StepState> st;
-    DevBuf<LdvmDev> devs;
-    DevBuf<double> surf, tabs, wake, kin, mat, p2;
-    if (st.alloc(M) || devs.alloc(M) || surf.alloc(M * nsurf) || tabs.alloc(2 * (na + 1) * nd) || wake.alloc(M * 7 * tot) ||
-        kin.alloc(M * nsteps * 9) || mat.alloc(M * nsteps * 8) || p2.alloc(M * np2))
+    DevBuf<double> geo, img, tabs, kin, mat;
+    DevBuf<int> order, next;
+    DevBuf<long long> prof;
+    DevEvent ev0, ev1;
+    if (st.alloc(M) || geo.alloc(ngeo) || img.alloc(nimg) || tabs.alloc(2 * (na + 1) * nd) || kin.alloc(M * nsteps * 9) ||
+        mat.alloc(M * nsteps * 8) || order.alloc(M) || next.alloc(1) || ev0.create() || ev1.create())
         return 2;
     cudaStream_t stream = 0;
-    // ---- host staging of ONE member, replicated ------------------------------------------------
-    std::vector<double> hs((size_t)nsurf);
-    const double *sarr[9] = {sf->theta, sf->x, sf->cam, sf->cam_slope, sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
-    for (int k = 0; k < 9; k++) memcpy(&hs[(size_t)k * nd], sarr[k], sizeof(double) * nd);
-    memcpy(&hs[(size_t)9 * nd], sf->aterm, sizeof(double) * na);
-    memcpy(&hs[(size_t)9 * nd + na], sf->adot, sizeof(double) * na);
-    memcpy(&hs[(size_t)9 * nd + 2 * na], sf->aprev, sizeof(double) * na);
+    // ---- host staging --------------------------------------------------------------------------
+    std::vector<double> hg((size_t)ngeo), hi((size_t)nimg);
+    const double *garr[4] = {sf->theta, sf->x, sf->cam, sf->cam_slope};
+    for (int k = 0; k < 4; k++) memcpy(&hg[(size_t)k * nd], garr[k], sizeof(double) * nd);
+    const double *sarr[5] = {sf->bnd_x, sf->bnd_z, sf->uind, sf->wind, sf->downwash};
+    for (int k = 0; k < 5; k++) memcpy(&hi[(size_t)k * nd], sarr[k], sizeof(double) * nd);
+    memcpy(&hi[(size_t)5 * nd], sf->aterm, sizeof(double) * na);
+    memcpy(&hi[(size_t)5 * nd + na], sf->adot, sizeof(double) * na);
+    memcpy(&hi[(size_t)5 * nd + 2 * na], sf->aprev, sizeof(double) * na);
+    memcpy(&hi[(size_t)5 * nd + 3 * na], sf->bv.x, sizeof(double) * (nd - 1));
+    memcpy(&hi[(size_t)5 * nd + 3 * na + (nd - 1)], sf->bv.z, sizeof(double) * (nd - 1));
+    memcpy(&hi[(size_t)5 * nd + 3 * na + 2 * (nd - 1)], sf->bv.s, sizeof(double) * (nd - 1));
     std::vector<double> ht((size_t)(2 * (na + 1) * nd));
     for (int n = 0; n <= na; n++)
         for (int i = 0; i < nd; i++) {
@@ -841,15 +893,7 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
             ht[(size_t)(na + 1) * nd + (size_t)n * nd + i] = std::sin(n * sf->theta[i]);
         }
     const double vc_new = 0.02 * sf->c, vc4 = vc_new * vc_new * vc_new * vc_new;
-    std::vector<double> hw((size_t)(7 * tot), 0.0);
-    for (int64_t i = 0; i < tot; i++) { hw[3 * tot + i] = vc4; hw[4 * tot + i] = vc_new; }
-    for (int64_t i = 0; i < nd - 1; i++) {
-        hw[0 * tot + off_b + i] = sf->bv.x[i]; hw[1 * tot + off_b + i] = sf->bv.z[i]; hw[2 * tot + off_b + i] = sf->bv.s[i];
-        hw[4 * tot + off_b + i] = sf->bv.vc[i];
-        hw[3 * tot + off_b + i] = sf->bv.vc[i] * sf->bv.vc[i] * sf->bv.vc[i] * sf->bv.vc[i];
-    }
     std::vector<StepState> hst((size_t)M);
-    std::vector<LdvmDev> hd((size_t)M);
     StepState s0;
     memset(&s0, 0, sizeof(s0));
     s0.wake.begin[0] = 0; s0.wake.end[0] = 0;
@@ -866,49 +910,82 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
             memcpy(hst[m].sp, strpar + 11 * m, sizeof(double) * 11);
             memcpy(hst[m].k2, kinem2dof + 22 * m, sizeof(double) * 22);
         }
-        LdvmDev &d = hd[m];
-        memset(&d, 0, sizeof(d));
-        d.st = st.p + m;
-        d.ndiv = nd; d.naterm = na; d.driver = op->driver; d.solve_mode = op->solve_mode; d.del_kind = op->delvort_kind;
-        d.del_limit = op->del_limit; d.del_dist = op->del_dist; d.del_tol = op->del_tol;
-        d.c = sf->c; d.uref = sf->uref; d.pvt = sf->pvt; d.lespcrit = lespcrit ? lespcrit[m] : sf->lespcrit; d.dt = op->dt;
-        d.vc_new = vc_new; d.vc4_new = vc4;
-        double *sp = surf.p + m * nsurf;
-        d.theta = sp; d.x = sp + nd; d.cam = sp + 2 * nd; d.cam_slope = sp + 3 * nd; d.bnd_x = sp + 4 * nd; d.bnd_z = sp + 5 * nd;
-        d.uind = sp + 6 * nd; d.wind = sp + 7 * nd; d.downwash = sp + 8 * nd;
-        d.aterm = sp + 9 * nd; d.adot = sp + 9 * nd + na; d.aprev = sp + 9 * nd + 2 * na;
-        d.costab = tabs.p; d.sintab = tabs.p + (int64_t)(na + 1) * nd;
-        double *wp = wake.p + m * 7 * tot;
-        d.wx = wp; d.wz = wp + tot; d.wg = wp + 2 * tot; d.wvc4 = wp + 3 * tot; d.wvc = wp + 4 * tot; d.wvx = wp + 5 * tot; d.wvz = wp + 6 * tot;
-        d.kin = kin.p + m * nsteps * 9; d.kin_rows = nsteps;
-        d.mat = mat.p + m * nsteps * 8;
-        d.p2u = p2.p + m * np2; d.p2w = p2.p + m * np2 + ens_groups * ndp; d.p2stride = ndp; d.S2 = 1;
+    }
+    // Queue order: most expensive members first.  A member's cost is dominated by its wake size, i.e. by whether it
+    // sheds LEVs every step: rank by the largest quasi-steady leading-edge loading the table asks for, relative to the
+    // member's LESP threshold (a heuristic -- the order only affects load balance, never results).
+    std::vector<int> hord((size_t)M);
+    {
+        std::vector<double> score((size_t)M, 0.0);
+        for (int64_t m = 0; m < M; m++) {
+            const double *tb = tables + m * nsteps * 9;
+            double peak = 0.0;
+            for (int64_t k = 0; k < nsteps; k++) {
+                const double *r = tb + 9 * k;
+                const double u = std::fabs(r[5]) > 1e-12 ? std::fabs(r[5]) : 1.0;
+                peak = std::max(peak, std::fabs(r[1]) + std::fabs(r[3]) * sf->c / u + std::fabs(r[4]) / u);
+            }
+            const double lc = lespcrit ? lespcrit[m] : sf->lespcrit;
+            score[m] = peak / std::max(lc, 1e-6);
+        }
+        for (int64_t m = 0; m < M; m++) hord[m] = (int)m;
+        std::stable_sort(hord.begin(), hord.end(), [&](int x, int y) { return score[x] > score[y]; });
+    }
+    EnsArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    LdvmDev &d = ea.proto;
+    d.ndiv = nd; d.naterm = na; d.driver = op->driver; d.solve_mode = op->solve_mode; d.del_kind = op->delvort_kind;
+    d.del_limit = op->del_limit; d.del_dist = op->del_dist; d.del_tol = op->del_tol;
+    d.c = sf->c; d.uref = sf->uref; d.pvt = sf->pvt; d.lespcrit = sf->lespcrit; d.dt = op->dt;
+    d.vc_new = vc_new; d.vc4_new = vc4; d.nsurf = 1;
+    d.theta = geo.p; d.x = geo.p + nd; d.cam = geo.p + 2 * nd; d.cam_slope = geo.p + 3 * nd;
+    d.costab = tabs.p; d.sintab = tabs.p + (int64_t)(na + 1) * nd;
+    ea.img = img.p; ea.st = st.p; ea.kin = kin.p; ea.mat = mat.p; ea.order = order.p; ea.next = next.p;
+    ea.M = M; ea.nsteps = nsteps; ea.tot = tot; ea.off_l = off_l; ea.off_e = off_e; ea.off_b = off_b; ea.groups = groups;
+    DevBuf<double> lesp;
+    if (lespcrit) {
+        if (lesp.alloc(M)) return 2;
+        UF_CUDA(cudaMemcpyAsync(lesp.p, lespcrit, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
+        ea.lespcrit = lesp.p;
     }
     UF_CUDA(cudaMemcpyAsync(st.p, hst.data(), sizeof(StepState) * M, cudaMemcpyHostToDevice, stream));
-    UF_CUDA(cudaMemcpyAsync(devs.p, hd.data(), sizeof(LdvmDev) * M, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(geo.p, hg.data(), sizeof(double) * ngeo, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(img.p, hi.data(), sizeof(double) * nimg, cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemcpyAsync(tabs.p, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemcpyAsync(kin.p, tables, sizeof(double) * M * nsteps * 9, cudaMemcpyHostToDevice, stream));
-    // replicate the member image on the device: upload once, then D2D copies with doubling
-    UF_CUDA(cudaMemcpyAsync(surf.p, hs.data(), sizeof(double) * nsurf, cudaMemcpyHostToDevice, stream));
-    UF_CUDA(cudaMemcpyAsync(wake.p, hw.data(), sizeof(double) * 7 * tot, cudaMemcpyHostToDevice, stream));
-    for (int64_t have = 1; have < M; have *= 2) {
-        const int64_t cnt = std::min(have, M - have);
-        UF_CUDA(cudaMemcpyAsync(surf.p + have * nsurf, surf.p, sizeof(double) * nsurf * cnt, cudaMemcpyDeviceToDevice, stream));
-        UF_CUDA(cudaMemcpyAsync(wake.p + have * 7 * tot, wake.p, sizeof(double) * 7 * tot * cnt, cudaMemcpyDeviceToDevice, stream));
+    UF_CUDA(cudaMemcpyAsync(order.p, hord.data(), sizeof(int) * M, cudaMemcpyHostToDevice, stream));
+    UF_CUDA(cudaMemsetAsync(next.p, 0, sizeof(int), stream));
+    static const int want_occ = [] { const char *e = getenv("UNSFLOW_ENS_OCC"); const int v = e ? atoi(e) : 3; return v == 2 ? 2 : 3; }();
+    auto kern = want_occ == 2 ? k_ensemble<2> : k_ensemble<3>;
+    UF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSolveThreads, ens_dyn) != cudaSuccess || occ < 1) occ = 1;
+    static const int cap_occ = [] { const char *e = getenv("UNSFLOW_ENS_MAXOCC"); return e ? atoi(e) : 0; }();
+    if (cap_occ > 0) occ = std::min(occ, cap_occ);
+    const int grid = (int)std::min<int64_t>(M, (int64_t)occ * sm_count());
+    static const bool want_prof = [] { const char *e = getenv("UNSFLOW_ENS_PROFILE"); return e && atoi(e) != 0; }();
+    if (want_prof) {
+        if (prof.alloc((int64_t)grid * 8) || prof.zero(stream)) return 2;
+        ea.prof = prof.p;
     }
-    DevEvent ev0, ev1;
-    if (ev0.create() || ev1.create()) return 2;
-    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
-    UF_CUDA(cudaEventRecord(e0, stream));
-    UF_CUDA(cudaFuncSetAttribute(k_ensemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
-    k_ensemble<<<(unsigned)M, kSolveThreads, ens_dyn, stream>>>(devs.p, nsteps, tot);
+    UF_CUDA(cudaEventRecord(ev0.e, stream));
+    kern<<<grid, kSolveThreads, ens_dyn, stream>>>(ea);
     UF_CUDA(cudaGetLastError());
-    UF_CUDA(cudaEventRecord(e1, stream));
+    UF_CUDA(cudaEventRecord(ev1.e, stream));
     std::vector<double> hm((size_t)(M * nsteps * 8));
     UF_CUDA(cudaMemcpyAsync(hm.data(), mat.p, sizeof(double) * hm.size(), cudaMemcpyDeviceToHost, stream));
     UF_CUDA(cudaMemcpyAsync(hst.data(), st.p, sizeof(StepState) * M, cudaMemcpyDeviceToHost, stream));
     UF_CUDA(cudaStreamSynchronize(stream));
-    UF_CUDA(cudaEventElapsedTime(&g_batch_ms, e0, e1));
+    UF_CUDA(cudaEventElapsedTime(&g_batch_ms, ev0.e, ev1.e));
+    if (want_prof) {
+        g_batch_prof.assign((size_t)grid * 8, 0);
+        UF_CUDA(cudaMemcpy(g_batch_prof.data(), prof.p, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost));
+        long long tot_c[5] = {0, 0, 0, 0, 0};
+        for (int c = 0; c < grid; c++)
+            for (int q = 0; q < 5; q++) tot_c[q] += g_batch_prof[(size_t)c * 8 + q];
+        fprintf(stderr, "[unsflow ensemble profile] grid %d (occupancy %d/SM), %.3f ms; cycles per CTA (mean): head %.3e sweep %.3e solve %.3e rollup %.3e setup %.3e\n",
+                grid, occ, g_batch_ms, (double)tot_c[0] / grid, (double)tot_c[1] / grid, (double)tot_c[2] / grid, (double)tot_c[3] / grid, (double)tot_c[4] / grid);
+    }
     for (int64_t m = 0; m < M; m++) {
         double *mo = mat_out + m * nsteps * 8;
         const double *mi = &hm[(size_t)(m * nsteps * 8)];

@@ -5,14 +5,41 @@
 namespace unsflow {
 
 // ---------------------------------------------------------------------------------------------
-// Ensemble kernel (config 3): one CTA per member runs the WHOLE step loop.  The member's wake
-// slabs (x, z, strength, vx, vz -- a few hundred to a few thousand vortices) live in SHARED
-// MEMORY for the whole run: k_ensemble points the member's LdvmDev at them, so the unchanged
-// single-surface step functions (step_head / step_solve) and the two block-level induction
-// loops below all work in place, with no staging tiles and no barriers inside the pair loops.
+// Ensemble kernel (config 3): a PERSISTENT grid of member CTAs.  Each CTA pulls the next member from an atomic
+// queue (members are listed most-expensive-first by the host, so the long ones start early and the short ones
+// fill the gaps: longest-processing-time-first list scheduling) and runs the member's WHOLE step loop with
+// every piece of mutable member state in SHARED MEMORY: the wake slabs (x, z, strength, vx, vz), the StepState,
+// the mutable TwoDSurf arrays (bnd_x/z, uind, wind, downwash, aterm, adot, aprev), the bound-sweep partial
+// planes and the solve workspace.  The unchanged single-surface step functions (step_head / step_solve) run on
+// an LdvmDev whose pointers aim at that shared memory, so their single-thread sections walk shared-memory
+// latencies instead of L2 round trips.  Global memory per member: the kinematics table (read), the mat rows
+// (written) and the StepState (initial 2DOF parameters in, final counts out) -- no per-member slabs.
 // Members are independent: no inter-CTA communication, any number of GPUs by sharding members.
 // All ensemble vortices share the core radius 0.02c (calcs.jl:385,423), hence the scalar vc4.
 // ---------------------------------------------------------------------------------------------
+struct EnsArgs {
+    LdvmDev proto;            // scalars, geometry (theta, x, cam, cam_slope) and table pointers shared by all members
+    const double *img;        // initial mutable state shared by all members: [bnd_x, bnd_z, uind, wind, downwash](ndiv each),
+                              // [aterm, adot, aprev](naterm each), [bv_x, bv_z, bv_s](ndiv - 1 each)
+    StepState *st;            // [M] in: initial state (2DOF parameters per member); out: final counts / 2DOF state
+    const double *kin;        // [M][nsteps][9]
+    double *mat;              // [M][nsteps][8]
+    const double *lespcrit;   // [M] or null
+    const int *order;         // [M] member ids, most expensive first
+    int *next;                // queue head (zeroed before the launch)
+    long long M, nsteps;
+    long long tot, off_l, off_e, off_b;   // member slab layout [TEV | LEV | EXTV(empty) | BV]
+    int groups;               // source groups of the in-CTA bound sweep (= partial planes)
+    long long *prof;          // optional [gridDim.x][8] cycle counters (head, sweep, solve, roll-up, setup), or null
+};
+
+// dynamic shared memory of one member CTA, in doubles
+__host__ __device__ inline long long ens_smem_doubles(int nd, int na, long long tot, int groups) {
+    const long long ndp = (nd + 7) / 8 * 8, nap = (na + 7) / 8 * 8;
+    return 5 * tot + 5 * ndp + 3 * nap + 2 * (long long)groups * ndp + solve_ws_doubles(nd, na);
+}
+
+
 constexpr int kEnsR = 4;        // targets per thread in the member roll-up
 
 // pair kernel shared by the two block-level induction loops (13 FP64 instr, cubic rsqrt)

@@ -95,7 +95,8 @@ __device__ void step_head(const LdvmDev &d) {
             xloc = sh_te[0] + (1. / 3.) * (sh_last[0] - sh_te[0]);
             zloc = sh_te[1] + (1. / 3.) * (sh_last[1] - sh_te[1]);
         }
-        d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0; d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new;
+        d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0;
+        if (d.wvc4) { d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new; }      // (ensemble members: scalar core radius, no slabs)
         d.wvx[e] = 0.0; d.wvz[e] = 0.0;
         s->wake.end[0] = e + 1;
     }
@@ -177,15 +178,23 @@ __device__ void dev_spalart(const LdvmDev &d, long long *begin, long long end, d
 // costab / sintab: the [(naterm+1)][ndiv] cos(n theta) / sin(n theta) tables -- d.costab / d.sintab in global memory, or
 // a shared-memory copy that a TMA bulk copy started at kernel entry is still filling (tab_bar != nullptr: wait on it
 // before the first table read; the copy overlaps the partial-plane sums of phase A)
-__device__ void step_solve(const LdvmDev &d, const double *costab, const double *sintab, uint64_t *tab_bar) {
+// shared-memory workspace of step_solve in doubles: 12 arrays of max(ndiv, naterm + 1) entries (rounded up to 8),
+// 32 scalars, kinematics (6) + free stream (2)
+__host__ __device__ inline int solve_ws_len(int nd, int na) { return ((nd > na + 1 ? nd : na + 1) + 7) / 8 * 8; }
+__host__ __device__ inline int solve_ws_doubles(int nd, int na) { return 12 * solve_ws_len(nd, na) + 32 + 8; }
+
+// ws: solve_ws_doubles(ndiv, naterm) doubles of shared memory (sized by the actual discretisation, so that an
+// ensemble member CTA does not pay for kNdMax-wide arrays)
+__device__ void step_solve(const LdvmDev &d, const double *costab, const double *sintab, uint64_t *tab_bar, double *ws) {
     StepState *s = d.st;
     const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm;
-    __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
-    __shared__ double uT[kNdMax], wT[kNdMax], uL[kNdMax], wL[kNdMax], gam[kNdMax];
-    __shared__ double aterm[kNaMax + 1];   // aterm[0] unused slot for a0-style indexing: aterm[n] = A_n
-    __shared__ double dth[kNdMax];
-    __shared__ double sc[32];              // scalar scratch
-    __shared__ double kin[6], fs[2];
+    const int wl = solve_ws_len(nd, na);
+    double *uind = ws, *wind = ws + wl, *dw = ws + 2 * wl, *dw1 = ws + 3 * wl, *dw2 = ws + 4 * wl;
+    double *uT = ws + 5 * wl, *wT = ws + 6 * wl, *uL = ws + 7 * wl, *wL = ws + 8 * wl, *gam = ws + 9 * wl;
+    double *aterm = ws + 10 * wl;          // aterm[0] unused slot for a0-style indexing: aterm[n] = A_n
+    double *dth = ws + 11 * wl;
+    double *sc = ws + 12 * wl;             // scalar scratch [32]
+    double *kin = sc + 32, *fs = kin + 6;
     __shared__ int lev_shed;
     const double urefpi = d.uref * kPi;
     const double kfac = d.uref * d.c * kPi;
@@ -319,7 +328,8 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
                     xl = d.bnd_x[0] + (1. / 3.) * (d.wx[le - 1] - d.bnd_x[0]);
                     zl = d.bnd_z[0] + (1. / 3.) * (d.wz[le - 1] - d.bnd_z[0]);
                 }
-                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = 0.0; d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new;
+                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = 0.0;
+                if (d.wvc4) { d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new; }
                 d.wvx[le] = 0.0; d.wvz[le] = 0.0;
                 s->wake.end[1] = le + 1;
                 sc[12] = xl; sc[13] = zl;
@@ -460,7 +470,8 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
                 sc[8] = tevstr; sc[14] = levstr;
                 sc[10] = J1 + J2 * tevstr + J3 * levstr;                                // :587
                 const long long le = s->wake.end[1];
-                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = levstr; d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new;
+                d.wx[le] = xl; d.wz[le] = zl; d.wg[le] = levstr;
+                if (d.wvc4) { d.wvc4[le] = d.vc4_new; d.wvc[le] = d.vc_new; }
                 d.wvx[le] = 0.0; d.wvz[le] = 0.0;
                 s->wake.end[1] = le + 1;
             }
@@ -473,7 +484,8 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
             }
         }
         if (tid == 0) {   // push the TEV (:594 / :605)
-            d.wx[te] = xt; d.wz[te] = zt; d.wg[te] = gt; d.wvc4[te] = d.vc4_new; d.wvc[te] = d.vc_new;
+            d.wx[te] = xt; d.wz[te] = zt; d.wg[te] = gt;
+            if (d.wvc4) { d.wvc4[te] = d.vc4_new; d.wvc[te] = d.vc_new; }
             d.wvx[te] = 0.0; d.wvz[te] = 0.0;
             s->wake.end[0] = te + 1;
         }
