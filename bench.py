@@ -35,9 +35,10 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 13.0
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_induce_sym<8,3> launch at N = 1e6 from the
-# `ncu --set full` capture summarised in profiles/r01_sym_R8_N1e6_ncu_full.txt (4.42 + 3.90 GB: the
-# per-CTA partial planes' read-modify-write; 0.2 % of DRAM bandwidth -- the kernel is FP64-bound)
-NCU_TRAFFIC_SYM8_N1E6 = 8.3268e9
+# `ncu --set full` capture of this round (profiles/r02_sym_R8_N1e6_ncu_full.txt; the per-CTA partial planes'
+# read-modify-write, a fraction of a percent of DRAM bandwidth -- the kernel is FP64-bound).  None = not captured.
+NCU_TRAFFIC_SYM8_N1E6 = None
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA lanes x 2 flop x 1.965 GHz = 37.2
 NBV = 69                        # ndiv - 1 bound vortices (typedefs.jl:68)
 
 
@@ -238,7 +239,7 @@ def main():
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ---------------
     xs, zs, vxs, vzs = (np.zeros(n) for _ in range(4))
     dn = [cabi.dptr(a) for a in (xs, zs, vxs, vzs)]
-    ke = min(K, 2)
+    ke = max(5, min(K, 5))
     barrier()
     e0 = time.perf_counter()
     for _ in range(ke):
@@ -277,6 +278,50 @@ def main():
         verify = {"targets": int(len(idx)), "max_normalised_err": float(max(np.max(np.abs(vxs[idx] - tu)) / np.max(au),
                                                                              np.max(np.abs(vzs[idx] - tw)) / np.max(aw))),
                   "tolerance": 1e-12, "against": "oracle long-double sum"}
+    # ---- extra: the multi-GPU split BASELINE.json names -- targets sliced contiguously over the ranks (one-sided
+    # kernel, also the only path for non-uniform core radii), NCCL all-gather of the convected positions each step.
+    # Timed for 2 steps; every rank verifies 8 targets of ITS OWN slice against the long-double truth.
+    ag = None
+    try:
+        h1 = C.c_void_p()
+        uid1 = (C.c_ubyte * 128)()
+        if world > 1:
+            t1 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                cabi.check(L.unsflow_nccl_unique_id(uid1))
+                t1.copy_(torch.tensor(list(uid1), dtype=torch.uint8))
+            dist.broadcast(t1, 0)
+            for i, v in enumerate(t1.cpu().tolist()):
+                uid1[i] = v
+        cabi.check(L.unsflow_wake_create(C.byref(h1), n, NBV, rank, world, uid1 if world > 1 else None, 1))
+        cabi.check(L.unsflow_wake_upload(h1, *up))
+        cabi.check(L.unsflow_wake_step(h1, 1, 0.0, 0.0, 0.0))          # dt = 0: velocities of the original field
+        cabi.check(L.unsflow_wake_download(h1, None, None, dn[2], dn[3]))
+        b1, e1 = C.c_int64(), C.c_int64()
+        cabi.check(L.unsflow_partition(n, world, rank, 1, C.byref(b1), C.byref(e1)))
+        idx1 = np.linspace(b1.value, e1.value - 1, 8).astype(np.int64)
+        sx1 = np.concatenate([x, bx]); sz1 = np.concatenate([z, bz]); sg1 = np.concatenate([g, bs]); sv1 = np.concatenate([vc, bvc])
+        tu1, tw1, au1, aw1 = O.ind_vel_truth(sx1, sz1, sg1, sv1, x[idx1], z[idx1])
+        err1 = float(max(np.max(np.abs(vxs[idx1] - tu1)) / np.max(au1), np.max(np.abs(vzs[idx1] - tw1)) / np.max(aw1)))
+        barrier()
+        cabi.check(L.unsflow_wake_step(h1, 2, uinf, 0.0, dt))
+        ms1, msk1, nl1 = C.c_float(), C.c_float(), C.c_int64()
+        cabi.check(L.unsflow_wake_timing(h1, C.byref(ms1), C.byref(msk1), C.byref(nl1)))
+        # after the exchange every rank must hold the same positions: checksum of x over all ranks
+        cabi.check(L.unsflow_wake_download(h1, dn[0], dn[1], None, None))
+        cs = float(np.dot(xs, ((np.arange(n) % 97) + 1.0)))
+        ta = torch.tensor([ms1.value, err1, cs, -cs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        msmax, errmax, csmax, ncsmin = ta.tolist()
+        ag = {"split": "contiguous target slices + ncclAllGather of x, z (wake.cu, kernel variant 1 = one-sided)",
+              "interactions_per_s": inter_step * 2 / (msmax * 1e-3), "ms_per_step": msmax / 2,
+              "verify_max_normalised_err_over_ranks": errmax, "verify_targets_per_rank": 8, "tolerance": 1e-12,
+              "positions_identical_on_all_ranks": bool(csmax == -ncsmin)}
+        cabi.check(L.unsflow_wake_destroy(h1))
+    except Exception as e:
+        ag = {"error": str(e)[:200]}
+
     # ---- extra: opt-in FAST precision mode (bias-centred Newton rsqrt, <= 6.5e-13 per pair); the headline
     # above is FULL precision -- this block only documents what the relaxed mode would buy ---------------
     fast = None
@@ -328,57 +373,116 @@ def main():
         except Exception as e:
             ens = {"error": str(e)[:200]}
 
-    # ---- extra: LDVM steps/s with a 1e5-vortex wake (config C2 regime); with several GPUs the roll-up
-    # pair tiles are split over the ranks (unsflow_ldvm_set_parallel), everything else is replicated ----
+    # ---- extra: device-resident LDVM stepper (configs C2, C5, C1).  With several GPUs the roll-up pair tiles are
+    # split over the ranks (unsflow_ldvm_set_parallel), everything else is replicated bit-identically. -----------
     if args.ldvm_steps > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from cases import c1_surf, c2_surf, c5_2dof
+        from unsflow_b200.solvers import LdvmHandle, _opts
+        import hashlib
+
+        def new_uid():
+            u = (C.c_ubyte * 128)()
+            t2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                cabi.check(L.unsflow_nccl_unique_id(u))
+                t2.copy_(torch.tensor(list(u), dtype=torch.uint8))
+            dist.broadcast(t2, 0)
+            for i, v in enumerate(t2.cpu().tolist()):
+                u[i] = v
+            return u
+
+        def stepper_run(surf, fld, driver, ns, dtstar, nranks, delv=None, twodof=None, warm=3):
+            """ns timed steps after `warm` untimed ones; returns (device ms max over ranks, launches, mat, handle-final field)"""
+            hh = LdvmHandle(surf, fld, _opts(driver, dtstar, ns + warm, delv or uf.delNone(), None))
+            try:
+                if nranks > 1:
+                    hh.set_parallel(rank, nranks, new_uid())
+                if twodof:
+                    hh.set_2dof(*twodof)
+                hh.set_kinematics(uf.kinematics_table(surf, fld, ns + warm, dtstar, two_dof=twodof is not None))
+                hh.run(warm)
+                if nranks > 1:
+                    barrier()
+                mat = hh.run(ns)
+                ms, nl = hh.timing()
+                hh.download()
+                cnt = hh.counts()
+            finally:
+                hh.close()
+            tl = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if nranks > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            return tl.item(), nl, mat, cnt
+
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            from cases import c2_surf
-            from unsflow_b200.solvers import LdvmHandle, _opts
-            surf, fld, dtstar = c2_surf(uf)
+            # config C2 (pitch-plunge, no deletion), windows of the growth to 1e5 vortices: wake pre-seeded with S-wake(N)
+            win = {}
+            for nw, nsw in ((1_000, 64), (10_000, 64), (100_000, args.ldvm_steps)):
+                surf, fld, dtstar = c2_surf(uf)
+                wx, wz, wg, wvc = s_wake(nw)
+                fld.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
+                use_ranks = world if nw >= 100_000 else 1      # small wakes: replicas only (launch-bound)
+                if use_ranks == 1 and rank != 0:
+                    continue
+                ms, nl, mat, cnt = stepper_run(surf, fld, cabi.DRIVER_LDVM, nsw, dtstar, use_ranks)
+                win[str(nw)] = {"steps_per_s": nsw / (ms * 1e-3), "steps": nsw, "launches_per_step": nl / nsw, "ranks": use_ranks}
+                if nw == 100_000:
+                    extra["ldvm_steps_per_s_at_N1e5"] = nsw / (ms * 1e-3)
+                    extra["ldvm_launches_per_step"] = nl / nsw
+                    if world > 1:
+                        # parity of the N-rank stepper in this very run: (i) every rank must return the same bits,
+                        # (ii) rank 0 repeats the steps on ONE rank from the same state and reports the deviation
+                        dig = hashlib.sha256(np.ascontiguousarray(mat).tobytes() + np.ascontiguousarray(fld.tev.x).tobytes()
+                                             + np.ascontiguousarray(fld.tev.vz).tobytes()).digest()
+                        td = torch.tensor(list(dig), dtype=torch.uint8, device="cuda")
+                        allg = [torch.zeros_like(td) for _ in range(world)]
+                        dist.all_gather(allg, td)
+                        same = all(bool(torch.equal(allg[0], a)) for a in allg)
+                        par = {"ranks_bit_identical": same, "steps": nsw + 3}
+                        if rank == 0:
+                            s1, f1, _ = c2_surf(uf)
+                            f1.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
+                            ms1, nl1, mat1, cnt1 = stepper_run(s1, f1, cabi.DRIVER_LDVM, nsw, dtstar, 1)
+                            par["max_abs_dmat_vs_1_rank"] = float(np.max(np.abs(mat - mat1)))
+                            par["max_abs_dx_vs_1_rank"] = float(np.max(np.abs(fld.tev.x - f1.tev.x)))
+                            vs = float(np.max(np.abs(f1.tev.vz)))
+                            par["max_rel_dvz_vs_1_rank"] = float(np.max(np.abs(fld.tev.vz - f1.tev.vz)) / vs)
+                            par["one_rank_steps_per_s"] = nsw / (ms1 * 1e-3)
+                        extra["ldvm_multi_rank_parity"] = par
+            if rank == 0:
+                extra["ldvm_C2_windows"] = win
+        except Exception as e:   # never lose the headline line
+            extra["ldvm_error"] = str(e)[:300]
+        try:
+            # config C5: ldvm2DOF + delSpalart on a 1e5-vortex wake (merging active from step 1)
+            surf, fld, strpar, kin0 = c5_2dof(uf)
             nw = 100_000
             wx, wz, wg, wvc = s_wake(nw)
             fld.tev = uf.VortList.from_arrays(wx + 0.5, wz, wg, wvc)
-            ns = args.ldvm_steps
-            hh = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, ns + 3, uf.delNone(), cabi.SOLVE_EXACT))
-            if world > 1:
-                uid2 = (C.c_ubyte * 128)()
-                t2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
-                if rank == 0:
-                    cabi.check(L.unsflow_nccl_unique_id(uid2))
-                    t2.copy_(torch.tensor(list(uid2), dtype=torch.uint8))
-                dist.broadcast(t2, 0)
-                for i, v in enumerate(t2.cpu().tolist()):
-                    uid2[i] = v
-                hh.set_parallel(rank, world, uid2)
-            hh.set_kinematics(uf.kinematics_table(surf, fld, ns + 3, dtstar))
-            hh.run(3)
-            barrier()
-            hh.run(ns)
-            ms, nl = hh.timing()
-            hh.close()
-            tl = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-            extra["ldvm_steps_per_s_at_N1e5"] = ns / (tl.item() * 1e-3)
-            extra["ldvm_launches_per_step"] = nl / ns
-        except Exception as e:   # never lose the headline line
-            extra["ldvm_error"] = str(e)[:200]
+            ns5 = max(args.ldvm_steps, 40)
+            ms, nl, mat, cnt = stepper_run(surf, fld, cabi.DRIVER_LDVM2DOF, ns5, 0.015, world, delv=uf.delSpalart(nw, 10.0, 1e-6),
+                                           twodof=(strpar, kin0))
+            if rank == 0:
+                extra["ldvm2dof_C5"] = {"steps_per_s": ns5 / (ms * 1e-3), "steps": ns5, "wake0": nw, "tev_after": int(cnt[0]), "lev_after": int(cnt[1]),
+                                        "merged_tevs": int(nw + ns5 + 3 - cnt[0]), "finite": bool(np.all(np.isfinite(mat))),
+                                        "ranks": world, "launches_per_step": nl / ns5,
+                                        "parity": "tests/test_gpu_ldvm.py::test_c5_2dof_spalart_merging_on_a_large_wake_against_the_oracle (5.5e4 wake, every merge decision vs the oracle)"}
+        except Exception as e:
+            extra["ldvm2dof_C5"] = {"error": str(e)[:300]}
         # config C1 (the reference's own test case, test/ldvmLinTest.jl through ldvm, 468 steps from an empty
         # wake): device-resident steps/s on rank 0, with the CPU oracle's steps/s beside it
         if rank == 0:
             try:
-                from cases import c1_surf
                 surf1, fld1, n1, dts1 = c1_surf(uf)
                 uf.ldvm(copy.deepcopy(surf1), uf.TwoDFlowField(), n1, dts1, write_summary=False)        # warm-up (graph capture)
-                hh = LdvmHandle(surf1, fld1, _opts(cabi.DRIVER_LDVM, dts1 * surf1.c / surf1.uref, n1, uf.delNone(), cabi.SOLVE_EXACT))
+                hh = LdvmHandle(surf1, fld1, _opts(cabi.DRIVER_LDVM, dts1 * surf1.c / surf1.uref, n1, uf.delNone(), None))
                 hh.set_kinematics(uf.kinematics_table(surf1, fld1, n1, dts1))
                 hh.run(n1)
                 ms1, nl1 = hh.timing()
                 hh.close()
-                c1 = {"steps": n1, "device_ms": ms1, "steps_per_s": n1 / (ms1 * 1e-3), "launches_per_step": nl1 / n1}
+                c1 = {"steps": n1, "device_ms": ms1, "steps_per_s": n1 / (ms1 * 1e-3), "us_per_step": 1e3 * ms1 / n1, "launches_per_step": nl1 / n1}
                 if not args.no_cpu_baseline:
-                    from oracle import oracle as O
                     t0 = time.perf_counter()
                     O.Sim(surf1, uf.TwoDFlowField()).run(O.DRIVER_LDVM, uf.kinematics_table(surf1, uf.TwoDFlowField(), n1, dts1), dts1)
                     c1["cpu_oracle_steps_per_s"] = n1 / (time.perf_counter() - t0)
@@ -409,6 +513,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": ach_per_gpu, "peak": tf.value, "unit": "TFLOP/s",
                      "frac": ach_per_gpu / tf.value,
+                     "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": ach_per_gpu / FP64_NOMINAL_TFLOPS,
                      "traffic": NCU_TRAFFIC_SYM8_N1E6 if (world == 1 and n == 1_000_000 and args.variant == 0) else None,
                      "kernel": "k_induce_* (all-pairs Vatistas induction)",
                      "peak_source": f"measured in this run: DFMA-chain microbenchmark (unsflow_fp64_peak), ~{mhz.value:.0f} MHz "
@@ -416,6 +521,7 @@ def main():
                      "algorithmic": f"{FLOP_PER_INTERACTION:.0f} flop/interaction x {inter_step / world:.4e} interactions per launch per GPU"},
     }
     line["verify"] = verify
+    line["allgather_target_slices"] = ag
     line["ensemble_C3"] = ens
     line["fast_precision_mode"] = fast
     line.update(extra)

@@ -424,6 +424,22 @@ def test_multi_gpu_stepper_lockstep(gpu_lib, uf):
     assert "bit-identical across ranks True" in out.stdout
 
 
+def test_multi_gpu_target_slices_with_allgather(gpu_lib, uf):
+    """needs >= 2 GPUs on the box (skipped otherwise; log of the 2- and 8-GPU runs in profiles/): the split BASELINE.json
+    names -- contiguous target slices, one-sided kernel, NCCL all-gather of the convected positions (wake.cu variant 1),
+    on per-vortex core radii; slice velocities vs the long-double truth, ranks bit-identical, equal to a 1-rank run"""
+    import subprocess, sys
+    if uf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(__file__))
+    env = dict(os.environ, AG_N="40000", AG_STEPS="3")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29579", os.path.join(root, "tools", "allgather_check.py")],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bit-identical across ranks True" in out.stdout
+
+
 def test_nlsolve_mode_other_drivers(gpu_lib, uf, oracle):
     """UNSFLOW_SOLVE_NLSOLVE (stale finite-difference probe state) on ldvm2DOF and
     on the multi-surface driver, against the oracle's full trust-region emulation"""

@@ -44,7 +44,7 @@ def make(nw):
 nw = int(os.environ.get("MG_WAKE", 100000))
 nsteps = int(os.environ.get("MG_STEPS", 20))
 surf, fld, dtstar = make(nw)
-h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 3, uf.delNone(), cabi.SOLVE_EXACT))
+h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 3, uf.delNone(), None))
 h.set_parallel(rank, world, uid)
 h.set_kinematics(uf.kinematics_table(surf, fld, nsteps + 3, dtstar))
 m0 = h.run(3)
@@ -63,7 +63,7 @@ if rank == 0:
     same = all(bool(torch.equal(allt[0], a)) for a in allt)
     # single-GPU stepper on the same input
     s1, f1, _ = make(nw)
-    h1 = LdvmHandle(s1, f1, _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 3, uf.delNone(), cabi.SOLVE_EXACT))
+    h1 = LdvmHandle(s1, f1, _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 3, uf.delNone(), None))
     h1.set_kinematics(uf.kinematics_table(s1, f1, nsteps + 3, dtstar))
     h1.run(3)
     mat1 = h1.run(nsteps)
