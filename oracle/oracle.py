@@ -241,6 +241,12 @@ class Sim:
     def nfev(self):
         return lib().o_sim_nfev(self.h)
 
+    def delcp_edgevel(self, rho, velx=0.0, velz=0.0):
+        """calc_delcp / calc_edgeVel (postprocess.jl:184-244) on the current state -> (p_com, p_in, p_out, q_u, q_l)"""
+        out = np.zeros(5 * self.nd)
+        lib().o_sim_delcp_edgevel(self.h, C.c_double(rho), C.c_double(velx), C.c_double(velz), _p(out))
+        return tuple(out.reshape(5, self.nd))
+
 
 # synthetic inputs (counter-based generator shared by tests, bench and tools): see /synth.py
 import sys as _sys

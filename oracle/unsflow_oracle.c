@@ -999,6 +999,52 @@ void o_sim_set_forces(void *h, double cl, double cd, double cm) {
 }
 long o_sim_nfev(void *h) { return ((o_sim *)h)->nfev; }
 
+/* calc_delcp(surf, vels) -> (p_com, p_in, p_out), src/lowOrder2D/postprocess.jl:184-222, and
+ * calc_edgeVel(surf, vels) -> (q_com_u, q_com_l), :224-244: the five columns (after x) of the `delcp_edgevel`
+ * step file (postprocess.jl:100-110).  out = [p_com | p_in | p_out | q_com_u | q_com_l], ndiv each.
+ * rho = surf.rho (the LE radius parameter, typedefs.jl:68) is not part of the oracle's surf state and is passed in.
+ * Note the reference's own asymmetry, restated literally: calc_delcp ignores `vels`, calc_edgeVel uses it. */
+void o_sim_delcp_edgevel(void *h, double rho, double velx, double velz, double *out) {
+    const o_surf *s = &((o_sim *)h)->s;
+    const int nd = s->ndiv;
+    double *p_com = out, *p_in = out + nd, *p_out = out + 2 * nd, *q_u = out + 3 * nd, *q_l = out + 4 * nd;
+    for (int k = 0; k < 5 * nd; k++) out[k] = 0.0;
+    for (int i = 0; i < nd; i++) {                                                      /* :193-197 */
+        double udash = s->u * cos(s->alpha) + s->hdot * sin(s->alpha) + s->uind[i] * cos(s->alpha) - s->wind[i] * sin(s->alpha);
+        p_in[i] = 8 * s->uref * sqrt(s->c) * s->a0 * sqrt(s->x[i]) * udash / (rho * s->c + 2 * s->x[i])
+                  + 4 * s->uref * sqrt(s->c) * s->a0dot * sqrt(s->x[i]);
+    }
+    for (int i = 1; i < nd; i++) {                                                      /* :198-219 */
+        double udash = s->u * cos(s->alpha) + s->hdot * sin(s->alpha) + s->uind[i] * cos(s->alpha) - s->wind[i] * sin(s->alpha);
+        double th = s->theta[i];
+        double gam = s->a0 * (1.0 / tan(th / 2)), gamint = s->a0dot * (th + sin(th)), gammod = 0.0;
+        for (int n = 1; n <= s->naterm; n++) {
+            gam += s->aterm[n - 1] * sin(n * th);
+            gammod += s->aterm[n - 1] * sin(n * th);
+            if (n == 1) gamint += s->adot[0] * (th / 2 - sin(2 * th) / 4);
+            else gamint += s->adot[n - 1] / 2 * (sin((n - 1) * th) / (n - 1) - sin((n + 1) * th) / (n + 1));
+        }
+        gam = gam * s->uref;
+        gammod = gammod * s->uref;
+        gamint = gamint * s->uref * s->c;
+        p_out[i] = 2 * udash * gam + gamint;
+        p_com[i] = 2 * udash * s->uref * s->a0 * (cos(th / 2) - 1) / sin(th / 2) + 2 * udash * gammod + gamint
+                   + 8 * s->uref * udash * s->c * s->a0 * sin(th / 2) / (rho * s->c + 2 * s->c * (sin(th / 2) * sin(th / 2)));
+    }
+    q_u[0] = s->uref * s->a0 / sqrt(0.5 * rho);                                          /* :230-231 */
+    q_l[0] = s->uref * s->a0 / sqrt(0.5 * rho);
+    for (int i = 1; i < nd; i++) {                                                      /* :233-241 */
+        double udash = (s->u + velx) * cos(s->alpha) + (s->hdot - velz) * sin(s->alpha) + s->uind[i] * cos(s->alpha) - s->wind[i] * sin(s->alpha);
+        double th = s->theta[i], gammod = 0.0;
+        for (int n = 1; n <= s->naterm; n++) gammod += s->aterm[n - 1] * sin(n * th);
+        gammod = gammod * s->uref;
+        q_u[i] = s->uref * s->a0 * (cos(th / 2) - 1) / sin(th / 2) + s->uref * gammod
+                 + (sqrt(s->c) * s->uref * s->a0 + sqrt(s->x[i]) * udash) / sqrt(s->x[i] + rho * s->c / 2);
+        q_l[i] = -s->uref * s->a0 * (cos(th / 2) - 1) / sin(th / 2) - s->uref * gammod
+                 + (-sqrt(s->c) * s->uref * s->a0 + sqrt(s->x[i]) * udash) / sqrt(s->x[i] + rho * s->c / 2);
+    }
+}
+
 /* run nsteps of the chosen driver; returns 0 */
 int o_sim_run(void *h, int driver, long nsteps, double dt, const double *kin /*nsteps x 9*/,
               int solver_mode, int dkind, long dlimit, double ddist, double dtol,

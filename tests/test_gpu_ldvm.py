@@ -299,12 +299,29 @@ def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):
     assert nlev.max() > 10 and nlev.min() == 0
 
 
-def test_write_stamps_from_device_snapshots(gpu_lib, uf, tmp_path, monkeypatch):
+def test_write_stamps_from_device_snapshots(gpu_lib, uf, oracle, tmp_path, monkeypatch):
     """writeflag = 1: the write schedule of solvers.jl:164-175 and the `Step Files/<t>/...`
-    layout of postprocess.jl:34-113, produced from device snapshots"""
+    layout of postprocess.jl:34-113, produced from device snapshots; the VALUES of every step file
+    (incl. calc_delcp / calc_edgeVel, postprocess.jl:184-244) against the oracle state at that step"""
     monkeypatch.chdir(tmp_path)
     surf, fld, _, dtstar = c1r_surf(uf)
+    o_surf, o_fld = copy.deepcopy(surf), copy.deepcopy(fld)
     mat, surf, fld = uf.ldvm(surf, fld, 120, dtstar, 0, 1, 0.6, uf.delNone(), maxwrite=5)
+    # oracle state at the second stamp (t = 1.2, step 80)
+    tab = uf.kinematics_table(o_surf, o_fld, 80, dtstar)
+    sim = oracle.Sim(o_surf, o_fld)
+    sim.run(oracle.DRIVER_LDVM, tab, dtstar)
+    ref = np.stack((o_surf.x,) + sim.delcp_edgevel(o_surf.rho, 0.0, 0.0), axis=1)
+    got = np.loadtxt(os.path.join("Step Files", "1.2", "delcp_edgevel"))
+    assert got.shape == ref.shape == (70, 6)
+    assert np.max(np.abs(got - ref)) <= 1e-8 * max(1.0, np.max(np.abs(ref)))
+    ot = sim.get_vorts(0)
+    tv = np.loadtxt(os.path.join("Step Files", "1.2", "tev"))
+    assert np.max(np.abs(tv - np.stack([ot["s"], ot["x"], ot["z"]], axis=1))) <= 1e-9
+    so = sim.get_surf()
+    fc = np.loadtxt(os.path.join("Step Files", "1.2", "FourierCoeffs"))
+    assert np.max(np.abs(fc[1:, 0] - so["aterm"])) <= 1e-9 and abs(fc[0, 0] - so["a0"]) <= 1e-9
+    assert np.max(np.abs(fc[1:4, 1] - so["adot"][:3])) <= 1e-7 and abs(fc[0, 1] - so["a0dot"]) <= 1e-7
     dirs = sorted(os.listdir("Step Files"), key=float)
     assert dirs == ["0.6", "1.2", "1.8"]
     for name in ("timeKinem", "FourierCoeffs", "tev", "lev", "boundv", "delcp_edgevel"):

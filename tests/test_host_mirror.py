@@ -79,3 +79,30 @@ def test_meshgrid_geometry(uf):
     assert abs(m.camX[0] - ((0 - 0.25) * np.cos(0.1) - 0.5 + 0.25)) < 1e-14
     w = uf.meshgrid(surf, tev, uf.VortList(), 0.25, 0.5, 100, "wake")
     assert w.x.shape == w.z.shape == (55, 100) and w.tev.shape[0] == 1
+
+
+def test_eldupint_motion_definitions(uf):
+    """EldUpIntDef / EldUpInttstartDef (kinem.jl:179-249): value = running rectangle-rule integral of the Eldredge ramp
+    with the reference's re-derived step (dt = t / (round(t/0.015 + 1) - 1)); derivative = what ForwardDiff returns
+    for that callable (checked by a finite difference inside a window where the step count does not change);
+    used for the plunge in update_kinem (calcs.jl:137-142) and, EldUpIntDef only, in the constructor (typedefs.jl:121)"""
+    import math
+    for m in (uf.EldUpIntDef(0.5, 0.2, 0.8), uf.EldUpInttstartDef(0.3, 0.4, 0.6, 0.5)):
+        assert m(0.0) == 0.0 and m.deriv(0.0) == 0.0 and m(0.004) == 0.0            # nsteps == 1 -> literal 0
+        for t in (0.3, 1.234, 2.71):
+            n = int(round(t / 0.015 + 1))
+            dt = t / (n - 1)
+            sm = math.pi ** 2 * m.K / (2 * m.amp * (1 - m.a))
+            t1 = m._tstart()
+            t2 = t1 + m.amp / (2 * m.K)
+            ref = sum(((m.K / sm) * math.log(math.cosh(sm * (i * dt - t1)) / math.cosh(sm * (i * dt - t2))) + m.amp / 2) * dt for i in range(n))
+            assert abs(m(t) - ref) < 1e-14
+            h = 1e-6
+            assert int(round((t + h) / 0.015 + 1)) == n == int(round((t - h) / 0.015 + 1))
+            assert abs(m.deriv(t) - (m(t + h) - m(t - h)) / (2 * h)) < 1e-8
+    # wired into the plunge branch of update_kinem and of the TwoDSurf constructor
+    kin = uf.KinemDef(uf.ConstDef(0.1), uf.EldUpIntDef(0.5, 0.2, 0.8), uf.ConstDef(1.0))
+    surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [0.2], c=2.0, uref=1.5)
+    tab = uf.kinematics_table(surf, uf.TwoDFlowField(), 100, 0.015 * 2.0 / 1.5)
+    t = tab[-1, 0]
+    assert abs(tab[-1, 2] - kin.h(t) * 2.0) < 1e-15 and abs(tab[-1, 4] - kin.h.deriv(t) * 1.5) < 1e-15 and tab[-1, 2] > 0

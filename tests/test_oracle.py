@@ -263,3 +263,26 @@ def test_exact_mode_two_root_step_found_by_the_fuzz_sweep(oracle, uf):
     a0 = om[:, 4]
     assert np.any(np.abs(a0 - cs["lesp"]) < 1e-12) and np.any(np.abs(a0 + cs["lesp"]) < 1e-12)     # sheds on both branches
     assert np.max(np.abs(om - nm)) < 1e-9
+
+
+def test_delcp_and_edge_velocity_mirror_against_oracle_restatement(oracle, uf):
+    """calc_delcp / calc_edgeVel (postprocess.jl:184-244): the host mirror that writes `delcp_edgevel` from a device
+    snapshot against the C restatement, on an LEV-shedding state with a non-zero external velocity"""
+    from unsflow_b200.postprocess import calc_delcp, calc_edgeVel
+    surf, fld, _, dtstar = c1r_surf(uf)
+    tab = uf.kinematics_table(surf, fld, 90, dtstar)
+    sim = oracle.Sim(surf, fld)
+    sim.run(oracle.DRIVER_LDVM, tab, dtstar)
+    s = sim.get_surf()
+    for name in ("uind", "wind", "aterm", "adot"):
+        getattr(surf, name)[:] = s[name]
+    surf.a0[0], surf.a0dot[0] = s["a0"], s["a0dot"]
+    for a in ("alpha", "h", "alphadot", "hdot", "u", "udot"):
+        setattr(surf.kinem, a, s[a])
+    vels = [0.07, -0.03]
+    p_com, p_in, p_out = calc_delcp(surf, vels)
+    qu, ql = calc_edgeVel(surf, vels)
+    o = sim.delcp_edgevel(surf.rho, *vels)
+    for got, ref, nm in zip((p_com, p_in, p_out, qu, ql), o, ("p_com", "p_in", "p_out", "qu", "ql")):
+        assert np.max(np.abs(ref)) > 1e-3, nm
+        assert np.max(np.abs(got - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), nm

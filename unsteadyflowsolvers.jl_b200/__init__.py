@@ -8,7 +8,7 @@ from . import _cabi
 from ._cabi import UnsflowError, device_count, lib
 from .calcs import ind_vel, mutual_ind, update_indbound, wakeroll
 from .delvort import delNone, delSpalart, delVortDef
-from .kinem import (ConstDef, CosDef, EldRampReturnDef, EldRampReturntstartDef, EldUpDef, EldUptstartDef, FileDef,
+from .kinem import (ConstDef, CosDef, EldRampReturnDef, EldRampReturntstartDef, EldUpDef, EldUpIntDef, EldUpInttstartDef, EldUptstartDef, FileDef,
                     KinemDef, KinemPar, LinearDef, MotionDef, SinDef, StepGustDef)
 from .postprocess import calc_delcp, calc_edgeVel, writeStamp, meshgrid
 from .solvers import LVE, kinematics_table, lautat, ldvm, ldvm2DOF, ldvm2DOF_batch, ldvm_batch, ldvmLin, lve_table

@@ -202,6 +202,56 @@ class StepGustDef(MotionDef):
 
 
 @dataclass
+class EldUpIntDef(MotionDef):
+    """Eldredge ramp integrated in time with a running rectangle rule (plunge from a prescribed plunge-rate ramp),
+    kinem.jl:179-213.  `deriv` is what ForwardDiff.derivative returns for that callable: the step count
+    round(Int, t/0.015 + 1) carries no derivative, dt = t/(nsteps - 1) does (d dt/dt = 1/(nsteps - 1)), and so do the
+    sample times (i-1) dt; for nsteps == 1 the result is the literal 0. (value 0, derivative 0)."""
+    amp: float
+    K: float
+    a: float
+
+    def _tstart(self):
+        return 1.0
+
+    def _eval(self, t):
+        dt = 0.015
+        nsteps = int(round(t / dt + 1))            # round(Int, x): ties to even, like Python's round
+        if nsteps == 1:
+            return 0.0, 0.0
+        dt = t / (nsteps - 1)
+        ddt = 1.0 / (nsteps - 1)
+        if self.amp == 0.0:
+            return 0.0, 0.0
+        sm = math.pi * math.pi * self.K / (2 * self.amp * (1 - self.a))
+        t1 = self._tstart()
+        t2 = t1 + (self.amp / (2 * self.K))
+        amp = damp = 0.0
+        for i in range(1, nsteps + 1):
+            tmpt, dtmpt = (i - 1) * dt, (i - 1) * ddt
+            hdot = ((self.K / sm) * math.log(math.cosh(sm * (tmpt - t1)) / math.cosh(sm * (tmpt - t2)))) + (self.amp / 2.0)
+            dhdot = self.K * (math.tanh(sm * (tmpt - t1)) - math.tanh(sm * (tmpt - t2))) * dtmpt
+            amp = amp + hdot * dt
+            damp = damp + dhdot * dt + hdot * ddt
+        return amp, damp
+
+    def __call__(self, t):
+        return self._eval(t)[0]
+
+    def deriv(self, t):
+        return self._eval(t)[1]
+
+
+@dataclass
+class EldUpInttstartDef(EldUpIntDef):
+    """kinem.jl:215-249"""
+    tstart: float = 1.0
+
+    def _tstart(self):
+        return self.tstart
+
+
+@dataclass
 class FileDef(MotionDef):
     """kinem.jl:252-262: nearest-sample lookup (piecewise constant => derivative 0)"""
     tvec: np.ndarray
@@ -224,7 +274,7 @@ def eval_kinem(kindef: KinemDef, t: float, c: float, uref: float, prev: KinemPar
     if isinstance(a, (EldUpDef, EldRampReturnDef, ConstDef, SinDef, CosDef, FileDef)):
         k.alpha = a(t)
         k.alphadot = 0.0 if isinstance(a, ConstDef) else a.deriv(t) * uref / c
-    if isinstance(h, (EldUpDef, EldRampReturnDef, ConstDef, SinDef, CosDef, FileDef)):
+    if isinstance(h, (EldUpDef, EldUpIntDef, EldRampReturnDef, ConstDef, SinDef, CosDef, FileDef)):      # calcs.jl:131-163
         k.h = h(t) if isinstance(h, FileDef) else h(t) * c
         k.hdot = 0.0 if isinstance(h, ConstDef) else h.deriv(t) * uref
     if isinstance(u, (EldUpDef, EldRampReturnDef, ConstDef, SinDef, CosDef, LinearDef, FileDef)) and not isinstance(

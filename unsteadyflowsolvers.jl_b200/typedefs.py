@@ -9,7 +9,7 @@ from dataclasses import dataclass, field as dc_field
 
 import numpy as np
 
-from .kinem import (ConstDef, CosDef, EldRampReturnDef, EldUpDef, FileDef, KinemDef, KinemPar, MotionDef, SinDef)
+from .kinem import (ConstDef, CosDef, EldRampReturnDef, EldUpDef, EldUpIntDef, FileDef, KinemDef, KinemPar, MotionDef, SinDef)
 
 _FIELDS = ("x", "z", "s", "vc", "vx", "vz")
 
@@ -147,7 +147,7 @@ def _init_kinem(kindef: KinemDef, c: float, uref: float) -> KinemPar:
     elif type(a) is ConstDef:
         k.alpha = a(0.0)
         k.alphadot = 0.0
-    if type(h) in (EldUpDef, EldRampReturnDef, SinDef, CosDef):
+    if type(h) in (EldUpDef, EldUpIntDef, EldRampReturnDef, SinDef, CosDef):      # typedefs.jl:118-135 (EldUpInttstartDef is not listed there)
         k.h = h(0.0) * c
         k.hdot = h.deriv(0.0) * uref
     elif type(h) is ConstDef:
