@@ -39,7 +39,7 @@ int rsqrt_order() {
     static int order = [] {
         const char *e = getenv("UNSFLOW_RSQRT_ORDER");
         int o = e ? atoi(e) : 3;
-        return (o == 2 || (o >= 4 && o <= 6)) ? o : 3;
+        return (o == 2) ? 2 : 3;
     }();
     return order;
 }

@@ -128,17 +128,17 @@ long long sym_threshold() {
     return v;
 }
 
-template <int R, int O, int V = 0>
+template <int R, int O>
 static int launch_sym_one(const SymArgs &a, int ctas, cudaStream_t st) {
     static bool attr_set[64] = {false};      // per device (a process may drive several through unsflow_set_device)
     const size_t smem = sym_smem_bytes(R);
     int dev = 0;
     UF_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<R, O, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UF_CUDA(cudaFuncSetAttribute(k_induce_sym<R, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
-    k_induce_sym<R, O, V><<<ctas, kThreads, smem, st>>>(a);
+    k_induce_sym<R, O><<<ctas, kThreads, smem, st>>>(a);
     UF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -161,20 +161,6 @@ int sym_ctas_max() { return std::max(std::max(sym_ctas(8), sym_ctas(4)), std::ma
 
 int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st) {
     const int ctas = sym_ctas(R);
-    // experiments (R = 8 only): UNSFLOW_SYM_VAR = bit mask of kernel variants, UNSFLOW_RSQRT_ORDER in {4,5,6} = mixed-precision Halley
-    static int var = [] { const char *e = getenv("UNSFLOW_SYM_VAR"); return e ? atoi(e) : 0; }();
-    if (R == 8 && order != 2) {
-        switch (order * 10 + var) {
-            case 31: return launch_sym_one<8, 3, 1>(a, ctas, st);
-            case 32: return launch_sym_one<8, 3, 2>(a, ctas, st);
-            case 33: return launch_sym_one<8, 3, 3>(a, ctas, st);
-            case 34: return launch_sym_one<8, 3, 4>(a, ctas, st);
-            case 38: return launch_sym_one<8, 3, 8>(a, ctas, st);
-            case 40: return launch_sym_one<8, 4, 0>(a, ctas, st);
-            case 60: return launch_sym_one<8, 6, 0>(a, ctas, st);
-            default: break;
-        }
-    }
     if (R == 8) return order == 2 ? launch_sym_one<8, 2>(a, ctas, st) : launch_sym_one<8, 3>(a, ctas, st);
     if (R == 4) return order == 2 ? launch_sym_one<4, 2>(a, ctas, st) : launch_sym_one<4, 3>(a, ctas, st);
     if (R == 2) return order == 2 ? launch_sym_one<2, 2>(a, ctas, st) : launch_sym_one<2, 3>(a, ctas, st);

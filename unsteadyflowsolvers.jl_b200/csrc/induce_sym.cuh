@@ -117,7 +117,6 @@ __device__ __forceinline__ int sym_block_live(const Regions &rg, int nreg, long 
 // row-major upper triangle incl. diagonal: row I starts at I*nb - I*(I-1)/2
 __device__ __forceinline__ long long sym_row_offset(long long I, long long nb) { return I * nb - I * (I - 1) / 2; }
 
-// VAR (experiments, bit mask): 1 = two partial chains per column accumulator, 2 = step loop unrolled by two
 // (I, J) of tile t in the row-major upper-triangle list of nb blocks
 __device__ __forceinline__ void sym_tile_coords(long long t, long long nb, long long *Io, long long *Jo) {
     long long I = (long long)(((2.0 * nb + 1.0) - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
@@ -129,7 +128,31 @@ __device__ __forceinline__ void sym_tile_coords(long long t, long long nb, long 
     *Jo = I + (t - sym_row_offset(I, nb));
 }
 
-template <int R, int ORDER, int VAR = 0>
+// Blocks this CTA will write: one row -> that row block and its column range; several rows -> every block from the
+// first row on.  Zero them in the CTA's own plane (the planes are never memset as a whole) and publish the ranges.
+// Kept out of line so that the prologue does not perturb the register allocation of the pair loops.
+template <int TB>
+__device__ __noinline__ void sym_zero_touched(const Regions &reg, int nreg, long long nb, long long t1, long long I, long long J,
+                                              double *Pu, double *Pw, SymTouch *touch) {
+    long long I1, J1;
+    sym_tile_coords(t1 - 1, nb, &I1, &J1);
+    SymTouch tc;
+    if (I1 > I) tc = SymTouch{I, nb, 0, 0};
+    else tc = SymTouch{I, I + 1, J, J1 + 1};
+    const int tid = threadIdx.x;
+    if (tid == 0) *touch = tc;
+    for (int part = 0; part < 2; part++) {
+        const long long kb = part ? tc.b0 : tc.a0, ke = part ? tc.b1 : tc.a1;
+        for (long long k = kb; k < ke; k++) {
+            if (part && k >= tc.a0 && k < tc.a1) continue;
+            const long long e0 = sym_block_start<TB>(reg, nreg, k);
+            double2 *pu2 = reinterpret_cast<double2 *>(Pu + e0), *pw2 = reinterpret_cast<double2 *>(Pw + e0);
+            for (int c = tid; c < TB / 2; c += kThreads) { pu2[c] = make_double2(0.0, 0.0); pw2[c] = make_double2(0.0, 0.0); }
+        }
+    }
+}
+
+template <int R, int ORDER>
 __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_induce_sym(const SymArgs a) {
     constexpr int TB = kThreads * R, kChunk = TB / (kThreads / 32);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -154,30 +177,12 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
     }
     const long long t0 = u0 / kSymSub, t1 = (u1 + kSymSub - 1) / kSymSub;
 
-    long long I, J, I1, J1;
+    long long I, J;
     sym_tile_coords(t0, nb, &I, &J);
-    sym_tile_coords(t1 - 1, nb, &I1, &J1);
 
     double *Pu = a.P + (long long)blockIdx.x * 2 * a.n;
     double *Pw = Pu + a.n;
-    {
-        // blocks this CTA will write: one row -> that row block and its column range; several rows -> every
-        // block from the first row on.  Zero them (the planes are never memset as a whole) and publish the ranges.
-        SymTouch tc;
-        if (I1 > I) tc = SymTouch{I, nb, 0, 0};
-        else tc = SymTouch{I, I + 1, J, J1 + 1};
-        if (tid == 0) *touch = tc;
-        for (int part = 0; part < 2; part++) {
-            const long long kb = part ? tc.b0 : tc.a0, ke = part ? tc.b1 : tc.a1;
-            for (long long k = kb; k < ke; k++) {
-                if (part && k >= tc.a0 && k < tc.a1) continue;
-                const long long e0 = sym_block_start<TB>(reg, a.nreg, k);
-                double2 *pu2 = reinterpret_cast<double2 *>(Pu + e0), *pw2 = reinterpret_cast<double2 *>(Pw + e0);
-                for (int c = tid; c < TB / 2; c += kThreads) { pu2[c] = make_double2(0.0, 0.0); pw2[c] = make_double2(0.0, 0.0); }
-            }
-        }
-    }
-
+    sym_zero_touched<TB>(reg, a.nreg, nb, t1, I, J, Pu, Pw, touch);
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -212,7 +217,6 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
     double tx[R], tz[R], tg[R], u[R], w[R];
     long long rowI = -1, row_start = 0;
     const double vc4 = a.vc4;
-    const double k375 = fma(vc4, 0.0, 0.375);   // 0.375 as a run-time value: stays in a (uniform) register instead of two MOVs per use
 
     for (long long t = t0; t < t1; t++) {
         const int k = (int)(t - t0), stage = k & 1;
@@ -328,118 +332,48 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
             mbar_wait(&s_bar[stage], (k >> 1) & 1);
             __syncthreads();
             // one phase: warp w works on column chunk (w + p) mod 8, steps [sb, se) of the lane rotation
-            // VAR & 8: every lane works on TWO columns per step (one in each half of the warp's chunk): 2R independent
-            // pair chains per warp instead of R, half as many steps per phase
-            constexpr int kSteps = (VAR & 8) ? kChunk / 2 : kChunk;
-            auto run_phase2 = [&](const int p, const int sb, const int se) {
-                const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
-                int ja = base + ((sb + lane) & (kSteps - 1));
-                double xa = sx[ja], za = sz[ja], ga = sg[ja], xb = sx[ja + kSteps], zb = sz[ja + kSteps], gb = sg[ja + kSteps];
-#pragma unroll 1
-                for (int s = sb; s < se; s++) {
-                    const int jn = base + ((s + 1 + lane) & (kSteps - 1));
-                    const double xan = sx[jn], zan = sz[jn], gan = sg[jn], xbn = sx[jn + kSteps], zbn = sz[jn + kSteps], gbn = sg[jn + kSteps];
-                    double cua = 0.0, cwa = 0.0, cub = 0.0, cwb = 0.0;
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        {
-                            const double dx = xa - tx[r], dz = za - tz[r];
-                            const double d2 = fma(dz, dz, dx * dx);
-                            const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
-                            const double t1v = y * dz, t2v = y * dx;
-                            u[r] = fma(-ga, t1v, u[r]);
-                            w[r] = fma(ga, t2v, w[r]);
-                            cua = fma(tg[r], t1v, cua);
-                            cwa = fma(-tg[r], t2v, cwa);
-                        }
-                        {
-                            const double dx = xb - tx[r], dz = zb - tz[r];
-                            const double d2 = fma(dz, dz, dx * dx);
-                            const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
-                            const double t1v = y * dz, t2v = y * dx;
-                            u[r] = fma(-gb, t1v, u[r]);
-                            w[r] = fma(gb, t2v, w[r]);
-                            cub = fma(tg[r], t1v, cub);
-                            cwb = fma(-tg[r], t2v, cwb);
-                        }
-                    }
-                    double2 acca = s_acc[ja], accb = s_acc[ja + kSteps];
-                    acca.x += cua; acca.y += cwa; accb.x += cub; accb.y += cwb;
-                    s_acc[ja] = acca;
-                    s_acc[ja + kSteps] = accb;
-                    __syncwarp();
-                    ja = jn; xa = xan; za = zan; ga = gan; xb = xbn; zb = zbn; gb = gbn;
-                }
-                __syncthreads();
-            };
             auto run_phase = [&](const int p, const int sb, const int se) {
-                if (VAR & 8) { run_phase2(p, sb, se); return; }
                 const int base = ((warp + p) & (kThreads / 32 - 1)) * kChunk;
-                // one step of the lane rotation: column j (already in registers) against the R rows
-                auto step = [&](const int j, const double xj, const double zj, const double gj) {
-                    double cu = 0.0, cw = 0.0, cu2 = 0.0, cw2 = 0.0;
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const double dx = xj - tx[r], dz = zj - tz[r];
-                        const double d2 = fma(dz, dz, dx * dx);
-                        const double q = fma(d2, d2, vc4);
-                        const double y = (VAR & 4) ? rsqrt_full_lo<ORDER>(q, d2, k375) : rsqrt_full<ORDER>(q);
-                        const double t1v = y * dz, t2v = y * dx;
-                        u[r] = fma(-gj, t1v, u[r]);
-                        w[r] = fma(gj, t2v, w[r]);
-                        if ((VAR & 1) && (r & 1)) {
-                            cu2 = fma(tg[r], t1v, cu2);
-                            cw2 = fma(-tg[r], t2v, cw2);
-                        } else {
-                            cu = fma(tg[r], t1v, cu);
-                            cw = fma(-tg[r], t2v, cw);
-                        }
-                    }
-                    double2 acc = s_acc[j];
-                    if (VAR & 1) { cu += cu2; cw += cw2; }
-                    acc.x += cu;
-                    acc.y += cw;
-                    s_acc[j] = acc;
-                    __syncwarp();   // lane l+1 wrote column j+1 in this step; lane l reads it next step
-                };
                 // software pipeline: the column read for step s+1 is issued before the
                 // accumulator read-modify-write of step s (column data is read-only in a tile)
                 int j = base + ((sb + lane) & (kChunk - 1));
                 double xj = sx[j], zj = sz[j], gj = sg[j];
-                if (VAR & 4) {
-                    // two steps per trip with ping-pong column registers: no loop-carried register copies
-                    // (se - sb is even: phases are cut in units of kUnit steps)
 #pragma unroll 1
-                    for (int s = sb; s < se; s += 2) {
-                        const int jb = base + ((s + 1 + lane) & (kChunk - 1));
-                        const double xb = sx[jb], zb = sz[jb], gb = sg[jb];
-                        step(j, xj, zj, gj);
-                        j = base + ((s + 2 + lane) & (kChunk - 1));
-                        xj = sx[j]; zj = sz[j]; gj = sg[j];
-                        step(jb, xb, zb, gb);
+                for (int s = sb; s < se; s++) {
+                    const int jn = base + ((s + 1 + lane) & (kChunk - 1));
+                    const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
+                    double cu = 0.0, cw = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const double dx = xj - tx[r], dz = zj - tz[r];
+                        const double d2 = fma(dz, dz, dx * dx);
+                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                        const double t1v = y * dz, t2v = y * dx;
+                        u[r] = fma(-gj, t1v, u[r]);
+                        w[r] = fma(gj, t2v, w[r]);
+                        cu = fma(tg[r], t1v, cu);
+                        cw = fma(-tg[r], t2v, cw);
                     }
-                } else {
-#pragma unroll(VAR & 2 ? 2 : 1)
-                    for (int s = sb; s < se; s++) {
-                        const int jn = base + ((s + 1 + lane) & (kChunk - 1));
-                        const double xn = sx[jn], zn = sz[jn], gn = sg[jn];
-                        step(j, xj, zj, gj);
-                        j = jn; xj = xn; zj = zn; gj = gn;
-                    }
+                    double2 acc = s_acc[j];
+                    acc.x += cu;
+                    acc.y += cw;
+                    s_acc[j] = acc;
+                    __syncwarp();   // lane l+1 wrote column j+1 in this step; lane l reads it next step
+                    j = jn; xj = xn; zj = zn; gj = gn;
                 }
                 __syncthreads();
             };
             if (pb == 0 && pe == kSymSub) {
                 // whole tile (the common case): compile-time loop bounds
 #pragma unroll 1
-                for (int p = 0; p < kThreads / 32; p++) run_phase(p, 0, kSteps);
+                for (int p = 0; p < kThreads / 32; p++) run_phase(p, 0, kChunk);
             } else {
                 // first / last tile of this CTA's share: a unit = kUnit consecutive steps of the
                 // (phase, step) sequence of the tile
-                constexpr int kUnit = (kThreads / 32) * kSteps / kSymSub;
+                constexpr int kUnit = (kThreads / 32) * kChunk / kSymSub;
                 const int gs0 = pb * kUnit, gs1 = pe * kUnit;
-                for (int p = gs0 / kSteps; p * kSteps < gs1; p++)
-                    run_phase(p, max(gs0 - p * kSteps, 0), min(gs1 - p * kSteps, kSteps));
+                for (int p = gs0 / kChunk; p * kChunk < gs1; p++)
+                    run_phase(p, max(gs0 - p * kChunk, 0), min(gs1 - p * kChunk, kChunk));
             }
             // flush the column accumulators into this CTA's private plane
             const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);
