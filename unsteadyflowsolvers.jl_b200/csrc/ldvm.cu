@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_lve_solve(const LdvmDev d) {
     lve_solve(d, lve_dyn);
 }
 
-// OCC = member CTAs per SM the register budget is cut for (3: 85 registers, 2: 128)
-template <int OCC>
+// OCC = member CTAs per SM the register budget is cut for (3: 85 registers, 2: 128); UN = independent source chains
+// per thread in the member roll-up and bound sweep (what the register budget lets the compiler keep interleaved)
+template <int OCC, int UN>
 __global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a) {
     extern __shared__ __align__(16) double ens_smem[];
     __shared__ LdvmDev d;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a
     //         [p2u | p2w](groups * ndp each) [solve workspace]
     double *wk = ens_smem, *sm_surf = wk + 5 * tot, *sm_at = sm_surf + 5 * ndp, *sm_p2 = sm_at + 3 * nap;
     double *ws = sm_p2 + 2 * (long long)a.groups * ndp;
-    long long prof[5] = {0, 0, 0, 0, 0};
+    long long prof[6] = {0, 0, 0, 0, 0, 0};      // cycles: head, sweep, solve, roll-up, set-up; [5] = roll-up interactions
     for (;;) {
         long long c0 = clock64();
         __syncthreads();                                  // everyone is done with the previous member's shared state
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a
             c0 = clock64(); prof[0] += c0 - c1;
             if (d.driver != UNSFLOW_DRIVER_LAUTAT) {
                 int S2;
-                ens_sweep(d, sm_p2, sm_p2 + (long long)a.groups * ndp, &S2, wk, tot);
+                ens_sweep<UN>(d, sm_p2, sm_p2 + (long long)a.groups * ndp, &S2, wk, tot);
                 if (tid == 0) d.S2 = S2;
                 __syncthreads();
             }
@@ -129,13 +130,17 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a
             step_solve(d, d.costab, d.sintab, nullptr, ws);
             __syncthreads();
             c0 = clock64(); prof[2] += c0 - c1;
-            ens_rollup(d, wk, tot);
+            ens_rollup<UN>(d, wk, tot);
             c1 = clock64(); prof[3] += c1 - c0;
+            if (a.prof && tid == 0) {
+                const long long nfree = (sst.wake.end[0] - sst.wake.begin[0]) + (sst.wake.end[1] - sst.wake.begin[1]);
+                prof[5] += nfree * (nfree + (sst.wake.end[3] - sst.wake.begin[3]));
+            }
         }
         if (tid == 0) a.st[m] = sst;
     }
     if (a.prof && tid == 0)
-        for (int q = 0; q < 5; q++) a.prof[(long long)blockIdx.x * 8 + q] = prof[q];
+        for (int q = 0; q < 6; q++) a.prof[(long long)blockIdx.x * 8 + q] = prof[q];
 }
 
 }  // namespace unsflow
@@ -956,7 +961,7 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     UF_CUDA(cudaMemcpyAsync(order.p, hord.data(), sizeof(int) * M, cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemsetAsync(next.p, 0, sizeof(int), stream));
     static const int want_occ = [] { const char *e = getenv("UNSFLOW_ENS_OCC"); const int v = e ? atoi(e) : 3; return v == 2 ? 2 : 3; }();
-    auto kern = want_occ == 2 ? k_ensemble<2> : k_ensemble<3>;
+    auto kern = want_occ == 2 ? k_ensemble<2, 8> : k_ensemble<3, 4>;
     UF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSolveThreads, ens_dyn) != cudaSuccess || occ < 1) occ = 1;
@@ -980,11 +985,12 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     if (want_prof) {
         g_batch_prof.assign((size_t)grid * 8, 0);
         UF_CUDA(cudaMemcpy(g_batch_prof.data(), prof.p, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost));
-        long long tot_c[5] = {0, 0, 0, 0, 0};
+        long long tot_c[6] = {0, 0, 0, 0, 0, 0};
         for (int c = 0; c < grid; c++)
-            for (int q = 0; q < 5; q++) tot_c[q] += g_batch_prof[(size_t)c * 8 + q];
-        fprintf(stderr, "[unsflow ensemble profile] grid %d (occupancy %d/SM), %.3f ms; cycles per CTA (mean): head %.3e sweep %.3e solve %.3e rollup %.3e setup %.3e\n",
-                grid, occ, g_batch_ms, (double)tot_c[0] / grid, (double)tot_c[1] / grid, (double)tot_c[2] / grid, (double)tot_c[3] / grid, (double)tot_c[4] / grid);
+            for (int q = 0; q < 6; q++) tot_c[q] += g_batch_prof[(size_t)c * 8 + q];
+        fprintf(stderr, "[unsflow ensemble profile] grid %d (occupancy %d/SM), %.3f ms; cycles per CTA (mean): head %.3e sweep %.3e solve %.3e rollup %.3e setup %.3e; roll-up interactions %.4e total = %.3f per CTA-cycle in the roll-up phase\n",
+                grid, occ, g_batch_ms, (double)tot_c[0] / grid, (double)tot_c[1] / grid, (double)tot_c[2] / grid, (double)tot_c[3] / grid, (double)tot_c[4] / grid,
+                (double)tot_c[5], (double)tot_c[5] / (double)tot_c[3]);
     }
     for (int64_t m = 0; m < M; m++) {
         double *mo = mat_out + m * nsteps * 8;

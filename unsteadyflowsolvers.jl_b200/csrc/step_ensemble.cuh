@@ -40,7 +40,6 @@ __host__ __device__ inline long long ens_smem_doubles(int nd, int na, long long 
 }
 
 
-constexpr int kEnsR = 4;        // targets per thread in the member roll-up
 
 // pair kernel shared by the two block-level induction loops (13 FP64 instr, cubic rsqrt)
 __device__ __forceinline__ void pair_acc(double xj, double zj, double gj, double vc4, double tx, double tz, double &u, double &w) {
@@ -53,9 +52,10 @@ __device__ __forceinline__ void pair_acc(double xj, double zj, double gj, double
 }
 
 // update_indbound (calcs.jl:35-38) inside one CTA: group g of threads owns sources j = g (mod G);
-// 2 independent source chains per thread
+// kEnsUnroll independent source chains per thread
 // (sm = the member's shared-memory slabs [x | z | g | vx | vz], each `tot` long: passed as a raw
 // shared pointer so the loops compile to LDS instead of generic loads)
+template <int kEnsUnroll>
 __device__ __forceinline__ void ens_sweep(const LdvmDev &d, double *p2u, double *p2w, int *S2_out, const double *sm, long long tot) {
     const double *wx = sm, *wz = sm + tot, *wg = sm + 2 * tot;
     const StepState *s = d.st;
@@ -65,74 +65,87 @@ __device__ __forceinline__ void ens_sweep(const LdvmDev &d, double *p2u, double 
     const double vc4 = d.vc4_new;
     if (act) {
         const double tx = d.bnd_x[i], tz = d.bnd_z[i];
-        double u0 = 0.0, w0 = 0.0, u1 = 0.0, w1 = 0.0;
+        double u[kEnsUnroll], w[kEnsUnroll];
+#pragma unroll
+        for (int q = 0; q < kEnsUnroll; q++) { u[q] = 0.0; w[q] = 0.0; }
         for (int r = 0; r < 3; r++) {
-            const long long e = s->wake.end[r];
-            long long j = s->wake.begin[r] + grp;
-            for (; j + G < e; j += 2 * G) {
-                pair_acc(wx[j], wz[j], wg[j], vc4, tx, tz, u0, w0);
-                pair_acc(wx[j + G], wz[j + G], wg[j + G], vc4, tx, tz, u1, w1);
+            const int e = (int)s->wake.end[r];
+            int j = (int)s->wake.begin[r] + grp;
+            for (; j + (kEnsUnroll - 1) * G < e; j += kEnsUnroll * G) {
+#pragma unroll
+                for (int q = 0; q < kEnsUnroll; q++) pair_acc(wx[j + q * G], wz[j + q * G], wg[j + q * G], vc4, tx, tz, u[q], w[q]);
             }
-            if (j < e) pair_acc(wx[j], wz[j], wg[j], vc4, tx, tz, u0, w0);
+#pragma unroll
+            for (int q = 0; q < kEnsUnroll - 1; q++)      // remainder, static accumulator indices
+                if (j + q * G < e) pair_acc(wx[j + q * G], wz[j + q * G], wg[j + q * G], vc4, tx, tz, u[q], w[q]);
         }
-        p2u[grp * d.p2stride + i] = u0 + u1;
-        p2w[grp * d.p2stride + i] = w0 + w1;
+        double su = 0.0, sw = 0.0;
+#pragma unroll
+        for (int q = 0; q < kEnsUnroll; q++) { su += u[q]; sw += w[q]; }
+        p2u[grp * d.p2stride + i] = su;
+        p2w[grp * d.p2stride + i] = sw;
     }
     *S2_out = G;
 }
 
-// one chunk of RR*blockDim targets of region tr against all sources (free + bound vortices);
-// velocities go to vx, vz -- positions are convected only after every chunk is done
-template <int RR>
-__device__ __forceinline__ void ens_rollup_chunk(const LdvmDev &d, const StepState *s, int tr, long long tb, double *sm, long long tot) {
+// Free vortices of the member as ONE index space: virtual index v in [0, nt + nl) -> slab index (TEV slab first,
+// then the LEV slab; members have no external vortices), so a short LEV family does not get a pass of its own.
+struct EnsIndex {
+    long long tb, nt, lb, nl;
+    __device__ __forceinline__ long long phys(long long v) const { return v < nt ? tb + v : lb + (v - nt); }
+};
+
+// One pass of the member roll-up: ONE target per thread (virtual index v0 + t) against all sources (free + bound
+// vortices) with UN INDEPENDENT source chains per thread (UN accumulator pairs, added in a fixed order at the end).
+// The pair chain is 13 dependent FP64 instructions of ~8 cycles each: a member CTA only keeps the FP64 pipe busy if
+// every thread has several pairs in flight, and with the register budget of a 3-CTA-per-SM kernel the compiler only
+// interleaves chains that are this cheap to keep live (one target, UN sources).
+template <int UN>
+__device__ __forceinline__ void ens_rollup_pass(const LdvmDev &d, const StepState *s, const EnsIndex ix, long long v0, long long v1, double *sm, long long tot) {
     const double *wx = sm, *wz = sm + tot, *wg = sm + 2 * tot;
     double *wvx = sm + 3 * tot, *wvz = sm + 4 * tot;
-    const long long tend = s->wake.end[tr];
-    if (tb + (threadIdx.x & ~31) >= tend) return;      // warps without a single live target
+    const long long v = v0 + threadIdx.x;
+    if (v0 + (threadIdx.x & ~31) >= v1) return;      // warps without a single live target in this pass
+    const bool ok = v < v1;
+    const long long pi = ok ? ix.phys(v) : 0;
     const double vc4 = d.vc4_new;
-    double tx[RR], tz[RR], u[RR], w[RR];
+    const double tx = ok ? wx[pi] : 0.0, tz = ok ? wz[pi] : 0.0;
+    double u[UN], w[UN];
 #pragma unroll
-    for (int r = 0; r < RR; r++) {
-        const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
-        const bool ok = i < tend;
-        tx[r] = ok ? wx[i] : 0.0; tz[r] = ok ? wz[i] : 0.0; u[r] = 0.0; w[r] = 0.0;
-    }
+    for (int q = 0; q < UN; q++) { u[q] = 0.0; w[q] = 0.0; }
     for (int sr = 0; sr < 4; sr++) {
-        const long long b = s->wake.begin[sr], e = s->wake.end[sr];
-#pragma unroll 2
-        for (long long j = b; j < e; j++) {
-            const double xj = wx[j], zj = wz[j], gj = wg[j];      // broadcast shared-memory reads
+        const int b = (int)s->wake.begin[sr], e = (int)s->wake.end[sr];
+        int j = b;
+        for (; j + UN <= e; j += UN) {
 #pragma unroll
-            for (int r = 0; r < RR; r++) pair_acc(xj, zj, gj, vc4, tx[r], tz[r], u[r], w[r]);
+            for (int q = 0; q < UN; q++) pair_acc(wx[j + q], wz[j + q], wg[j + q], vc4, tx, tz, u[q], w[q]);      // broadcast shared-memory reads
         }
+#pragma unroll
+        for (int q = 0; q < UN - 1; q++)      // remainder with STATIC accumulator indices (a dynamic one would push u[], w[] to local memory)
+            if (j + q < e) pair_acc(wx[j + q], wz[j + q], wg[j + q], vc4, tx, tz, u[q], w[q]);
     }
+    double su = 0.0, sw = 0.0;
 #pragma unroll
-    for (int r = 0; r < RR; r++) {
-        const long long i = tb + threadIdx.x + (long long)r * blockDim.x;
-        if (i < tend) {
-            wvx[i] = u[r] * kInvTwoPi + s->fs[0];      // calcs.jl:252-277
-            wvz[i] = w[r] * kInvTwoPi + s->fs[1];
-        }
+    for (int q = 0; q < UN; q++) { su += u[q]; sw += w[q]; }
+    if (ok) {
+        wvx[pi] = su * kInvTwoPi + s->fs[0];      // calcs.jl:252-277
+        wvz[pi] = sw * kInvTwoPi + s->fs[1];
     }
 }
 
 // wakeroll (calcs.jl:222-294) inside one CTA
+template <int kEnsUnroll>
 __device__ __forceinline__ void ens_rollup(const LdvmDev &d, double *sm, long long tot) {
     StepState *s = d.st;
-    for (int tr = 0; tr < 3; tr++) {
-        for (long long tb = s->wake.begin[tr]; tb < s->wake.end[tr]; tb += (long long)kEnsR * blockDim.x) {
-            const long long rem = s->wake.end[tr] - tb;
-            const int nrow = (int)min((long long)kEnsR, (rem + blockDim.x - 1) / blockDim.x);   // block-uniform
-            switch (nrow) {
-                case 1: ens_rollup_chunk<1>(d, s, tr, tb, sm, tot); break;
-                case 2: ens_rollup_chunk<2>(d, s, tr, tb, sm, tot); break;
-                case 3: ens_rollup_chunk<3>(d, s, tr, tb, sm, tot); break;
-                default: ens_rollup_chunk<4>(d, s, tr, tb, sm, tot); break;
-            }
-        }
-    }
+    EnsIndex ix;
+    ix.tb = s->wake.begin[0]; ix.nt = s->wake.end[0] - ix.tb;
+    ix.lb = s->wake.begin[1]; ix.nl = s->wake.end[1] - ix.lb;
+    const long long N = ix.nt + ix.nl;
+    // passes of blockDim targets: the last, partly filled one runs with one warp per scheduler and finishes sooner
+    // (equal-size passes were measured slower: the pass time follows the scheduler with the most warps)
+    for (long long v0 = 0; v0 < N; v0 += blockDim.x) ens_rollup_pass<kEnsUnroll>(d, s, ix, v0, min(N, v0 + (long long)blockDim.x), sm, tot);
     __syncthreads();
-    for (int tr = 0; tr < 3; tr++)                                // calcs.jl:280-291
+    for (int tr = 0; tr < 2; tr++)                                // calcs.jl:280-291
         for (long long i = s->wake.begin[tr] + threadIdx.x; i < s->wake.end[tr]; i += blockDim.x) {
             sm[i] += d.dt * sm[3 * tot + i];
             sm[tot + i] += d.dt * sm[4 * tot + i];
