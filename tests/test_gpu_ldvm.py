@@ -552,7 +552,8 @@ def test_500_step_attached_history(gpu_lib, uf, oracle, mode):
     err = np.max(np.abs(mat[:, 5:8] - omat[:, 5:8]))
     assert err <= HTOL, err
     assert err < (1e-11 if mode == 0 else 1e-9)      # measured 2.4e-14 / 1.8e-11 (NLsolve mode: the finite-difference Jacobian
-    _cmp_state(surf, fld, sim, tol=1e-9 if mode == 0 else 1e-8)   # of eps = 6e-6 leaves the iterate defined to ~1e-13 only)
+    _cmp_state(surf, fld, sim, tol=1e-9 if mode == 0 else 1e-7)   # of eps = 6e-6 leaves the iterate defined to ~1e-13 only;
+    # the newest TEV sits 0.005c from its neighbour, so a 1e-10 difference in its strength is 3e-8 in their velocities)
 
 
 def test_randomised_configurations_against_oracle(gpu_lib, uf, oracle):
