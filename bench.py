@@ -398,6 +398,7 @@ def main():
             try:
                 if nranks > 1:
                     hh.set_parallel(rank, nranks, new_uid())
+                    extra["ldvm_exchange"] = "NVLink peer memory (fused finish + exchange kernel)" if hh.parallel_info()[2] else "NCCL all-reduce"
                 if twodof:
                     hh.set_2dof(*twodof)
                 hh.set_kinematics(uf.kinematics_table(surf, fld, ns + warm, dtstar, two_dof=twodof is not None))

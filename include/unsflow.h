@@ -181,6 +181,10 @@ int unsflow_ldvm_set_kinematics(unsflow_ldvm *h, int64_t nrows, const double *ta
  * replicated bit-identically, so every rank returns the same mat and state.  nccl_unique_id:
  * 128 bytes from unsflow_nccl_unique_id() of rank 0.  Needs a uniform core radius. */
 int unsflow_ldvm_set_parallel(unsflow_ldvm *h, int rank, int nranks, const void *nccl_unique_id);
+/* rank / nranks of the handle and whether the step exchanges through NVLink peer memory (1: the ranks' buffers are
+ * mapped into each other with CUDA IPC and one fused kernel sums the partial velocities, convects and writes every
+ * rank's slabs; 0: NCCL all-reduce -- taken by all ranks when the mapping could not be set up on one of them) */
+int unsflow_ldvm_parallel_info(unsflow_ldvm *h, int *rank, int *nranks, int *peer_exchange);
 /* TwoDOFPar (typedefs.jl:178-190, 11 doubles in field order) and KinemPar2DOF
  * (typedefs.jl:193-220, 22 doubles in field order) for ldvm2DOF */
 int unsflow_ldvm_set_2dof(unsflow_ldvm *h, const double *strpar11, const double *kinem22);

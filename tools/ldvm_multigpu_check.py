@@ -46,6 +46,7 @@ nsteps = int(os.environ.get("MG_STEPS", 20))
 surf, fld, dtstar = make(nw)
 h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, nsteps + 3, uf.delNone(), None))
 h.set_parallel(rank, world, uid)
+peer = h.parallel_info()[2]
 h.set_kinematics(uf.kinematics_table(surf, fld, nsteps + 3, dtstar))
 m0 = h.run(3)
 dist.barrier()
@@ -72,7 +73,7 @@ if rank == 0:
     h1.close()
     dm = float(np.max(np.abs(mat - mat1)))
     dx = float(np.max(np.abs(fld.tev.x - f1.tev.x)))
-    print(f"ranks {world} N {nw}: bit-identical across ranks {same}; vs single GPU max|dmat| {dm:.2e} max|dx| {dx:.2e}; "
+    print(f"ranks {world} N {nw} (exchange: {'NVLink peer memory, fused finish' if peer else 'NCCL all-reduce'}): bit-identical across ranks {same}; vs single GPU max|dmat| {dm:.2e} max|dx| {dx:.2e}; "
           f"{nsteps} steps: {tm.item():.1f} ms on {world} GPUs ({nsteps / tm.item() * 1e3:.1f} steps/s) vs {ms1:.1f} ms on 1 "
           f"({nsteps / ms1 * 1e3:.1f} steps/s), speed-up {ms1 / tm.item():.2f}")
     assert same and dm <= 1e-10 and dx <= 1e-12

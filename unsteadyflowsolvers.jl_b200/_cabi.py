@@ -108,6 +108,7 @@ def lib():
         "unsflow_lve_get_circ": [vp, d, d],
         "unsflow_ldvm_set_kinematics": [vp, i64, d],
         "unsflow_ldvm_set_parallel": [vp, C.c_int, C.c_int, vp],
+        "unsflow_ldvm_parallel_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "unsflow_ldvm_set_2dof": [vp, d, d],
         "unsflow_ldvm_get_2dof": [vp, d],
         "unsflow_ldvm_run": [vp, i64, d],

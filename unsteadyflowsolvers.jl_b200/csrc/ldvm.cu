@@ -17,6 +17,7 @@
 #include "induce_sym.cuh"
 #include "sweep.cuh"
 #include "nccl_dl.h"
+#include "peer.cuh"
 #include "runtime.h"
 #include <algorithm>
 #include <cmath>
@@ -189,7 +190,8 @@ struct unsflow_ldvm {
     // multi-GPU: pair tiles of the roll-up split over ranks, everything else replicated bit-identically
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
-    DevBuf<double> vsum;      // [2][tot] raw plane sums exchanged by all-reduce
+    DevBuf<double> vsum;      // [2][tot] raw plane sums exchanged by all-reduce / read by the peers
+    PeerGroup peer;           // NVLink peer mapping of vsum and the wake slabs (fused finish + exchange)
     // CUDA-graph cache for the launch-bound regime
     cudaGraphExec_t gexec = nullptr;
     int64_t gkey_t = -1, gkey_l = -1;
@@ -207,6 +209,17 @@ extern "C" {
 int unsflow_ldvm_destroy(unsflow_ldvm *h) {
     if (!h) return 0;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->peer.ready) {
+        // nobody may unmap / free while a peer kernel can still touch the memory: barrier, then close the imports,
+        // then a host-side rendezvous over NCCL before the exported buffers are freed
+        launch_peer_barrier(&h->peer, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    peer_destroy(&h->peer);
+    if (h->comm && nccl_api() && h->vsum.p && h->nranks > 1) {
+        nccl_api()->AllReduce(h->vsum.p, h->vsum.p, 1, ncclDouble, ncclSum, h->comm, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
     if (h->comm && nccl_api()) nccl_api()->CommDestroy(h->comm);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -507,6 +520,10 @@ int unsflow_ldvm_set_parallel(unsflow_ldvm *h, int rank, int nranks, const void 
     if (h->vsum.alloc(2 * h->tot) || h->vsum.zero(h->stream)) return 2;
     UF_CUDA(cudaStreamSynchronize(h->stream));
     h->rank = rank; h->nranks = nranks;
+    // NVLink peer mapping for the fused finish + exchange; when it cannot be set up on every rank the step keeps
+    // the NCCL all-reduce (both are GPU paths; all ranks take the same one)
+    void *bufs[kPeerBufs] = {h->vsum.p, h->wake.p};
+    if (int rc = peer_setup(&h->peer, h->comm, h->stream, rank, nranks, bufs)) return rc;
     return 0;
 }
 
@@ -617,8 +634,22 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         // convection.  The all-reduce returns identical bits on every rank, so the replicated state stays in lockstep.
         fs.raw = 1; fs.packed = 1; fs.packed_stride = nwake_ub; fs.vx = h->vsum.p;
         if (int rc = launch_sym_finish(fs, nwake_ub, st)) return rc;
+        if (h->peer.ready) {
+            // fused finish + exchange over NVLink peer memory: barrier (all partial sums written) -> every rank sums,
+            // convects and broadcasts ITS slice of the vortices into all ranks' slabs -> barrier (all slabs complete)
+            if (int rc = launch_peer_barrier(&h->peer, st)) return rc;
+            PeerFinishArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.reg = &h->st.p->wake; pa.nreg = 3; pa.rank = h->rank; pa.nranks = h->nranks; pa.stride = nwake_ub;
+            for (int q = 0; q < h->nranks; q++) { pa.sums[q] = (const double *)h->peer.bufs[q][0]; pa.slab[q] = (double *)h->peer.bufs[q][1]; }
+            pa.off_x = 0; pa.off_z = tot; pa.off_vx = 5 * tot; pa.off_vz = 6 * tot;
+            pa.fs = h->st.p->fs; pa.dt = h->opts.dt;
+            if (int rc = launch_peer_finish(pa, nwake_ub, st)) return rc;
+            if (int rc = launch_peer_barrier(&h->peer, st)) return rc;
+            h->launches += 5;
+            return 0;
+        }
         const NcclApi *nc = nccl_api();
-        if (!nc) return 4;
         if (nc->AllReduce(h->vsum.p, h->vsum.p, (size_t)(2 * nwake_ub), ncclDouble, ncclSum, h->comm, st) != ncclSuccess) { set_error("ncclAllReduce failed"); return 4; }
         FinishArgs f2;
         memset(&f2, 0, sizeof(f2));
@@ -746,6 +777,7 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
     for (int64_t i = 0; i < nsteps; i++)
         for (int j = 0; j < mc; j++) mat_out[i + j * nsteps] = hm[(size_t)(mc * i + j)];
     UF_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (int rc = peer_check(&h->peer, st)) return rc;
     // exact counts are known now
     StepState s;
     if (int rc = ldvm_sync_counts(h, &s)) return rc;
@@ -825,6 +857,14 @@ int unsflow_ldvm_get_state(unsflow_ldvm *h, unsflow_surf *sf, unsflow_field *fl)
 
 int unsflow_ldvm_multi_get_state(unsflow_ldvm *h, int32_t nsurf, unsflow_surf *surfs, unsflow_field *fl) {
     return ldvm_get_state_impl(h, nsurf, surfs, fl);
+}
+
+int unsflow_ldvm_parallel_info(unsflow_ldvm *h, int *rank, int *nranks, int *peer_exchange) {
+    UF_CHECK(h != nullptr, "unsflow_ldvm_parallel_info: null handle");
+    if (rank) *rank = h->rank;
+    if (nranks) *nranks = h->nranks;
+    if (peer_exchange) *peer_exchange = h->peer.ready ? 1 : 0;
+    return 0;
 }
 
 int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {

@@ -105,6 +105,12 @@ class LdvmHandle:
         """unsflow_ldvm_set_parallel: split the roll-up pair tiles over `nranks` GPUs (one process each)"""
         cabi.check(cabi.lib().unsflow_ldvm_set_parallel(self._h, rank, nranks, nccl_unique_id))
 
+    def parallel_info(self):
+        """(rank, nranks, peer_exchange): peer_exchange = 1 when the step exchanges through NVLink peer memory"""
+        a, b, c = C.c_int(0), C.c_int(1), C.c_int(0)
+        cabi.check(cabi.lib().unsflow_ldvm_parallel_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def set_2dof(self, strpar: TwoDOFPar, kinem: KinemPar2DOF):
         a, b = strpar.as_array(), kinem.as_array()
         cabi.check(cabi.lib().unsflow_ldvm_set_2dof(self._h, cabi.dptr(a), cabi.dptr(b)))
