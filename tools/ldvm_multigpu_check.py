@@ -76,6 +76,6 @@ if rank == 0:
     print(f"ranks {world} N {nw} (exchange: {'NVLink peer memory, fused finish' if peer else 'NCCL all-reduce'}): bit-identical across ranks {same}; vs single GPU max|dmat| {dm:.2e} max|dx| {dx:.2e}; "
           f"{nsteps} steps: {tm.item():.1f} ms on {world} GPUs ({nsteps / tm.item() * 1e3:.1f} steps/s) vs {ms1:.1f} ms on 1 "
           f"({nsteps / ms1 * 1e3:.1f} steps/s), speed-up {ms1 / tm.item():.2f}")
-    assert same and dm <= 1e-10 and dx <= 1e-12
+    assert same and dm <= 1e-9 and dx <= 1e-12 * max(1.0, float(np.max(np.abs(f1.tev.x)))), (same, dm, dx)
 dist.barrier()
 dist.destroy_process_group()

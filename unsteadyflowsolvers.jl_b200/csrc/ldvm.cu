@@ -549,16 +549,39 @@ static void step_bounds(const unsflow_ldvm *h, int64_t ahead, int64_t *ntev_ub, 
     *nlev_ub = std::min(h->cap_l, h->known_nlev_end + since);
 }
 
+// UNSFLOW_STEP_TRACE=1: CUDA events between the launches of the LAST non-graph step of a run; the segment times are
+// printed to stderr by unsflow_ldvm_run (names the segments of a step, also on several ranks where ncu cannot go)
+static bool step_trace_enabled() {
+    static bool v = [] { const char *e = getenv("UNSFLOW_STEP_TRACE"); return e && atoi(e) != 0; }();
+    return v;
+}
+struct StepTrace {
+    cudaEvent_t ev[12] = {};
+    const char *name[12] = {};
+    int n = 0;
+    bool armed = false;
+    void mark(const char *nm, cudaStream_t st) {
+        if (!armed || n >= 12) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        name[n++] = nm;
+    }
+};
+static thread_local StepTrace g_trace;
+
 // one time step = 5 launches on the handle's stream (also used under stream capture)
 static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaStream_t st) {
     const int driver = h->opts.driver, smc = sm_count(), order = rsqrt_order();
     const int64_t tot = h->tot, nwake_ub = ntev_ub + nlev_ub + h->nextv;
     const bool multi = h->nsurf > 1;
     const bool lve = driver == UNSFLOW_DRIVER_LVE_INTERNAL;
+    g_trace.n = 0;
+    g_trace.mark("start", st);
     if (lve) k_lve_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     else if (multi) k_mstep_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     else k_step_head<<<1, kSolveThreads, 0, st>>>(h->dev);
     h->launches++;
+    g_trace.mark("head", st);
     if (driver != UNSFLOW_DRIVER_LAUTAT) {
         // bound-point sweep (update_indbound, calcs.jl:35-38): targets = bound points
         InducePlan p2 = plan_induce((long long)h->ndiv * h->nsurf, 1, nwake_ub, 3, smc, h->S2max);
@@ -580,6 +603,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         }
         h->dev.S2 = p2.S;
         h->launches++;
+        g_trace.mark("sweep", st);
     }
     if (lve) k_lve_solve<<<1, kSolveThreads, sizeof(double) * h->ndiv * h->ndiv, st>>>(h->dev);
     else if (multi) k_mstep_solve<<<1, kSolveThreads, 0, st>>>(h->dev);
@@ -599,6 +623,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         k_step_solve<<<1, kSolveThreads, dyn, st>>>(h->dev, in_smem);
     }
     h->launches++;
+    g_trace.mark("solve", st);
     // wake roll-up (calcs.jl:222-294): targets = free vortices, sources = free + bound
     const bool sym = h->uniform && nwake_ub >= sym_threshold();
     InducePlan p1 = plan_induce(nwake_ub, 3, nwake_ub + (long long)h->nsurf * (h->ndiv - 1), 4, smc, h->S1max);
@@ -617,6 +642,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         sa.reg = &h->st.p->wake; sa.nreg = 3; sa.bv_reg = 3;
         sa.vc4 = h->vc4u; sa.P = h->planes.p; sa.n = tot; sa.rank = h->rank; sa.nranks = h->nranks;
         if (int rc = launch_induce_sym(sa, symR, order, st)) return rc;
+        g_trace.mark("pair tiles", st);
         // sum of the planes that touched each block (+ 1/2pi, free stream, explicit Euler when single-rank)
         SymFinishArgs fs;
         memset(&fs, 0, sizeof(fs));
@@ -626,6 +652,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         fs.fs = h->st.p->fs; fs.dt = h->opts.dt;
         if (h->nranks == 1) {
             if (int rc = launch_sym_finish(fs, nwake_ub, st)) return rc;
+            g_trace.mark("finish", st);
             h->launches += 2;
             return 0;
         }
@@ -634,6 +661,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         // convection.  The all-reduce returns identical bits on every rank, so the replicated state stays in lockstep.
         fs.raw = 1; fs.packed = 1; fs.packed_stride = nwake_ub; fs.vx = h->vsum.p;
         if (int rc = launch_sym_finish(fs, nwake_ub, st)) return rc;
+        g_trace.mark("plane sums", st);
         if (h->peer.ready) {
             // fused finish + exchange over NVLink peer memory: barrier (all partial sums written) -> every rank sums,
             // convects and broadcasts ITS slice of the vortices into all ranks' slabs -> barrier (all slabs complete)
@@ -646,6 +674,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
             pa.fs = h->st.p->fs; pa.dt = h->opts.dt;
             if (int rc = launch_peer_finish(pa, nwake_ub, st)) return rc;
             if (int rc = launch_peer_barrier(&h->peer, st)) return rc;
+            g_trace.mark("peer exchange", st);
             h->launches += 5;
             return 0;
         }
@@ -658,6 +687,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         f2.vx = h->dev.wvx; f2.vz = h->dev.wvz; f2.x = h->dev.wx; f2.z = h->dev.wz;
         f2.fs = h->st.p->fs; f2.dt = h->opts.dt;
         if (int rc = launch_induce_finish(f2, nwake_ub, st)) return rc;
+        g_trace.mark("all-reduce + finish", st);
         h->launches += 3;
         return 0;
     }
@@ -669,6 +699,7 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
     f.vx = h->dev.wvx; f.vz = h->dev.wvz; f.x = h->dev.wx; f.z = h->dev.wz;
     f.fs = h->st.p->fs; f.dt = h->opts.dt;
     if (int rc = launch_induce_finish(f, nwake_ub, st)) return rc;
+    g_trace.mark("roll-up + finish", st);
     h->launches += 2;
     return 0;
 }
@@ -743,7 +774,9 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         } else {
             step_bounds(h, 1, &tev_ub, &lev_ub);
             if (int rc = ensure_planes(h, tev_ub + lev_ub + h->nextv)) return rc;
+            g_trace.armed = step_trace_enabled() && is == nsteps - 1;
             if (int rc = enqueue_step(h, tev_ub, lev_ub, st)) return rc;
+            g_trace.armed = false;
             UF_CUDA(cudaGetLastError());
             h->steps_done++;
             is++;
@@ -778,6 +811,16 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         for (int j = 0; j < mc; j++) mat_out[i + j * nsteps] = hm[(size_t)(mc * i + j)];
     UF_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (int rc = peer_check(&h->peer, st)) return rc;
+    if (step_trace_enabled() && g_trace.n > 1) {
+        fprintf(stderr, "[unsflow step trace] rank %d/%d last step:", h->rank, h->nranks);
+        for (int k = 1; k < g_trace.n; k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, g_trace.ev[k - 1], g_trace.ev[k]);
+            fprintf(stderr, " %s %.1f us;", g_trace.name[k], 1e3 * ms);
+        }
+        fprintf(stderr, "\n");
+        g_trace.n = 0;
+    }
     // exact counts are known now
     StepState s;
     if (int rc = ldvm_sync_counts(h, &s)) return rc;
