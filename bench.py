@@ -362,8 +362,8 @@ def main():
                 tb = uf.kinematics_table(sf, uf.TwoDFlowField(), ens_steps, 0.015)
                 for lc in np.linspace(0.05, 0.35, nl):
                     tabs.append(tb); lesp.append(float(lc))
-            mine = slice(rank, None, world)
-            mats, ntev, nlev, ems = uf.ldvm_batch(base, np.array(tabs[mine]), np.array(lesp[mine]), 0.015)
+            mine = uf.ensemble_shard(np.array(tabs), lesp, rank, world)      # cost-balanced deal of the members over the ranks
+            mats, ntev, nlev, ems = uf.ldvm_batch(base, np.array(tabs)[mine], np.array(lesp)[mine], 0.015)
             tm = torch.tensor([ems], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)

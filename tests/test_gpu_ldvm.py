@@ -299,6 +299,41 @@ def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):
     assert nlev.max() > 10 and nlev.min() == 0
 
 
+@pytest.mark.parametrize("threads,sym,occ", [("256", "0", "3"), ("256", "0", "2"), ("256", "3", "3"), ("256", "4", "2"), ("256", "2", "3"),
+                                             ("512", "4", "1"), ("1024", "2", "1")])
+def test_ensemble_long_members_every_kernel_variant(gpu_lib, uf, oracle, threads, sym, occ):
+    """member wakes of 1150 vortices against the oracle for every variant of the member kernel: the default one-sided
+    roll-up at 3 and 2 CTAs per SM, and the opt-in pair-symmetric roll-up (step_ensemble.cuh: 2-4 rows per lane, odd
+    and even super-block counts, two rounds of super-blocks once 1150 > 8 warps x 128) at every member CTA width --
+    attached flow, so the history can be followed free-running (H2)"""
+    import subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent("""
+        import sys, os, math, numpy as np
+        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+        import unsflow_b200 as uf
+        nsteps, dtstar = 1150, 0.015
+        tabs, lc = [], []
+        for k, amp in ((0.2, 5.0), (0.6, 3.0)):
+            kin = uf.KinemDef(uf.SinDef(0.0, amp * math.pi / 180, k, 0.0), uf.ConstDef(0.0), uf.ConstDef(1.0))
+            surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [10.0])
+            tabs.append(uf.kinematics_table(surf, uf.TwoDFlowField(), nsteps, dtstar)); lc.append(10.0)
+        mats, ntev, nlev, ms = uf.ldvm_batch(surf, np.array(tabs), np.array(lc), dtstar, solve_mode=uf._cabi.SOLVE_EXACT)
+        np.savez(sys.argv[1], mats=mats, tabs=np.array(tabs), ntev=ntev, nlev=nlev)
+    """)
+    f = tempfile.mktemp(suffix=".npz")
+    env = dict(os.environ, UNSFLOW_ENS_THREADS=threads, UNSFLOW_ENS_SYM=sym, UNSFLOW_ENS_OCC=occ)
+    subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+    out = np.load(f)
+    nsteps, dtstar = 1150, 0.015
+    assert np.all(out["ntev"] == nsteps) and np.all(out["nlev"] == 0)
+    for m, (k, amp) in enumerate(((0.2, 5.0), (0.6, 3.0))):
+        kin = uf.KinemDef(uf.SinDef(0.0, amp * math.pi / 180, k, 0.0), uf.ConstDef(0.0), uf.ConstDef(1.0))
+        surf = uf.TwoDSurf("FlatPlate", 0.25, kin, [10.0])
+        sim = oracle.Sim(surf, uf.TwoDFlowField())
+        omat = sim.run(oracle.DRIVER_LDVM, out["tabs"][m], dtstar, solver_mode=oracle.SOLVER_EXACT)
+        assert np.max(np.abs(out["mats"][m] - omat)) <= HTOL, (m, threads, sym, occ)
+
+
 def test_write_stamps_from_device_snapshots(gpu_lib, uf, oracle, tmp_path, monkeypatch):
     """writeflag = 1: the write schedule of solvers.jl:164-175 and the `Step Files/<t>/...`
     layout of postprocess.jl:34-113, produced from device snapshots; the VALUES of every step file

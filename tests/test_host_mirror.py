@@ -106,3 +106,22 @@ def test_eldupint_motion_definitions(uf):
     tab = uf.kinematics_table(surf, uf.TwoDFlowField(), 100, 0.015 * 2.0 / 1.5)
     t = tab[-1, 0]
     assert abs(tab[-1, 2] - kin.h(t) * 2.0) < 1e-15 and abs(tab[-1, 4] - kin.h.deriv(t) * 1.5) < 1e-15 and tab[-1, 2] > 0
+
+
+def test_ensemble_shard_is_a_balanced_partition():
+    """ensemble_shard deals the members over the ranks: every member exactly once, shard sizes within one, and the
+    expensive members (low LESPcrit, fast pitching) spread evenly instead of all landing on rank 0"""
+    import unsflow_b200 as uf
+    rng = np.random.default_rng(3)
+    nm, ns = 101, 40
+    tables = np.zeros((nm, ns, 9))
+    tables[:, :, 5] = 1.0
+    tables[:, :, 1] = rng.uniform(0.0, 0.4, (nm, 1)) * np.sin(np.linspace(0, 6, ns))[None, :]
+    lesp = rng.uniform(0.05, 0.4, nm)
+    for world in (1, 2, 4, 8):
+        parts = [uf.ensemble_shard(tables, lesp, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(nm))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        score = np.max(np.abs(tables[:, :, 1]), axis=1) / lesp
+        top = set(np.argsort(-score)[:world].tolist())
+        assert all(len(top & set(p.tolist())) == 1 for p in parts)

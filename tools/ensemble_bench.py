@@ -11,6 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unsflow_b200 as uf
 
+if "LOCAL_RANK" in os.environ:
+    uf._cabi.check(uf._cabi.lib().unsflow_set_device(int(os.environ["LOCAL_RANK"])))
 nk = int(os.environ.get("ENS_NK", 64))
 nl = int(os.environ.get("ENS_NL", 64))
 nsteps = int(os.environ.get("ENS_STEPS", 500))
@@ -26,7 +28,11 @@ for k in np.linspace(0.05, 1.0, nk):
     for l in np.linspace(0.05, 0.35, nl):
         tables.append(tab)
         lesp.append(float(l))
+world = int(os.environ.get("ENS_WORLD", 1))      # emulate rank 0's shard of a `world`-GPU run on one GPU
 tables = np.array(tables)
+if world > 1:
+    mine = uf.ensemble_shard(tables, lesp, int(os.environ.get("ENS_RANK", os.environ.get("LOCAL_RANK", 0))), world) if os.environ.get("ENS_DEAL", "1") == "1" else np.arange(len(lesp))[0::world]
+    tables, lesp = tables[mine], list(np.array(lesp)[mine])
 print(f"members {len(lesp)} steps {nsteps} (tables built in {time.time() - t0:.1f} s)", flush=True)
 t0 = time.time()
 mats, ntev, nlev, ms = uf.ldvm_batch(base, tables, np.array(lesp), dtstar)

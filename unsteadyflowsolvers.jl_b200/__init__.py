@@ -11,7 +11,7 @@ from .delvort import delNone, delSpalart, delVortDef
 from .kinem import (ConstDef, CosDef, EldRampReturnDef, EldRampReturntstartDef, EldUpDef, EldUpIntDef, EldUpInttstartDef, EldUptstartDef, FileDef,
                     KinemDef, KinemPar, LinearDef, MotionDef, SinDef, StepGustDef)
 from .postprocess import calc_delcp, calc_edgeVel, writeStamp, meshgrid
-from .solvers import LVE, kinematics_table, lautat, ldvm, ldvm2DOF, ldvm2DOF_batch, ldvm_batch, ldvmLin, lve_table
+from .solvers import LVE, ensemble_shard, kinematics_table, lautat, ldvm, ldvm2DOF, ldvm2DOF_batch, ldvm_batch, ldvmLin, lve_table
 from .typedefs import KinemPar2DOF, TwoDFlowField, TwoDOFPar, TwoDSurf, TwoDVort, VortList
 from .utils import find_tstep, simpleTrapz
 

@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_lve_solve(const LdvmDev d) {
 
 // OCC = member CTAs per SM the register budget is cut for (3: 85 registers, 2: 128); UN = independent source chains
 // per thread in the member roll-up and bound sweep (what the register budget lets the compiler keep interleaved)
-template <int OCC, int UN>
-__global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a) {
+template <int THREADS, int OCC, int UN, int SYM>
+__global__ void __launch_bounds__(THREADS, OCC) k_ensemble(const EnsArgs a) {
     extern __shared__ __align__(16) double ens_smem[];
     __shared__ LdvmDev d;
     __shared__ StepState sst;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_ensemble(const EnsArgs a
             step_solve(d, d.costab, d.sintab, nullptr, ws);
             __syncthreads();
             c0 = clock64(); prof[2] += c0 - c1;
-            ens_rollup<UN>(d, wk, tot);
+            ens_rollup<UN, SYM>(d, wk, tot, a.sym_min);
             c1 = clock64(); prof[3] += c1 - c0;
             if (a.prof && tid == 0) {
                 const long long nfree = (sst.wake.end[0] - sst.wake.begin[0]) + (sst.wake.end[1] - sst.wake.begin[1]);
@@ -921,6 +921,9 @@ int unsflow_ldvm_timing(unsflow_ldvm *h, float *ms_total, int64_t *n_launches) {
 
 // shared body of the two ensemble entry points; strpar/kinem2dof non-null <=> ldvm2DOF members
 static thread_local std::vector<long long> g_batch_prof;   // per-CTA phase cycle sums of the last run (UNSFLOW_ENS_PROFILE=1)
+static int ens_auto_threads(int64_t M) {
+    return 256;
+}
 static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_t nmember, int64_t nsteps,
                           const double *tables, const double *lespcrit, const double *strpar, const double *kinem2dof,
                           double *mat_out, double *kinem2dof_out, int64_t *ntev_out, int64_t *nlev_out) {
@@ -944,7 +947,11 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     // per-member slabs (shared memory): [TEV | LEV | EXTV(empty) | BV]
     const int64_t cap_t = round_up(nsteps + 1, 8), cap_l = round_up(nsteps + 1, 8), cap_e = 8, bvp = round_up(nd - 1, 8);
     const int64_t off_l = cap_t, off_e = off_l + cap_l, off_b = off_e + cap_e, tot = off_b + bvp;
-    const int groups = std::max(1, kSolveThreads / nd);      // source groups of ens_sweep = partial planes it writes
+    // member CTA width: 256 threads x 3 per SM when there are members enough to fill the GPU several times over; wider,
+    // fewer CTAs when a GPU only holds a few hundred members (the tail of the longest member would dominate)
+    static const int env_threads = [] { const char *e = getenv("UNSFLOW_ENS_THREADS"); return e ? atoi(e) : 0; }();
+    const int threads = env_threads == 512 || env_threads == 1024 || env_threads == 256 ? env_threads : ens_auto_threads(M);
+    const int groups = std::max(1, threads / nd);      // source groups of ens_sweep = partial planes it writes
     const size_t ens_dyn = sizeof(double) * (size_t)ens_smem_doubles(nd, na, tot, groups);
     UF_CHECK(ens_dyn <= 200 * 1024, "unsflow_ldvm_batch_run: %lld steps need %zu bytes of shared memory per member (max 200 KB); use unsflow_ldvm_run", (long long)nsteps, ens_dyn);
     // the member kernels use the scalar core radius 0.02c of every reference-created vortex (calcs.jl:385,423)
@@ -1028,7 +1035,7 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     d.vc_new = vc_new; d.vc4_new = vc4; d.nsurf = 1;
     d.theta = geo.p; d.x = geo.p + nd; d.cam = geo.p + 2 * nd; d.cam_slope = geo.p + 3 * nd;
     d.costab = tabs.p; d.sintab = tabs.p + (int64_t)(na + 1) * nd;
-    ea.img = img.p; ea.st = st.p; ea.kin = kin.p; ea.mat = mat.p; ea.order = order.p; ea.next = next.p;
+    ea.img = img.p; ea.st = st.p; ea.kin = kin.p; ea.mat = mat.p; ea.order = order.p;
     ea.M = M; ea.nsteps = nsteps; ea.tot = tot; ea.off_l = off_l; ea.off_e = off_e; ea.off_b = off_b; ea.groups = groups;
     DevBuf<double> lesp;
     if (lespcrit) {
@@ -1043,11 +1050,24 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
     UF_CUDA(cudaMemcpyAsync(kin.p, tables, sizeof(double) * M * nsteps * 9, cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemcpyAsync(order.p, hord.data(), sizeof(int) * M, cudaMemcpyHostToDevice, stream));
     UF_CUDA(cudaMemsetAsync(next.p, 0, sizeof(int), stream));
-    static const int want_occ = [] { const char *e = getenv("UNSFLOW_ENS_OCC"); const int v = e ? atoi(e) : 3; return v == 2 ? 2 : 3; }();
-    auto kern = want_occ == 2 ? k_ensemble<2, 8> : k_ensemble<3, 4>;
+    ea.next = next.p;
+    // UNSFLOW_ENS_SYM: 0 = one-sided roll-up, r = pair-symmetric with up to r rows per lane; UNSFLOW_ENS_OCC: CTAs per SM
+    static const int want_sym = [] { const char *e = getenv("UNSFLOW_ENS_SYM"); return e ? atoi(e) : 0; }();
+    // 3 member CTAs per SM (85 registers, 4 source chains per thread) give the best throughput; when the GPU holds
+    // fewer than ~1.5 members per such slot the run time is the LONGEST member's, and 2 CTAs per SM (128 registers,
+    // 8 chains) finish a single member sooner (512 members: 72.9 vs 81.5 ms, profiles/r02_ensemble_few_members.md)
+    static const int env_occ = [] { const char *e = getenv("UNSFLOW_ENS_OCC"); return e ? atoi(e) : 0; }();
+    const int want_occ = env_occ == 2 || env_occ == 3 ? env_occ : (M <= (int64_t)sm_count() * 9 / 2 ? 2 : 3);
+    static const int sym_min = [] { const char *e = getenv("UNSFLOW_ENS_SYM_MIN"); return e ? atoi(e) : kEnsSymMin; }();
+    ea.sym_min = std::max(sym_min, 64);
+    void (*kern)(const EnsArgs) = nullptr;
+    if (threads == 256 && want_occ == 2) kern = want_sym == 0 ? k_ensemble<256, 2, 8, 0> : want_sym == 2 ? k_ensemble<256, 2, 8, 2> : want_sym == 3 ? k_ensemble<256, 2, 8, 3> : k_ensemble<256, 2, 8, 4>;
+    else if (threads == 256) kern = want_sym == 0 ? k_ensemble<256, 3, 4, 0> : want_sym == 1 ? k_ensemble<256, 3, 4, 1> : want_sym == 2 ? k_ensemble<256, 3, 4, 2> : k_ensemble<256, 3, 4, 3>;
+    else if (threads == 512) kern = want_sym ? k_ensemble<512, 1, 4, 4> : k_ensemble<512, 1, 4, 0>;
+    else kern = want_sym ? k_ensemble<1024, 1, 4, 2> : k_ensemble<1024, 1, 4, 0>;
     UF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ens_dyn));
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSolveThreads, ens_dyn) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, ens_dyn) != cudaSuccess || occ < 1) occ = 1;
     static const int cap_occ = [] { const char *e = getenv("UNSFLOW_ENS_MAXOCC"); return e ? atoi(e) : 0; }();
     if (cap_occ > 0) occ = std::min(occ, cap_occ);
     const int grid = (int)std::min<int64_t>(M, (int64_t)occ * sm_count());
@@ -1057,7 +1077,7 @@ static int batch_run_impl(const unsflow_surf *sf, const unsflow_opts *op, int64_
         ea.prof = prof.p;
     }
     UF_CUDA(cudaEventRecord(ev0.e, stream));
-    kern<<<grid, kSolveThreads, ens_dyn, stream>>>(ea);
+    kern<<<grid, threads, ens_dyn, stream>>>(ea);
     UF_CUDA(cudaGetLastError());
     UF_CUDA(cudaEventRecord(ev1.e, stream));
     std::vector<double> hm((size_t)(M * nsteps * 8));

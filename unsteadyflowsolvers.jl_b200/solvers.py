@@ -313,6 +313,24 @@ def ldvm_batch(surf, tables, lespcrit, dtstar=0.015, *, driver=cabi.DRIVER_LDVM,
     return np.ascontiguousarray(mats.transpose(0, 2, 1)), ntev, nlev, ms.value
 
 
+def ensemble_shard(tables, lespcrit, rank, world, c=1.0):
+    """Member indices rank `rank` of `world` should run: members sorted by the same cost heuristic the ensemble
+    kernel orders its queues by (largest quasi-steady leading-edge loading the table asks for over the member's LESP
+    threshold -- a member that sheds LEVs every step has a wake twice as long) and dealt over the ranks boustrophedon,
+    so that every GPU gets the same mix of long and short members.  Members are independent: any split is valid,
+    this one only balances the load."""
+    tables = np.asarray(tables)
+    nmember = tables.shape[0]
+    lesp = np.broadcast_to(np.asarray(lespcrit, dtype=np.float64), (nmember,))
+    u = np.where(np.abs(tables[:, :, 5]) > 1e-12, np.abs(tables[:, :, 5]), 1.0)
+    peak = np.max(np.abs(tables[:, :, 1]) + np.abs(tables[:, :, 3]) * c / u + np.abs(tables[:, :, 4]) / u, axis=1)
+    order = np.argsort(-(peak / np.maximum(lesp, 1e-6)), kind="stable")
+    pos = np.arange(nmember)
+    row, col = pos // world, pos % world
+    owner = np.where(row % 2 == 1, world - 1 - col, col)
+    return np.sort(order[owner == rank])
+
+
 def ldvm2DOF_batch(surf, tables, lespcrit, strpars, kinems, dtstar=0.015, *, delvort=None, solve_mode=None):
     """Ensemble of independent ldvm2DOF runs (solvers.jl:657-788), e.g. a sweep over structural
     parameters: member m uses TwoDOFPar strpars[m], starts from KinemPar2DOF kinems[m] and follows
