@@ -136,4 +136,128 @@ __device__ inline void dev_nlsolve_tr(F &fn, double *x) {
     }
 }
 
+// ---- the same iteration for a system whose size is only known at run time (n <= NMAX): the multi-surface driver's
+// KelvinConditionMult (n = nsurf, solvers.jl:343) and KelvinKuttaMult (n = nsurf + nshed, :372).  All work arrays live
+// in a caller-provided workspace (shared memory, trn_ws_doubles(NMAX) doubles) instead of the thread's stack. ---------
+__host__ __device__ constexpr int trn_ws_doubles(int nmax) { return 2 * nmax * nmax + 14 * nmax; }
+
+// Gaussian elimination with partial pivoting, same operation order as the oracle's solve_lin; A = n x (n + 1) scratch
+__device__ inline void trn_solve_lin(int n, const double *J, const double *rhs, double *p, double *A) {
+    const int w = n + 1;
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * w + j] = J[i * n + j]; A[i * w + n] = rhs[i]; }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(A[r * w + c]) > fabs(A[piv * w + c])) piv = r;
+        if (piv != c) for (int j = 0; j <= n; j++) { const double t = A[c * w + j]; A[c * w + j] = A[piv * w + j]; A[piv * w + j] = t; }
+        for (int r = c + 1; r < n; r++) {
+            const double f = A[r * w + c] / A[c * w + c];
+            for (int j = c; j <= n; j++) A[r * w + j] -= f * A[c * w + j];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double v = A[i * w + n];
+        for (int j = i + 1; j < n; j++) v -= A[i * w + j] * p[j];
+        p[i] = v / A[i * w + i];
+    }
+}
+
+__device__ inline double trn_wnorm(int n, const double *d, const double *v) {
+    double s = 0;
+    for (int i = 0; i < n; i++) s += (d[i] * v[i]) * (d[i] * v[i]);
+    return sqrt(s);
+}
+
+// t = 3 n doubles of scratch
+template <class F>
+__device__ inline void trn_fd_jacobian(F &fn, int n, const double *x, double *J, double *t) {
+    const double cbrt_eps = 6.0554544523933395e-06;
+    double *xt = t, *fp = t + n, *fm = t + 2 * n;
+    for (int j = 0; j < n; j++) {
+        const double e = cbrt_eps * fmax(1.0, fabs(x[j]));
+        for (int k = 0; k < n; k++) xt[k] = x[k];
+        xt[j] = x[j] + e; fn(xt, fp);
+        xt[j] = x[j] - e; fn(xt, fm);
+        for (int i = 0; i < n; i++) J[i * n + j] = (fp[i] - fm[i]) / (2 * e);
+    }
+}
+
+// t = 6 n + n (n + 1) doubles of scratch
+__device__ inline void trn_dogleg(int n, const double *r, const double *d, const double *J, double delta, double *p, double *t) {
+    double *pi_ = t, *rhs = t + n, *g = t + 2 * n, *Jg = t + 3 * n, *pc = t + 4 * n, *df = t + 5 * n, *A = t + 6 * n;
+    for (int i = 0; i < n; i++) rhs[i] = -r[i];
+    trn_solve_lin(n, J, rhs, pi_, A);
+    if (trn_wnorm(n, d, pi_) <= delta) { for (int i = 0; i < n; i++) p[i] = pi_[i]; return; }
+    for (int j = 0; j < n; j++) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += J[i * n + j] * r[i];
+        g[j] = s / (d[j] * d[j]);
+    }
+    for (int i = 0; i < n; i++) { double s = 0; for (int j = 0; j < n; j++) s += J[i * n + j] * g[j]; Jg[i] = s; }
+    const double gn = trn_wnorm(n, d, g);
+    double Jgn2 = 0;
+    for (int i = 0; i < n; i++) Jgn2 += Jg[i] * Jg[i];
+    for (int i = 0; i < n; i++) pc[i] = -(gn * gn / Jgn2) * g[i];
+    const double pcn = trn_wnorm(n, d, pc);
+    if (pcn >= delta) { for (int i = 0; i < n; i++) p[i] = pc[i] * (delta / pcn); return; }
+    for (int i = 0; i < n; i++) df[i] = pi_[i] - pc[i];
+    double b = 0;
+    for (int i = 0; i < n; i++) b += 2 * pc[i] * df[i] * d[i] * d[i];
+    double a = trn_wnorm(n, d, df);
+    a = a * a;
+    const double tau = (-b + sqrt(b * b - 4 * a * (pcn * pcn - delta * delta))) / (2 * a);
+    for (int i = 0; i < n; i++) p[i] = pc[i] + tau * df[i];
+}
+
+// x: start on entry, soln.zero on exit; ws: trn_ws_doubles(nmax >= n) doubles
+template <class F>
+__device__ inline void dev_nlsolve_tr_n(F &fn, int n, double *x, double *ws) {
+    const double ftol = 1e-8, eta = 1e-4;
+    double *r = ws, *rn = ws + n, *d = ws + 2 * n, *p = ws + 3 * n, *rp = ws + 4 * n, *J = ws + 5 * n, *t = J + n * n;
+    fn(x, r);
+    trn_fd_jacobian(fn, n, x, J, t);
+    double fmaxv = 0;
+    for (int i = 0; i < n; i++) fmaxv = fmax(fmaxv, fabs(r[i]));
+    if (fmaxv <= ftol) return;
+    for (int j = 0; j < n; j++) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += J[i * n + j] * J[i * n + j];
+        d[j] = sqrt(s);
+        if (d[j] == 0) d[j] = 1;
+    }
+    double delta = trn_wnorm(n, d, x);
+    if (delta == 0) delta = 1.0;
+    for (int it = 0; it < 1000; it++) {
+        trn_dogleg(n, r, d, J, delta, p, t);
+        for (int i = 0; i < n; i++) x[i] += p[i];
+        fn(x, rn);
+        double s_r = 0, s_rn = 0, s_rp = 0;
+        for (int i = 0; i < n; i++) {
+            double v = r[i];
+            for (int j = 0; j < n; j++) v += J[i * n + j] * p[j];
+            rp[i] = v;
+            s_r += r[i] * r[i]; s_rn += rn[i] * rn[i]; s_rp += rp[i] * rp[i];
+        }
+        const double rho = (s_r - s_rn) / (s_r - s_rp);
+        bool converged = false;
+        if (rho > eta) {
+            for (int i = 0; i < n; i++) r[i] = rn[i];
+            trn_fd_jacobian(fn, n, x, J, t);
+            for (int j = 0; j < n; j++) {
+                double s = 0;
+                for (int i = 0; i < n; i++) s += J[i * n + j] * J[i * n + j];
+                d[j] = fmax(0.1 * d[j], sqrt(s));
+            }
+            fmaxv = 0;
+            for (int i = 0; i < n; i++) fmaxv = fmax(fmaxv, fabs(r[i]));
+            converged = fmaxv <= ftol;
+        } else {
+            for (int i = 0; i < n; i++) x[i] -= p[i];
+        }
+        if (rho < 0.1) delta = delta / 2;
+        else if (rho >= 0.9) delta = 2 * trn_wnorm(n, d, p);
+        else if (rho >= 0.5) delta = fmax(delta, 2 * trn_wnorm(n, d, p));
+        if (converged) break;
+    }
+}
+
 }  // namespace unsflow

@@ -69,7 +69,8 @@ __device__ void mstep_solve(const LdvmDev &d) {
     __shared__ double uind[kNdMax], wind[kNdMax], dw[kNdMax], dw1[kNdMax], dw2[kNdMax];
     __shared__ double uT[kNdMax], wT[kNdMax], uL[kNdMax], wL[kNdMax], gam[kNdMax];
     __shared__ double aterm[kNaMax + 1], dth[kNdMax], sc[32], fs[2];
-    __shared__ double gts[kMaxSurf], a0s[kMaxSurf];
+    __shared__ double gts[kMaxSurf], gap[kMaxSurf], gts2[kMaxSurf], gls[kMaxSurf], gla[kMaxSurf], a0s[kMaxSurf], cK[kMaxSurf][8];
+    __shared__ double trx[2 * kMaxSurf], trws[trn_ws_doubles(2 * kMaxSurf)];      // trust-region iterate and work space (thread 0)
     __shared__ int shed[kMaxSurf], nshed;
     __shared__ SurfState ms[kMaxSurf];
     const double eps_fd = 6.0554544523933395e-06;
@@ -81,7 +82,8 @@ __device__ void mstep_solve(const LdvmDev &d) {
     const long long bv0 = s->wake.begin[3];
     const int nb = nd - 1;
 
-    // ---------------- pass 1: per surface, update_indbound + add_indbound_b + 1x1 Kelvin ----------
+    // ---------------- pass 1a: per surface, update_indbound + add_indbound_b, Kelvin coefficients ----------
+    // The residual of surface q is affine in its own TEV strength only: K0 + g K1 - Kp + g (typedefs.jl:298-300).
     for (int q = 0; q < ns; q++) {
         const SurfState &m = ms[q];
         const double urefpi = m.uref * kPi, kfac = m.uref * m.c * kPi;
@@ -107,7 +109,7 @@ __device__ void mstep_solve(const LdvmDev &d) {
                 }
                 u += uj; w += wj;
             }
-            uind[i] = u; wind[i] = w;
+            d.uind[t] = u; d.wind[t] = w;                          // base: everything but the new TEV
             unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
             dw[i] = mdownwash_at(d, m, fs, t, u, w, sa, ca);
             dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
@@ -120,18 +122,40 @@ __device__ void mstep_solve(const LdvmDev &d) {
         __syncthreads();
         if (tid == 0) {
             const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
-            const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
-            const double g = -(K0 - Kp) / (K1 + 1.0);
-            sc[8] = g;
-            // NLsolve emulation: only the LAST unknown is one probe away from the root
-            sc[9] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE && q == ns - 1) ? g - eps_fd * fmax(1.0, fabs(g)) : g;
-            gts[q] = g;
+            cK[q][0] = kfac * (a00 + a10 / 2.); cK[q][1] = kfac * (a01 + a11 / 2.); cK[q][2] = kfac * (m.a0prev + d.aprev[q * na] / 2.);
         }
         __syncthreads();
-        const double ga = sc[9];
+    }
+    // ---------------- Kelvin condition of all surfaces (solvers.jl:342-343) ----------
+    if (tid == 0) {
+        for (int q = 0; q < ns; q++) gts[q] = gap[q] = -(cK[q][0] - cK[q][2]) / (cK[q][1] + 1.0);
+        if (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) {
+            // nlsolve(not_in_place(kelv), ones(nsurf)*-0.01): the trust-region iteration on the joint system; the
+            // reference is left in the state of its last functor call, the probe x - eps e_n of the last Jacobian
+            // column: every surface at soln.zero except the last one
+            double *xs = trx;
+            for (int q = 0; q < ns; q++) xs[q] = -0.01;
+            auto fk = [&](const double *x, double *r) {
+                for (int q = 0; q < ns; q++) r[q] = cK[q][0] + x[q] * cK[q][1] - cK[q][2] + x[q];
+            };
+            dev_nlsolve_tr_n(fk, ns, xs, trws);
+            for (int q = 0; q < ns; q++) gts[q] = gap[q] = xs[q];
+            gap[ns - 1] = xs[ns - 1] - eps_fd * fmax(1.0, fabs(xs[ns - 1]));
+        }
+    }
+    __syncthreads();
+    // ---------------- pass 1b: the functor's side effects at the applied strengths ----------
+    for (int q = 0; q < ns; q++) {
+        const SurfState &m = ms[q];
+        const double urefpi = m.uref * kPi;
+        double sa, ca;
+        sincos(m.kin[0], &sa, &ca);
+        const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
+        const double ga = gap[q];
         for (int i = tid; i < nd; i += blockDim.x) {
             const int t = q * nd + i;
-            uind[i] += ga * uT[i]; wind[i] += ga * wT[i];
+            unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
+            uind[i] = d.uind[t] + ga * uT[i]; wind[i] = d.wind[t] + ga * wT[i];
             dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
             d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
         }
@@ -186,92 +210,130 @@ __device__ void mstep_solve(const LdvmDev &d) {
     }
     __syncthreads();
     const long long le = s->wake.end[1];
-    // ---------------- pass 2: Kelvin-Kutta 2x2 for shedding surfaces, bv, forces -------------------
-    for (int q = 0; q < ns; q++) {
-        const SurfState &m = ms[q];
-        const double urefpi = m.uref * kPi, kfac = m.uref * m.c * kPi;
-        double sa, ca;
-        sincos(m.kin[0], &sa, &ca);
-        double gt = gts[q], gl = 0.0;
-        for (int i = tid; i < nd; i += blockDim.x) { const int t = q * nd + i; uind[i] = d.uind[t]; wind[i] = d.wind[t]; dw[i] = d.downwash[t]; }
-        __syncthreads();
-        if (nshed > 0 && shed[q]) {
+    // ---------------- pass 2a: Kelvin-Kutta coefficients (only when some surface sheds) -------------------
+    // Shedding surface: K0 + g1 (K1 + 1) + g2 (K2 + 1) - Kp and A0 = a00 + a01 g1 + a02 g2 (typedefs.jl:400-411);
+    // a surface that does not shed re-solves its TEV on the base the first solve left (:413-417).
+    if (nshed > 0) {
+        for (int q = 0; q < ns; q++) {
+            const SurfState &m = ms[q];
+            const double urefpi = m.uref * kPi, kfac = m.uref * m.c * kPi;
+            double sa, ca;
+            sincos(m.kin[0], &sa, &ca);
+            const double gt0 = gts[q];
             const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
             const double xl = d.wx[le - ns + q], zl = d.wz[le - ns + q];
+            const bool sh = shed[q] != 0;
             for (int i = tid; i < nd; i += blockDim.x) {
                 const int t = q * nd + i;
                 unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
-                unit_influence(xl, zl, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uL[i], &wL[i]);
-                uind[i] -= gt * uT[i]; wind[i] -= gt * wT[i];           // functor subtracts the STORED strength
-                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
+                const double ub = d.uind[t] - gt0 * uT[i], wb = d.wind[t] - gt0 * wT[i];   // functor subtracts the STORED strength
+                d.uind[t] = ub; d.wind[t] = wb;
+                dw[i] = mdownwash_at(d, m, fs, t, ub, wb, sa, ca);
                 dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
-                dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[t] * (uL[i] * ca - wL[i] * sa);
+                if (sh) {
+                    unit_influence(xl, zl, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uL[i], &wL[i]);
+                    dw2[i] = -uL[i] * sa - wL[i] * ca + d.cam_slope[t] * (uL[i] * ca - wL[i] * sa);
+                }
             }
             __syncthreads();
-            for (int k = warp; k < 6; k += nwarps) {
+            for (int k = warp; k < (sh ? 6 : 4); k += nwarps) {
                 const double v = warp_trapz_cos(k < 2 ? dw : (k < 4 ? dw1 : dw2), dth, d.costab + (k & 1) * nd, nd);
                 if (lane == 0) sc[k] = v;
             }
             __syncthreads();
             if (tid == 0) {
                 const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
-                const double a02 = -sc[4] / urefpi, a12 = 2. * sc[5] / urefpi;
-                const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), K2 = kfac * (a02 + a12 / 2.);
-                const double Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
-                const double lesp_cond = (a0s[q] > 0) ? m.lespcrit : -m.lespcrit;
-                const double m11 = K1 + 1., m12 = K2 + 1., m21 = a01, m22 = a02, r1 = Kp - K0, r2 = lesp_cond - a00;
-                const double det = m11 * m22 - m12 * m21;
-                const double g1 = (r1 * m22 - m12 * r2) / det, g2 = (m11 * r2 - r1 * m21) / det;
-                sc[8] = g1; sc[14] = g2;
-                // last unknown of KelvinKuttaMult = LEV strength of the last shedding surface
-                int lastshed = -1;
-                for (int j = 0; j < ns; j++) if (shed[j]) lastshed = j;
-                sc[15] = (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE && q == lastshed) ? g2 - eps_fd * fmax(1.0, fabs(g2)) : g2;
-            }
-            __syncthreads();
-            gt = sc[8]; gl = sc[14];
-            const double gla = sc[15];
-            for (int i = tid; i < nd; i += blockDim.x) {
-                const int t = q * nd + i;
-                uind[i] += gt * uT[i] + gla * uL[i]; wind[i] += gt * wT[i] + gla * wL[i];
-                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
-                d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
+                cK[q][0] = kfac * (a00 + a10 / 2.); cK[q][1] = kfac * (a01 + a11 / 2.);
+                cK[q][3] = kfac * (m.a0prev + d.aprev[q * na] / 2.);
+                cK[q][4] = a00; cK[q][5] = a01;
+                if (sh) {
+                    const double a02 = -sc[4] / urefpi, a12 = 2. * sc[5] / urefpi;
+                    cK[q][2] = kfac * (a02 + a12 / 2.); cK[q][6] = a02;
+                }
             }
             __syncthreads();
         }
-        if (nshed > 0 && !shed[q]) {
-            // KelvinKuttaMult re-solves the TEV of a non-shedding surface too (typedefs.jl:413-417):
-            // same 1x1 system on the base left by the first solve (identical root unless that base
-            // carries the stale probe offset of the NLsolve emulation)
+        // ---------------- Kelvin + Kutta conditions of all surfaces (solvers.jl:371-372) ----------
+        if (tid == 0) {
+            int lastshed = -1;
+            for (int q = 0; q < ns; q++) {
+                const double *c = cK[q];
+                if (shed[q]) {
+                    // closed form on the branch of the A0 that triggered the shedding:
+                    // (K1+1) gt + (K2+1) gl = Kp - K0 ;   a01 gt + a02 gl = lesp_cond - a00
+                    const double lesp_cond = (a0s[q] > 0) ? ms[q].lespcrit : -ms[q].lespcrit;
+                    const double m11 = c[1] + 1., m12 = c[2] + 1., m21 = c[5], m22 = c[6], r1 = c[3] - c[0], r2 = lesp_cond - c[4];
+                    const double det = m11 * m22 - m12 * m21;
+                    gts2[q] = (r1 * m22 - m12 * r2) / det; gls[q] = (m11 * r2 - r1 * m21) / det;
+                    lastshed = q;
+                } else {
+                    gts2[q] = -(c[0] - c[3]) / (c[1] + 1.0); gls[q] = 0.0;
+                }
+                gla[q] = gls[q];
+            }
+            if (d.solve_mode == UNSFLOW_SOLVE_NLSOLVE) {
+                // nlsolve(not_in_place(kelvkutta), -0.01*ones(nshed+nsurf)): unknowns = the nsurf TEV strengths, then the
+                // LEV strengths of the shedding surfaces in surface order.  The LESP target follows the sign of A0 at every
+                // evaluation (typedefs.jl:404-408): two self-consistent roots per shedding surface, the iteration picks.
+                double *xs = trx;
+                const int n = ns + nshed;
+                for (int k = 0; k < n; k++) xs[k] = -0.01;
+                auto fkk = [&](const double *x, double *r) {
+                    int lc = 0;
+                    for (int q = 0; q < ns; q++) {
+                        const double *c = cK[q];
+                        if (shed[q]) {
+                            const double g1 = x[q], g2 = x[ns + lc];
+                            const double a0x = c[4] + c[5] * g1 + c[6] * g2;
+                            r[q] = c[0] + c[1] * g1 + c[2] * g2 - c[3] + g1 + g2;
+                            r[ns + lc] = a0x - (a0x > 0 ? ms[q].lespcrit : -ms[q].lespcrit);
+                            lc++;
+                        } else {
+                            r[q] = c[0] + x[q] * c[1] - c[3] + x[q];
+                        }
+                    }
+                };
+                dev_nlsolve_tr_n(fkk, n, xs, trws);
+                int lc = 0;
+                for (int q = 0; q < ns; q++) {
+                    gts2[q] = xs[q];
+                    gls[q] = gla[q] = shed[q] ? xs[ns + lc++] : 0.0;
+                }
+                // last functor call = probe of the last unknown = LEV strength of the last shedding surface
+                gla[lastshed] = gls[lastshed] - eps_fd * fmax(1.0, fabs(gls[lastshed]));
+            }
+        }
+        __syncthreads();
+    }
+    // ---------------- pass 2b: side effects of the second solve, bv, forces -------------------
+    for (int q = 0; q < ns; q++) {
+        const SurfState &m = ms[q];
+        const double urefpi = m.uref * kPi;
+        double sa, ca;
+        sincos(m.kin[0], &sa, &ca);
+        double gt = gts[q], gl = 0.0;
+        if (nshed > 0) {
+            gt = gts2[q]; gl = gls[q];
+            const double glq = gla[q];
+            const bool sh = shed[q] != 0;
             const double xt = d.wx[te - ns + q], zt = d.wz[te - ns + q];
+            const double xl = d.wx[le - ns + q], zl = d.wz[le - ns + q];
             for (int i = tid; i < nd; i += blockDim.x) {
                 const int t = q * nd + i;
                 unit_influence(xt, zt, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uT[i], &wT[i]);
-                uind[i] -= gt * uT[i]; wind[i] -= gt * wT[i];
-                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
-                dw1[i] = -uT[i] * sa - wT[i] * ca + d.cam_slope[t] * (uT[i] * ca - wT[i] * sa);
+                double u = d.uind[t] + gt * uT[i], w = d.wind[t] + gt * wT[i];
+                if (sh) {
+                    unit_influence(xl, zl, m.vc4_new, d.bnd_x[t], d.bnd_z[t], &uL[i], &wL[i]);
+                    u += glq * uL[i]; w += glq * wL[i];
+                }
+                uind[i] = u; wind[i] = w;
+                dw[i] = mdownwash_at(d, m, fs, t, u, w, sa, ca);
+                d.uind[t] = u; d.wind[t] = w; d.downwash[t] = dw[i];
             }
-            __syncthreads();
-            for (int k = warp; k < 4; k += nwarps) {
-                const double v = warp_trapz_cos((k & 2) ? dw1 : dw, dth, d.costab + (k & 1) * nd, nd);
-                if (lane == 0) sc[k] = v;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const double a00 = -sc[0] / urefpi, a10 = 2. * sc[1] / urefpi, a01 = -sc[2] / urefpi, a11 = 2. * sc[3] / urefpi;
-                const double K0 = kfac * (a00 + a10 / 2.), K1 = kfac * (a01 + a11 / 2.), Kp = kfac * (m.a0prev + d.aprev[q * na] / 2.);
-                sc[8] = -(K0 - Kp) / (K1 + 1.0);
-            }
-            __syncthreads();
-            gt = sc[8];
-            for (int i = tid; i < nd; i += blockDim.x) {
-                const int t = q * nd + i;
-                uind[i] += gt * uT[i]; wind[i] += gt * wT[i];
-                dw[i] = mdownwash_at(d, m, fs, t, uind[i], wind[i], sa, ca);
-                d.uind[t] = uind[i]; d.wind[t] = wind[i]; d.downwash[t] = dw[i];
-            }
-            __syncthreads();
+        } else {
+            for (int i = tid; i < nd; i += blockDim.x) { const int t = q * nd + i; uind[i] = d.uind[t]; wind[i] = d.wind[t]; dw[i] = d.downwash[t]; }
         }
+        __syncthreads();
         // final Fourier coefficients of this surface from its final downwash
         block_trapz_cos_all(dw, dth, d.costab, nd, na, aterm);
         __syncthreads();
