@@ -141,7 +141,7 @@ __device__ inline void dev_nlsolve_tr(F &fn, double *x) {
 // in a caller-provided workspace (shared memory, trn_ws_doubles(NMAX) doubles) instead of the thread's stack. ---------
 __host__ __device__ constexpr int trn_ws_doubles(int nmax) { return 2 * nmax * nmax + 14 * nmax; }
 
-// Gaussian elimination with partial pivoting, same operation order as the oracle's solve_lin; A = n x (n + 1) scratch
+// Gaussian elimination with partial pivoting, row-by-row elimination, fixed operation order; A = n x (n + 1) scratch
 __device__ inline void trn_solve_lin(int n, const double *J, const double *rhs, double *p, double *A) {
     const int w = n + 1;
     for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) A[i * w + j] = J[i * n + j]; A[i * w + n] = rhs[i]; }
