@@ -17,7 +17,11 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 cabi = uf._cabi
 surf, fld, dtstar = c2_surf(uf)
 x, z, g, vc = s_wake(n)
-fld.tev = uf.VortList.from_arrays(x + 0.5, z, g, vc)
+if os.environ.get("STEPPER_TWO_FAMILIES"):   # half TEVs, half LEVs (the wake of tools/ldvm_multigpu_check.py)
+    fld.tev = uf.VortList.from_arrays(x[: n // 2] + 0.5, z[: n // 2], g[: n // 2], vc[: n // 2])
+    fld.lev = uf.VortList.from_arrays(x[n // 2:] + 0.5, z[n // 2:], g[n // 2:], vc[n // 2:])
+else:
+    fld.tev = uf.VortList.from_arrays(x + 0.5, z, g, vc)
 h = LdvmHandle(surf, fld, _opts(cabi.DRIVER_LDVM, dtstar, steps, uf.delNone(), None))
 h.set_kinematics(uf.kinematics_table(surf, fld, steps, dtstar))
 h.run(steps)

@@ -147,7 +147,7 @@ static int induce_host(const HostGroup *g, int ng, int64_t nt, const double *tx,
     if (sym) { plan.S = ctas; }
     // few targets against many sources (update_indbound): dedicated sweep kernel
     const bool sweep = !sym && !self_targets && nt <= 256 && ns >= 2048 && sweep_supported((int)nt);
-    if (sweep) plan.S = (int)std::max<int64_t>(1, std::min<int64_t>((ns + kTS - 1) / kTS + ng, 256));
+    if (sweep) plan.S = sweep_splits(ns, ng, 1024);
     const int64_t npart = sym ? sym_plane_doubles(ctas, tot) : 2 * (int64_t)plan.S * ntp;
     if (d_part.ensure(npart)) return 2;
     if (d_out.ensure(4 * ntp)) return 2;  // vx, vz, (x, z for convection)
@@ -408,7 +408,7 @@ int unsflow_bench_sweep(int64_t n, int ndiv, int reps, float *ms_sweep, float *m
     const int64_t npad = round_up(n, kSymTB), ndp = round_up(ndiv, 8);
     DevBuf<double> src, tgt, part;
     DevBuf<Regions> reg;
-    const int S = (int)std::max<int64_t>(1, std::min<int64_t>((n + kTS - 1) / kTS + 1, 592));
+    const int S = sweep_splits(n, 1, 592);
     InducePlan plan = plan_induce(ndiv, 1, n, 1, sm_count(), 592);
     const int Smax = std::max(S, plan.S);
     if (src.alloc(3 * npad) || tgt.alloc(2 * ndp) || part.alloc(2 * (int64_t)Smax * ndp) || reg.alloc(2)) return 2;

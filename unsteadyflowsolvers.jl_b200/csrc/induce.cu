@@ -66,21 +66,29 @@ int launch_induce_direct(const InduceArgs &a, const InducePlan &p, bool uniform,
 
 int sweep_supported(int ndiv) { return ndiv >= 1 && ndiv <= 256; }
 
-template <int RT, int TS>
+template <int RT>
 static void launch_sweep_rt(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
-    if (uniform) k_sweep<RT, true, TS><<<S, kThreads, 0, st>>>(a, ndiv);
-    else k_sweep<RT, false, TS><<<S, kThreads, 0, st>>>(a, ndiv);
+    if (uniform) k_sweep<RT, true><<<S, kThreads, 0, st>>>(a, ndiv);
+    else k_sweep<RT, false><<<S, kThreads, 0, st>>>(a, ndiv);
 }
 
-int sweep_tile(int ndiv, long long nsrc_ub) { return (ndiv <= 9 * kSweepTG && nsrc_ub <= 16384) ? 64 : kTS; }
+int sweep_splits(long long nsrc_ub, int nsreg, int max_S) {
+    // chunks of 32 sources; a region adds at most two partial ones.  One CTA per SM for wakes below ~5*10^4 sources,
+    // two per SM from there on (profiles/r02_sweep_split_scan.md: 18.5 -> 15.0 us at 10^5, 114 -> 77 us at 10^6 -- eight
+    // warps per SM leave the FP64 pipe 46 % busy, sixteen 73 %; below 5*10^4 the second CTA only adds planes);
+    // env UNSFLOW_SWEEP_M forces the CTAs per SM (experiments)
+    static int forced = [] { const char *e = getenv("UNSFLOW_SWEEP_M"); return e ? atoi(e) : 0; }();
+    const long long chunks = std::max<long long>(1, (nsrc_ub + kSweepGroups - 1) / kSweepGroups + 2LL * nsreg);
+    const long long smc = sm_count();
+    const long long m = forced > 0 ? forced : (chunks >= smc * 10 ? 2 : 1);
+    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(chunks, m * smc), max_S));
+}
 
-int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st, int ts) {
+int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st) {
     if (!sweep_supported(ndiv)) { set_error("launch_sweep: ndiv=%d not supported", ndiv); return 1; }
-    if (ndiv <= 9 * kSweepTG) {
-        if (ts == 64) launch_sweep_rt<9, 64>(a, ndiv, S, uniform, st);
-        else launch_sweep_rt<9, kTS>(a, ndiv, S, uniform, st);
-    } else if (ndiv <= 16 * kSweepTG) launch_sweep_rt<16, kTS>(a, ndiv, S, uniform, st);
-    else launch_sweep_rt<32, kTS>(a, ndiv, S, uniform, st);
+    if (ndiv <= 9 * kSweepTG) launch_sweep_rt<9>(a, ndiv, S, uniform, st);
+    else if (ndiv <= 16 * kSweepTG) launch_sweep_rt<16>(a, ndiv, S, uniform, st);
+    else launch_sweep_rt<32>(a, ndiv, S, uniform, st);
     UF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -159,8 +167,15 @@ int sym_ctas(int R) {
 
 int sym_ctas_max() { return std::max(std::max(sym_ctas(8), sym_ctas(4)), std::max(sym_ctas(2), sym_ctas(1))); }
 
-int launch_induce_sym(const SymArgs &a, int R, int order, cudaStream_t st) {
+int launch_induce_sym(const SymArgs &a_in, int R, int order, cudaStream_t st) {
     const int ctas = sym_ctas(R);
+    // timing probe only (results are then partial sums): UNSFLOW_SYM_SHARE="rank,nranks" makes a single GPU run the
+    // pair-tile share of one rank of a multi-GPU split (profiles/r02_stepper_rank_shares.md)
+    static int share[2] = {0, 0};
+    static bool parsed = [] { const char *e = getenv("UNSFLOW_SYM_SHARE"); if (e) sscanf(e, "%d,%d", &share[0], &share[1]); return true; }();
+    (void)parsed;
+    SymArgs a = a_in;
+    if (share[1] > 1 && share[0] >= 0 && share[0] < share[1]) { a.rank = share[0]; a.nranks = share[1]; }
     if (R == 8) return order == 2 ? launch_sym_one<8, 2>(a, ctas, st) : launch_sym_one<8, 3>(a, ctas, st);
     if (R == 4) return order == 2 ? launch_sym_one<4, 2>(a, ctas, st) : launch_sym_one<4, 3>(a, ctas, st);
     if (R == 2) return order == 2 ? launch_sym_one<2, 2>(a, ctas, st) : launch_sym_one<2, 3>(a, ctas, st);

@@ -128,8 +128,10 @@ __device__ __forceinline__ void sym_tile_coords(long long t, long long nb, long 
     *Jo = I + (t - sym_row_offset(I, nb));
 }
 
-// Blocks this CTA will write: one row -> that row block and its column range; several rows -> every block from the
-// first row on.  Zero them in the CTA's own plane (the planes are never memset as a whole) and publish the ranges.
+// Blocks this CTA will write: one row -> that row block and its column range; two rows (the usual row crossing: the
+// tail of row I, the head of row I+1) -> [I, J1] and [J, nb); more rows -> every block from the first row on.  (A
+// crossing CTA used to zero -- and k_sym_finish to read -- everything from its first row on: 1.6 MB of stores at
+// 50 blocks, +30 us on the critical CTA of 2 of 8 ranks at N = 10^5, profiles/r02_stepper_rank_shares.md.)  Zero them in the CTA's own plane (the planes are never memset as a whole) and publish the ranges.
 // Kept out of line so that the prologue does not perturb the register allocation of the pair loops.
 template <int TB>
 __device__ __noinline__ void sym_zero_touched(const Regions &reg, int nreg, long long nb, long long t1, long long I, long long J,
@@ -137,8 +139,9 @@ __device__ __noinline__ void sym_zero_touched(const Regions &reg, int nreg, long
     long long I1, J1;
     sym_tile_coords(t1 - 1, nb, &I1, &J1);
     SymTouch tc;
-    if (I1 > I) tc = SymTouch{I, nb, 0, 0};
-    else tc = SymTouch{I, I + 1, J, J1 + 1};
+    if (I1 == I) tc = SymTouch{I, I + 1, J, J1 + 1};                 // one row: its row block, columns J..J1
+    else if (I1 == I + 1) tc = SymTouch{I, J1 + 1, J, nb};          // two rows: row blocks I, I+1, columns I+1..J1 of the second, J..nb-1 of the first
+    else tc = SymTouch{I, nb, 0, 0};                                 // more rows: everything from the first row on
     const int tid = threadIdx.x;
     if (tid == 0) *touch = tc;
     for (int part = 0; part < 2; part++) {
@@ -268,16 +271,30 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                 }
             }
             if (a.bv_reg >= 0 && pb == 0) {   // bound vortices act on this row block exactly once (here)
-                for (long long j = reg.begin[a.bv_reg]; j < reg.end[a.bv_reg]; j++) {
-                    const double xj = __ldg(a.x + j), zj = __ldg(a.z + j), gj = __ldg(a.g + j);
+                // staged through the column accumulators' shared memory (free on a diagonal tile) in one coalesced pass:
+                // read one by one from global memory every bound vortex cost an exposed L2 round trip (69 of them = 35 us,
+                // 5 % of a CTA's share when 8 GPUs split a 10^5 wake -- profiles/r02_stepper_rank_shares.md)
+                double *sb = reinterpret_cast<double *>(s_acc);
+                constexpr int cap = (2 * TB) / 3;
+                const long long b0 = reg.begin[a.bv_reg], b1 = reg.end[a.bv_reg];
+                for (long long base = b0; base < b1; base += cap) {
+                    const int nbv = (int)(b1 - base < cap ? b1 - base : cap);
+                    __syncthreads();
+                    for (int c = tid; c < nbv; c += kThreads) {
+                        sb[c] = a.x[base + c]; sb[cap + c] = a.z[base + c]; sb[2 * cap + c] = a.g[base + c];
+                    }
+                    __syncthreads();
+                    for (int j = 0; j < nbv; j++) {
+                        const double xj = sb[j], zj = sb[cap + j], gj = sb[2 * cap + j];
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const double dx = xj - tx[r], dz = zj - tz[r];
-                        const double d2 = fma(dz, dz, dx * dx);
-                        const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
-                        const double m = gj * y;
-                        u[r] = fma(-dz, m, u[r]);
-                        w[r] = fma(dx, m, w[r]);
+                        for (int r = 0; r < R; r++) {
+                            const double dx = xj - tx[r], dz = zj - tz[r];
+                            const double d2 = fma(dz, dz, dx * dx);
+                            const double y = rsqrt_full<ORDER>(fma(d2, d2, vc4));
+                            const double m = gj * y;
+                            u[r] = fma(-dz, m, u[r]);
+                            w[r] = fma(dx, m, w[r]);
+                        }
                     }
                 }
             }

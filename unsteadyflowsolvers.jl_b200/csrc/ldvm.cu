@@ -279,7 +279,7 @@ static int ldvm_create_impl(unsflow_ldvm **out, int nsurf, const unsflow_surf *s
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evc);
     if (cudaMallocHost((void **)&h->pinned, sizeof(StepState)) != cudaSuccess) { set_error("cudaMallocHost failed"); return fail(2); }
     const int64_t tot = h->tot;
-    h->S2max = 256;
+    h->S2max = std::max(256, 2 * sm_count());
     h->S1max = (int)std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)2e9 / (16 * tot)));
     if (h->st.alloc(1) || h->ms.alloc(ns) || h->surf.alloc(ns * (9 * nd + 3 * na)) || h->tabs.alloc(2 * (na + 1) * nd) || h->wake.alloc(7 * tot) ||
         h->mat.alloc(h->mat_cols * h->mat_cap) || h->p2.alloc(2 * (int64_t)h->S2max * h->ndivpad) ||
@@ -594,10 +594,8 @@ static int enqueue_step(unsflow_ldvm *h, int64_t ntev_ub, int64_t nlev_ub, cudaS
         if (lve || (!multi && sweep_supported(h->ndiv))) {
             // dedicated few-targets kernel (sweep.cuh): one partial plane per block
             const int nt2 = lve ? h->ndiv - 1 : h->ndiv;
-            const int ts2 = sweep_tile(nt2, nwake_ub);
-            const long long tsrc = (nwake_ub + ts2 - 1) / ts2 + 3;
-            p2.S = (int)std::max<long long>(1, std::min<long long>(tsrc, h->S2max));
-            if (int rc = launch_sweep(a, nt2, p2.S, h->uniform, st, ts2)) return rc;
+            p2.S = sweep_splits(nwake_ub, 3, h->S2max);
+            if (int rc = launch_sweep(a, nt2, p2.S, h->uniform, st)) return rc;
         } else {
             if (int rc = launch_induce_direct(a, p2, h->uniform, order, st)) return rc;
         }

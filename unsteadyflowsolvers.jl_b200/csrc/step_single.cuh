@@ -211,26 +211,58 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
     double sa, ca;
     sincos(s->kin[0], &sa, &ca);
     // ---- A: induced velocity at the bound points from the sweep partials (update_indbound) ----
-    for (int i = tid; i < nd; i += blockDim.x) {
+    // The S2 partial planes are cut into Q contiguous ranges summed side by side by Q groups of nd threads (masked
+    // batches of 16 independent loads: one L2 latency per batch; additions in plane order inside a range), then the
+    // Q range sums are added in range order: fixed grouping for a given (S2, nd, block size) -> deterministic.
+    {
+        const int bd = blockDim.x;
+        const int Q = (lautat || nd > bd) ? 1 : (bd / nd < 3 ? bd / nd : 3);
         if (lautat) {   // lautat never calls update_indbound: uind/wind persist (solvers.jl:76-92)
-            uind[i] = d.uind[i];
-            wind[i] = d.wind[i];
-        } else {
-            // masked batches of 16 independent loads (one L2 latency per batch); additions stay in plane order
-            double su = 0.0, sw = 0.0;
-            for (int k = 0; k < d.S2; k += 16) {
-                double bu[16], bw[16];
+            for (int i = tid; i < nd; i += bd) { uind[i] = d.uind[i]; wind[i] = d.wind[i]; }
+        } else if (Q == 1) {
+            for (int i = tid; i < nd; i += bd) {
+                double su = 0.0, sw = 0.0;
+                for (int k = 0; k < d.S2; k += 16) {
+                    double bu[16], bw[16];
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const bool ok = k + q < d.S2;
-                    bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
-                    bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
+                    for (int q = 0; q < 16; q++) {
+                        const bool ok = k + q < d.S2;
+                        bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
+                        bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
                 }
-#pragma unroll
-                for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
+                uind[i] = su * kInvTwoPi;
+                wind[i] = sw * kInvTwoPi;
             }
-            uind[i] = su * kInvTwoPi;
-            wind[i] = sw * kInvTwoPi;
+        } else {
+            const int g = tid / nd, i = tid - g * nd;
+            if (g < Q) {
+                const int k1 = (int)((long long)d.S2 * (g + 1) / Q);
+                double su = 0.0, sw = 0.0;
+                for (int k = (int)((long long)d.S2 * g / Q); k < k1; k += 16) {
+                    double bu[16], bw[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const bool ok = k + q < k1;
+                        bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
+                        bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
+                }
+                // range sums: group 0 -> uind / wind, 1 -> uT / wT, 2 -> uL / wL (free until phase B)
+                (g == 0 ? uind : (g == 1 ? uT : uL))[i] = su;
+                (g == 0 ? wind : (g == 1 ? wT : wL))[i] = sw;
+            }
+            __syncthreads();
+            if (tid < nd) {
+                double su = uind[tid] + uT[tid], sw = wind[tid] + wT[tid];
+                if (Q > 2) { su += uL[tid]; sw += wL[tid]; }
+                uind[tid] = su * kInvTwoPi;
+                wind[tid] = sw * kInvTwoPi;
+            }
         }
     }
     if (tab_bar) mbar_wait(tab_bar, 0);

@@ -7,39 +7,63 @@
 // shared-memory word: broadcast; the 4 groups of a warp read 4 consecutive words).  RT
 // independent pair chains per lane keep the FP64 pipe busy; all 32 lanes do useful work, which
 // the generic kernel (one target per thread, 70 of 256 threads live) cannot.
+//
+// Work split: the live source ranges are cut into CHUNKS of 32 sources (one per source group) and the
+// chunk list is cut evenly over the grid, whose size is a multiple of the SM count (or the chunk count,
+// for a small wake): every CTA gets the same work to within one chunk, whatever the wake size -- with
+// whole 512-source tiles a 10^5 wake was 199 CTAs of one tile each on 148 SMs (51 SMs did double work).
+// A CTA stages its chunks in tiles of up to 512 sources (variable-size TMA bulk copies, double-buffered).
 // Per-block partial sums are reduced across the 32 groups in shared memory in a fixed order and
-// written to one plane per block; the consumer adds the planes in order (deterministic).
+// written to one plane per block; the consumer adds the planes in a fixed order (deterministic).
 #pragma once
 #include "induce.cuh"
 
 namespace unsflow {
 
 constexpr int kSweepTG = 8;                       // lanes per source group
-constexpr int kSweepGroups = kThreads / kSweepTG; // 32 source groups per block
+constexpr int kSweepGroups = kThreads / kSweepTG; // 32 source groups per block = sources per chunk
 
 int sweep_supported(int ndiv);                    // 1 when a k_sweep instantiation covers ndiv
-// grid.x = number of source splits = number of partial planes written (a.pu/pw, stride a.tstride)
-int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st, int ts = kTS);
-int sweep_tile(int ndiv, long long nsrc_ub);     // 64 for small wakes (ndiv <= 72), else 512
+// number of source splits = CTAs = partial planes for a wake of at most nsrc_ub sources in nsreg regions
+int sweep_splits(long long nsrc_ub, int nsreg, int max_S);
+// grid.x = S = number of partial planes written (a.pu/pw, stride a.tstride)
+int launch_sweep(const InduceArgs &a, int ndiv, int S, bool uniform, cudaStream_t st);
 
 #if defined(__CUDACC__) && defined(UNSFLOW_INDUCE_KERNELS)
 
-// TS = sources per tile: 512 (throughput) or 64 (latency: small wakes spread over more CTAs)
-template <int RT, bool UNIFORM, int TS>
+template <int RT, bool UNIFORM>
 __global__ void __launch_bounds__(kThreads) k_sweep(const InduceArgs a, int ndiv) {
     constexpr int NARR = UNIFORM ? 3 : 4;
+    constexpr int TS = kTS, CH = kSweepGroups, TCH = TS / CH;            // tile capacity in sources / chunks
     constexpr int kRed = (kThreads / 32) * 2 * RT * kSweepTG;          // reduction scratch (doubles)
     constexpr int kBuf = 2 * 4 * TS > kRed ? 2 * 4 * TS : kRed;         // tile buffers, reused by the reduction
     __shared__ __align__(128) double s_raw[kBuf];
     double (*s_buf)[4][TS] = reinterpret_cast<double (*)[4][TS]>(s_raw);   // [2][4][TS]
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ volatile int s_n[2];                                     // sources in the tile of each stage
 
     const int tid = threadIdx.x, lane8 = tid & (kSweepTG - 1), grp = tid / kSweepTG;
     const Regions sreg = *a.sreg;
-    long long T = 0;
-    for (int r = 0; r < a.nsreg; r++) T += tiles_in(sreg.begin[r], sreg.end[r], TS);
-    const long long S = gridDim.x;
-    const long long t0 = T * blockIdx.x / S, t1 = T * (blockIdx.x + 1) / S;
+    // chunk ranges of the regions (absolute CH-aligned chunks covering [begin, end)), this CTA's share [c0, c1)
+    long long cb[4], cn[4], C = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const bool live = r < a.nsreg && sreg.end[r] > sreg.begin[r];
+        cb[r] = live ? sreg.begin[r] / CH : 0;
+        cn[r] = live ? (sreg.end[r] + CH - 1) / CH - cb[r] : 0;
+        C += cn[r];
+    }
+    const long long c0 = C * blockIdx.x / gridDim.x, c1 = C * (blockIdx.x + 1) / gridDim.x;
+    int ntile = 0;
+    {
+        long long base = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const long long lo = c0 > base ? c0 : base, hi = c1 < base + cn[r] ? c1 : base + cn[r];
+            if (hi > lo) ntile += (int)((hi - lo + TCH - 1) / TCH);
+            base += cn[r];
+        }
+    }
 
     double tx[RT], tz[RT], u[RT], w[RT];
 #pragma unroll
@@ -57,24 +81,39 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const InduceArgs a, int ndiv
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](long long lin, int stage) {
-        const long long e0 = src_tile_start<TS>(sreg, a.nsreg, lin);
-        constexpr uint32_t bytes = TS * sizeof(double);
+    long long cur = c0;                                                 // next chunk to stage (thread 0)
+    auto issue = [&](int stage) {
+        // the tile starting at chunk `cur`: up to TCH chunks, never across a region boundary
+        long long base = 0, e0 = 0;
+        int nch = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (nch == 0 && cur < base + cn[r]) {
+                const long long seg_end = c1 < base + cn[r] ? c1 : base + cn[r];
+                nch = (int)(seg_end - cur < TCH ? seg_end - cur : TCH);
+                e0 = (cb[r] + (cur - base)) * CH;
+            }
+            base += cn[r];
+        }
+        cur += nch;
+        const uint32_t bytes = (uint32_t)(nch * CH * sizeof(double));
+        s_n[stage] = nch * CH;
         mbar_expect_tx(&s_bar[stage], NARR * bytes);
         tma_load_1d(&s_buf[stage][0][0], a.sx + e0, bytes, &s_bar[stage]);
         tma_load_1d(&s_buf[stage][1][0], a.sz + e0, bytes, &s_bar[stage]);
         tma_load_1d(&s_buf[stage][2][0], a.sg + e0, bytes, &s_bar[stage]);
         if (!UNIFORM) tma_load_1d(&s_buf[stage][NARR - 1][0], a.svc4 + e0, bytes, &s_bar[stage]);
     };
-    if (tid == 0 && t0 < t1) issue(t0, 0);
+    if (tid == 0 && ntile > 0) issue(0);
     const double vc4u = a.vc4_uniform;
-    for (long long it = t0; it < t1; it++) {
-        const int k = (int)(it - t0), stage = k & 1;
-        if (tid == 0 && it + 1 < t1) issue(it + 1, stage ^ 1);
+    for (int k = 0; k < ntile; k++) {
+        const int stage = k & 1;
+        if (tid == 0 && k + 1 < ntile) issue(stage ^ 1);
         mbar_wait(&s_bar[stage], (k >> 1) & 1);
+        const int n = s_n[stage];
         const double *sx = s_buf[stage][0], *sz = s_buf[stage][1], *sg = s_buf[stage][2], *sv = s_buf[stage][NARR - 1];
 #pragma unroll 1
-        for (int j = grp; j < TS; j += kSweepGroups) {
+        for (int j = grp; j < n; j += kSweepGroups) {
             const double xj = sx[j], zj = sz[j], gj = sg[j];
             const double vc4 = UNIFORM ? vc4u : sv[j];
 #pragma unroll
