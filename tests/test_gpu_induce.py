@@ -186,6 +186,20 @@ def test_ind_vel_dispatch_boundaries(gpu_lib, uf, oracle, ns, nt, uniform):
     assert rel_err_normalised(u, tu, au) <= TOL and rel_err_normalised(w, tw, aw) <= TOL
 
 
+@pytest.mark.parametrize("ns,nt,uniform", [
+    (2048, 70, True), (2080, 70, False), (4735, 72, True), (4737, 73, True),     # one chunk per CTA -> several (148 CTAs x 32 sources = 4736)
+    (47295, 70, True), (47400, 100, False), (100_001, 128, True), (300_000, 200, True),   # 1 -> 2 CTAs per SM near 4.7e4; RT = 9, 16, 32
+])
+def test_sweep_chunk_split(gpu_lib, uf, oracle, ns, nt, uniform):
+    """k_sweep (sweep.cuh): the wake is cut into chunks of 32 sources dealt evenly over a multiple of the SM count;
+    sizes on either side of the chunk / CTA-count rules of sweep_splits (induce.cu), all three target widths"""
+    x, z, g, vc = oracle.s_wake(ns, uniform_vc=uniform)
+    tx, tz, _, _ = oracle.s_wake(nt, seed=5)
+    u, w = uf.ind_vel(_vl(uf, x, z, g, vc), tx, tz)
+    tu, tw, au, aw = oracle.ind_vel_truth(x, z, g, vc, tx, tz)
+    assert rel_err_normalised(u, tu, au) <= TOL and rel_err_normalised(w, tw, aw) <= TOL
+
+
 @pytest.mark.parametrize("n", [2047, 2048, 2049, 4096, 16383, 16384, 16385, 18433, 28672, 32769, 40000, 90_000, 150_000])
 def test_mutual_ind_dispatch_boundaries(gpu_lib, uf, oracle, n):
     """direct <-> pair-tile switch (16384), partial last tiles, tile-size multiples; every

@@ -155,6 +155,16 @@ __device__ __noinline__ void sym_zero_touched(const Regions &reg, int nreg, long
     }
 }
 
+// row sums of the finished row block into the CTA's plane: all loads first (one L2 round trip, not R dependent ones)
+template <int R>
+__device__ __forceinline__ void sym_flush_rows(double *pu_t, double *pw_t, const double (&u)[R], const double (&w)[R]) {
+    double pu[R], pw[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { pu[r] = pu_t[r * kThreads]; pw[r] = pw_t[r * kThreads]; }
+#pragma unroll
+    for (int r = 0; r < R; r++) { pu_t[r * kThreads] = pu[r] + u[r]; pw_t[r * kThreads] = pw[r] + w[r]; }
+}
+
 template <int R, int ORDER>
 __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_induce_sym(const SymArgs a) {
     constexpr int TB = kThreads * R, kChunk = TB / (kThreads / 32);
@@ -232,14 +242,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
         if (tid == 0 && t + 1 < t1) issue(cbn, stage ^ 1);
 
         if (rb != rowI) {
-            if (rowI >= 0) {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const long long i = row_start + tid + r * kThreads;
-                    Pu[i] += u[r];
-                    Pw[i] += w[r];
-                }
-            }
+            if (rowI >= 0) sym_flush_rows<R>(Pu + row_start + tid, Pw + row_start + tid, u, w);
             rowI = rb;
             row_start = sym_block_start<TB>(reg, a.nreg, rb);
 #pragma unroll
@@ -393,11 +396,18 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
                     run_phase(p, max(gs0 - p * kChunk, 0), min(gs1 - p * kChunk, kChunk));
             }
             // flush the column accumulators into this CTA's private plane
-            const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);
-            for (int c = tid; c < TB; c += kThreads) {
-                const double2 acc = s_acc[c];
-                Pu[cstart + c] += acc.x;
-                Pw[cstart + c] += acc.y;
+            {
+                // all plane loads first, then the adds and stores: one L2 round trip instead of R dependent ones
+                const long long cstart = sym_block_start<TB>(reg, a.nreg, cb);
+                double pu[R], pw[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) { pu[r] = Pu[cstart + tid + r * kThreads]; pw[r] = Pw[cstart + tid + r * kThreads]; }
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double2 acc = s_acc[tid + r * kThreads];
+                    Pu[cstart + tid + r * kThreads] = pu[r] + acc.x;
+                    Pw[cstart + tid + r * kThreads] = pw[r] + acc.y;
+                }
             }
             __syncthreads();
         }
@@ -405,14 +415,7 @@ __global__ void __launch_bounds__(kThreads, (R >= 8 ? 1 : (R >= 4 ? 2 : 3))) k_i
         J = Jn;
         rb = rbn; cb = cbn; ncol = ncoln;
     }
-    if (rowI >= 0) {
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const long long i = row_start + tid + r * kThreads;
-            Pu[i] += u[r];
-            Pw[i] += w[r];
-        }
-    }
+    if (rowI >= 0) sym_flush_rows<R>(Pu + row_start + tid, Pw + row_start + tid, u, w);
 }
 
 // One CTA = kThreads consecutive entries of one block.  The planes that touched the block are found from the
