@@ -175,6 +175,26 @@ __device__ void dev_spalart(const LdvmDev &d, long long *begin, long long end, d
     }
 }
 
+// sum of the bound-sweep partial planes [k0, k1) at bound point i, in plane order: masked batches of W independent
+// loads (one L2 round trip per batch)
+template <int W>
+__device__ __forceinline__ void plane_range_sum(const LdvmDev &d, int i, int k0, int k1, double *su_out, double *sw_out) {
+    double su = 0.0, sw = 0.0;
+    for (int k = k0; k < k1; k += W) {
+        double bu[W], bw[W];
+#pragma unroll
+        for (int q = 0; q < W; q++) {
+            const bool ok = k + q < k1;
+            bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
+            bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < W; q++) { su += bu[q]; sw += bw[q]; }
+    }
+    *su_out = su;
+    *sw_out = sw;
+}
+
 // costab / sintab: the [(naterm+1)][ndiv] cos(n theta) / sin(n theta) tables -- d.costab / d.sintab in global memory, or
 // a shared-memory copy that a TMA bulk copy started at kernel entry is still filling (tab_bar != nullptr: wait on it
 // before the first table read; the copy overlaps the partial-plane sums of phase A)
@@ -211,47 +231,27 @@ __device__ void step_solve(const LdvmDev &d, const double *costab, const double 
     double sa, ca;
     sincos(s->kin[0], &sa, &ca);
     // ---- A: induced velocity at the bound points from the sweep partials (update_indbound) ----
-    // The S2 partial planes are cut into Q contiguous ranges summed side by side by Q groups of nd threads (masked
-    // batches of 16 independent loads: one L2 latency per batch; additions in plane order inside a range), then the
-    // Q range sums are added in range order: fixed grouping for a given (S2, nd, block size) -> deterministic.
+    // More than one batch of planes (wakes from ~10^4 vortices: 148 or 296 sweep CTAs): the S2 planes are cut into Q
+    // contiguous ranges summed side by side by Q groups of nd threads, then the Q range sums are added in range
+    // order: fixed grouping for a given (S2, nd, block size) -> deterministic, identical on all ranks.
     {
         const int bd = blockDim.x;
-        const int Q = (lautat || nd > bd) ? 1 : (bd / nd < 3 ? bd / nd : 3);
+        const int Q = (lautat || nd > bd || d.S2 <= 16) ? 1 : (bd / nd < 3 ? bd / nd : 3);
         if (lautat) {   // lautat never calls update_indbound: uind/wind persist (solvers.jl:76-92)
             for (int i = tid; i < nd; i += bd) { uind[i] = d.uind[i]; wind[i] = d.wind[i]; }
         } else if (Q == 1) {
             for (int i = tid; i < nd; i += bd) {
-                double su = 0.0, sw = 0.0;
-                for (int k = 0; k < d.S2; k += 16) {
-                    double bu[16], bw[16];
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const bool ok = k + q < d.S2;
-                        bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
-                        bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
-                }
+                double su, sw;
+                plane_range_sum<16>(d, i, 0, d.S2, &su, &sw);
                 uind[i] = su * kInvTwoPi;
                 wind[i] = sw * kInvTwoPi;
             }
         } else {
             const int g = tid / nd, i = tid - g * nd;
             if (g < Q) {
-                const int k1 = (int)((long long)d.S2 * (g + 1) / Q);
-                double su = 0.0, sw = 0.0;
-                for (int k = (int)((long long)d.S2 * g / Q); k < k1; k += 16) {
-                    double bu[16], bw[16];
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const bool ok = k + q < k1;
-                        bu[q] = ok ? d.p2u[(long long)(k + q) * d.p2stride + i] : 0.0;
-                        bw[q] = ok ? d.p2w[(long long)(k + q) * d.p2stride + i] : 0.0;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 16; q++) { su += bu[q]; sw += bw[q]; }
-                }
+                const int k0 = (int)((long long)d.S2 * g / Q), k1 = (int)((long long)d.S2 * (g + 1) / Q);
+                double su, sw;
+                plane_range_sum<16>(d, i, k0, k1, &su, &sw);      // (32-wide batches measured no faster)
                 // range sums: group 0 -> uind / wind, 1 -> uT / wT, 2 -> uL / wL (free until phase B)
                 (g == 0 ? uind : (g == 1 ? uT : uL))[i] = su;
                 (g == 0 ? wind : (g == 1 ? wT : wL))[i] = sw;
