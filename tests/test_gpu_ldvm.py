@@ -275,6 +275,60 @@ def test_wake_growing_through_the_pair_tile_threshold_inside_graph_chunks(gpu_li
     assert np.max(np.abs(a["vz"] - b["vz"])) <= 1e-11 * max(1.0, np.max(np.abs(b["vz"])))
 
 
+@pytest.mark.parametrize("env", [{"UNSFLOW_NO_CLUSTER": "1"}, {"UNSFLOW_CLUSTER_SIZE": "8"}, {"UNSFLOW_CLUSTER_SIZE": "16"},
+                                 {"UNSFLOW_CLUSTER_SIZE": "4", "UNSFLOW_CLUSTER_MAX_N": "2048"}],
+                         ids=["five-kernel", "cluster8", "cluster16", "cluster4-to-2048"])
+def test_small_wake_stepper_paths_against_the_oracle(gpu_lib, uf, oracle, env):
+    """the two steppers for small wakes -- the thread-block-cluster loop (step_cluster.cuh: whole chunks of steps in one
+    launch, several cluster sizes, its range stretched to the staging capacity) and the five-kernel CUDA-graph path it
+    replaces below ~1400 vortices -- on the same three runs against the oracle: C1r (LEV shedding, 150 steps, both vortex
+    families growing), C5-small (ldvm2DOF + Spalart merging: moving slab heads) and a run that starts on a 1200-vortex
+    wake with external vortices of their own core radii and grows through the hand-over between the two paths"""
+    import subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent("""
+        import sys, os, copy, numpy as np
+        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+        import unsflow_b200 as uf
+        from oracle import oracle as O
+        from cases import c1_surf, c1r_surf, c5_2dof
+        out = {}
+        surf, fld, _, dts = c1r_surf(uf)
+        out["c1r"], _, _ = uf.ldvm(surf, fld, 150, dts, write_summary=False)
+        surf, fld, strpar, kin0 = c5_2dof(uf)
+        out["c5"], _, f5 = uf.ldvm2DOF(surf, fld, strpar, kin0, 120, 0.015, 0, 0, 1000.0, uf.delSpalart(30, 10.0, 1e-6), write_summary=False)[:3]
+        out["c5_ntev"] = np.array([len(f5.tev)])
+        surf, fld, _, dts = c1_surf(uf)
+        x, z, g, vc = O.s_wake(1200)
+        fld.tev = uf.VortList.from_arrays(x[:1100] + 0.5, z[:1100], g[:1100], vc[:1100])
+        fld.extv = uf.VortList.from_arrays(x[1100:] + 0.5, z[1100:] + 0.3, g[1100:], 1.5 * vc[1100:])
+        out["grow"], _, fg = uf.ldvm(surf, fld, 200, dts, write_summary=False)
+        out["grow_x"] = fg.tev.x
+        np.savez(sys.argv[1], **out)
+    """)
+    f = tempfile.mktemp(suffix=".npz")
+    e = dict(os.environ)
+    for k in ("UNSFLOW_NO_CLUSTER", "UNSFLOW_CLUSTER_SIZE", "UNSFLOW_CLUSTER_MAX_N"):
+        e.pop(k, None)
+    e.update(env)
+    subprocess.run([sys.executable, "-c", code, f], check=True, env=e, cwd=os.path.dirname(os.path.dirname(__file__)))
+    got = np.load(f)
+    surf, fld, _, dts = c1r_surf(uf)
+    omat, _ = _oracle_run(oracle, uf, surf, fld, oracle.DRIVER_LDVM, 150, dts)
+    assert np.max(np.abs(got["c1r"] - omat)) <= HTOL
+    surf, fld, strpar, kin0 = c5_2dof(uf)
+    omat, sim = _oracle_run(oracle, uf, surf, fld, oracle.DRIVER_LDVM2DOF, 120, 0.015, twodof=(strpar, kin0), delvort=(1, 30, 10.0, 1e-6))
+    assert np.max(np.abs(got["c5"] - omat)) <= HTOL
+    assert int(got["c5_ntev"][0]) == len(sim.get_vorts(0)["x"])
+    surf, fld, _, dts = c1_surf(uf)
+    x, z, g, vc = oracle.s_wake(1200)
+    fld.tev = uf.VortList.from_arrays(x[:1100] + 0.5, z[:1100], g[:1100], vc[:1100])
+    fld.extv = uf.VortList.from_arrays(x[1100:] + 0.5, z[1100:] + 0.3, g[1100:], 1.5 * vc[1100:])
+    omat, sim = _oracle_run(oracle, uf, surf, fld, oracle.DRIVER_LDVM, 200, dts)
+    assert np.max(np.abs(got["grow"] - omat)) <= HTOL
+    ox = sim.get_vorts(0)["x"]
+    assert got["grow_x"].shape == ox.shape and np.max(np.abs(got["grow_x"] - ox)) <= 1e-9 * max(1.0, np.max(np.abs(ox)))
+
+
 def test_ensemble_batch_matches_oracle_per_member(gpu_lib, uf, oracle):
     """config 3 in miniature: members with different reduced frequency / LESPcrit, one CTA each"""
     ks = [0.1, 0.4, 0.8]

@@ -29,6 +29,7 @@
 #include "step_multi.cuh"
 #include "step_lve.cuh"
 #include "step_ensemble.cuh"
+#include "step_cluster.cuh"
 
 namespace unsflow {
 
@@ -56,6 +57,52 @@ __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d, i
         step_solve(d, tab_s, tab_s + (d.naterm + 1) * d.ndiv, &tab_bar, solve_dyn);
     } else {
         step_solve(d, d.costab, d.sintab, nullptr, solve_dyn);
+    }
+}
+
+// small wakes: a chunk of whole time steps in ONE launch of one thread-block cluster (step_cluster.cuh)
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kSolveThreads, 1) k_cluster_steps(const ClusterArgs a) {
+    // dynamic shared memory: [step_solve workspace | cos / sin tables (optional) | source staging of the roll-up]
+    extern __shared__ __align__(128) double cl_dyn[];
+    __shared__ __align__(8) uint64_t tab_bar;
+    const unsigned rank = cl_rank(), C = cl_size();
+    const LdvmDev &d = a.d;
+    double *ws = cl_dyn;
+    double *tab_s = ws + (solve_ws_doubles(d.ndiv, d.naterm) + 15) / 16 * 16;
+    double *stg = tab_s + (a.tabs_in_smem ? (2 * (d.naterm + 1) * d.ndiv + 15) / 16 * 16 : 0);
+    if (rank == 0 && a.tabs_in_smem) {      // once per chunk, not once per step
+        tabs_to_smem(d, tab_s, &tab_bar);
+        mbar_wait(&tab_bar, 0);
+    }
+    const double *ct = a.tabs_in_smem ? tab_s : d.costab;
+    const double *stb = a.tabs_in_smem ? tab_s + (d.naterm + 1) * d.ndiv : d.sintab;
+    long long pc[4] = {0, 0, 0, 0}, t0 = clock64();
+    for (long long is = 0; is < a.nsteps; is++) {
+        if (rank == 0) step_head(d);
+        cl_sync();
+        long long t1 = clock64(); pc[0] += t1 - t0;
+        if (d.driver != UNSFLOW_DRIVER_LAUTAT) cl_sweep<UNIFORM>(a, rank, C, stg);
+        cl_sync();
+        t0 = clock64(); pc[1] += t0 - t1;
+        // (counts as the head left them: identical on every CTA)
+        const long long n1_pre = d.st->wake.end[1] - d.st->wake.begin[1];
+        long long nf_pre = n1_pre;
+        for (int r = 0; r < 3; r += 2) { const long long c = d.st->wake.end[r] - d.st->wake.begin[r]; nf_pre += c > 0 ? c : 0; }
+        const bool overlap = a.overlap && cl_overlap_ok(d, C, nf_pre);
+        ClEarly es;
+        if (rank == 0) step_solve(d, ct, stb, nullptr, ws);
+        else if (overlap) cl_rollup_early<UNIFORM>(a, rank, C, stg, es);      // wake-on-wake part, while CTA 0 solves
+        cl_sync();
+        t1 = clock64(); pc[2] += t1 - t0;
+        if (overlap) cl_rollup_late<UNIFORM>(a, rank, C, stg, es, n1_pre);
+        else cl_rollup<UNIFORM>(a, rank, C, stg);
+        cl_sync();
+        t0 = clock64(); pc[3] += t0 - t1;
+    }
+    if (a.prof && rank == 0 && threadIdx.x == 0) {
+        for (int q = 0; q < 4; q++) atomicAdd((unsigned long long *)a.prof + q, (unsigned long long)pc[q]);
+        atomicAdd((unsigned long long *)a.prof + 4, (unsigned long long)a.nsteps);
     }
 }
 
@@ -172,6 +219,7 @@ struct unsflow_ldvm {
     DevBuf<double> wake;      // 7 slabs
     DevBuf<double> kin;       // rows x 9
     DevBuf<double> mat;       // mat_cap x 8
+    DevBuf<long long> clprof; // optional phase counters of the cluster stepper
     DevBuf<double> p2;        // bound-sweep partials [2][S2max][ndivpad]
     DevBuf<double> p1;        // roll-up partials [2][S1max][tot]
     DevBuf<double> planes;    // symmetric kernel partial planes [ctas][2][tot] (allocated on first use)
@@ -717,6 +765,96 @@ static void poll_readback(unsflow_ldvm *h) {
     }
 }
 
+// Smallest wakes: chunks of whole steps inside one thread-block cluster (k_cluster_steps).  Single surface, the four
+// single-surface drivers, ndiv <= 72 (9 bound points per sweep lane), one rank; UNSFLOW_CLUSTER_SIZE (default 8; 16 =
+// non-portable size), UNSFLOW_CLUSTER_MAX_N (free vortices up to which the cluster path is taken), UNSFLOW_NO_CLUSTER=1.
+constexpr int64_t kClusterChunk = 64;
+static size_t cluster_dyn_probe() {      // shared memory of the default discretisation (cluster-size probe)
+    return sizeof(double) * cluster_smem_doubles(8 * kClRT, 35, true, true);
+}
+// cluster size: 16 CTAs (non-portable size) when the device can co-schedule such a cluster, else 8; the env forces it
+static int cluster_size() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 8;
+    int &c = cached[dev & 63];
+    if (c) return c;
+    const char *e = getenv("UNSFLOW_CLUSTER_SIZE");
+    const int want = e ? atoi(e) : 0;
+    if (want == 1 || want == 2 || want == 4 || want == 8) return c = want;
+    // 16: ask the driver whether one such cluster fits
+    void (*kern)(const ClusterArgs) = k_cluster_steps<true>;
+    const size_t dyn = cluster_dyn_probe();
+    int n16 = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) == cudaSuccess &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(16); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = dyn;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n16, kern, &cfg) != cudaSuccess) n16 = 0;
+    }
+    cudaGetLastError();
+    return c = (n16 >= 1 ? 16 : 8);
+}
+// free vortices (host-side upper bound at the end of a chunk) up to which the cluster path is taken: the crossover with
+// the five-kernel stepper measured on a growing C2 wake (profiles/r02_cluster_stepper.md) -- the roll-up of a cluster is
+// 8 or 16 SMs' worth of FP64, the five-kernel path has all 148
+static int64_t cluster_max_free() {
+    const char *off = getenv("UNSFLOW_NO_CLUSTER");
+    if (off && atoi(off) != 0) return -1;
+    const char *e = getenv("UNSFLOW_CLUSTER_MAX_N");
+    const int64_t n = e ? atoll(e) : (cluster_size() >= 16 ? 1408 : 1024);
+    return std::min<int64_t>(n, kClMaxFree);
+}
+static bool cluster_usable(const unsflow_ldvm *h) {
+    const int dr = h->opts.driver;
+    return cluster_max_free() >= 0 && h->nsurf == 1 && h->nranks == 1 && h->ndiv <= 8 * kClRT &&
+           (dr == UNSFLOW_DRIVER_LDVM || dr == UNSFLOW_DRIVER_LDVM2DOF || dr == UNSFLOW_DRIVER_LDVMLIN || dr == UNSFLOW_DRIVER_LAUTAT);
+}
+static int launch_cluster_steps(unsflow_ldvm *h, int64_t nsteps, cudaStream_t st) {
+    const int C = cluster_size();
+    const size_t tab_bytes = sizeof(double) * 2 * (size_t)(h->naterm + 1) * h->ndiv;
+    const bool tabs = tab_bytes <= 64 * 1024;
+    const size_t dyn = sizeof(double) * cluster_smem_doubles(h->ndiv, h->naterm, tabs, h->uniform);
+    h->dev.S2 = C;
+    ClusterArgs a;
+    a.d = h->dev;
+    a.planes_u = h->p2.p; a.planes_w = h->p2.p + (int64_t)h->S2max * h->ndivpad;
+    a.nsteps = nsteps; a.tabs_in_smem = tabs ? 1 : 0; a.vc4u = h->vc4u; a.dt = h->opts.dt;
+    static const bool no_overlap = [] { const char *e = getenv("UNSFLOW_CLUSTER_NO_OVERLAP"); return e && atoi(e) != 0; }();
+    a.overlap = no_overlap ? 0 : 1;
+    // UNSFLOW_CLUSTER_PROFILE=1: cycles of CTA 0 per phase, printed by unsflow_ldvm_run
+    static const bool want_prof = [] { const char *e = getenv("UNSFLOW_CLUSTER_PROFILE"); return e && atoi(e) != 0; }();
+    a.prof = nullptr;
+    if (want_prof) {
+        if (!h->clprof.p) { if (h->clprof.alloc(8) || h->clprof.zero(st)) return 2; }
+        a.prof = h->clprof.p;
+    }
+    void (*kern)(const ClusterArgs) = h->uniform ? k_cluster_steps<true> : k_cluster_steps<false>;
+    static size_t attr_bytes[64][2] = {{0}};      // per device and instantiation; the attribute only ever needs to grow
+    int dev = 0;
+    UF_CUDA(cudaGetDevice(&dev));
+    size_t &ab = attr_bytes[dev & 63][h->uniform ? 1 : 0];
+    if (dyn > ab) {
+        UF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        if (C > 8) UF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        ab = dyn;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    UF_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    return 0;
+}
+
 // Launch-bound regime (small wakes): replay a CUDA graph of kGraphChunk steps whose grids are
 // sized for a quantised upper bound at the END of the chunk; the graph is re-captured only when
 // that quantised bound (the key) changes.
@@ -747,7 +885,21 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         int64_t tev_ub, lev_ub;
         step_bounds(h, kGraphChunk, &tev_ub, &lev_ub);
         const bool small = tev_ub + lev_ub + h->nextv < 16384;
-        if (graphs_enabled() && small && nsteps - is >= kGraphChunk) {
+        bool in_cluster = false;
+        if (cluster_usable(h)) {
+            const int64_t chunk = std::min<int64_t>(nsteps - is, kClusterChunk);
+            int64_t ct_ub, cl_ub;
+            step_bounds(h, chunk, &ct_ub, &cl_ub);
+            in_cluster = ct_ub + cl_ub + h->nextv <= cluster_max_free();
+            if (in_cluster) {
+                if (int rc = launch_cluster_steps(h, chunk, st)) return rc;
+                h->launches += 1;
+                h->steps_done += chunk;
+                is += chunk;
+            }
+        }
+        if (in_cluster) {
+        } else if (graphs_enabled() && small && nsteps - is >= kGraphChunk) {
             const int64_t qt = std::min(h->cap_t, round_up(tev_ub, kGraphQuant)), ql = std::min(h->cap_l, round_up(lev_ub, kGraphQuant));
             if (int rc = ensure_planes(h, qt + ql + h->nextv)) return rc;
             if (!h->gexec || h->gkey_t != qt || h->gkey_l != ql || h->gkey_kin != h->dev.kin) {
@@ -809,6 +961,18 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
         for (int j = 0; j < mc; j++) mat_out[i + j * nsteps] = hm[(size_t)(mc * i + j)];
     UF_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (int rc = peer_check(&h->peer, st)) return rc;
+    if (h->clprof.p) {
+        long long pc[5] = {0, 0, 0, 0, 0};
+        UF_CUDA(cudaMemcpy(pc, h->clprof.p, sizeof(pc), cudaMemcpyDeviceToHost));
+        if (pc[4] > 0) {
+            int khz = 0;
+            cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+            const double us = 1e3 / (double)khz / (double)pc[4];
+            fprintf(stderr, "[unsflow cluster profile] %lld steps; us per step on CTA 0: head %.2f sweep %.2f solve %.2f roll-up %.2f\n",
+                    pc[4], pc[0] * us, pc[1] * us, pc[2] * us, pc[3] * us);
+        }
+        UF_CUDA(cudaMemset(h->clprof.p, 0, sizeof(pc)));
+    }
     if (step_trace_enabled() && g_trace.n > 1) {
         fprintf(stderr, "[unsflow step trace] rank %d/%d last step:", h->rank, h->nranks);
         for (int k = 1; k < g_trace.n; k++) {
