@@ -482,7 +482,8 @@ def main():
                 hh.run(n1)
                 ms1, nl1 = hh.timing()
                 hh.close()
-                c1 = {"steps": n1, "device_ms": ms1, "steps_per_s": n1 / (ms1 * 1e-3), "us_per_step": 1e3 * ms1 / n1, "launches_per_step": nl1 / n1}
+                c1 = {"steps": n1, "device_ms": ms1, "steps_per_s": n1 / (ms1 * 1e-3), "us_per_step": 1e3 * ms1 / n1, "launches_per_step": nl1 / n1,
+                      "path": "k_cluster_steps (64 steps per launch of one thread-block cluster)" if nl1 < n1 else "five kernels per step, CUDA graph"}
                 if not args.no_cpu_baseline:
                     t0 = time.perf_counter()
                     O.Sim(surf1, uf.TwoDFlowField()).run(O.DRIVER_LDVM, uf.kinematics_table(surf1, uf.TwoDFlowField(), n1, dts1), dts1)
