@@ -34,10 +34,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 13.0
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_induce_sym<8,3> launch at N = 1e6 from the
-# `ncu --set full` capture of this round (profiles/r02_sym_R8_N1e6_ncu_full.txt; the per-CTA partial planes'
-# read-modify-write, a fraction of a percent of DRAM bandwidth -- the kernel is FP64-bound).  None = not captured.
-NCU_TRAFFIC_SYM8_N1E6 = None
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_induce_sym<8,3> launch at N = 1e6 from the `ncu --set full`
+# capture of this round's final build (profiles/r02_sym_R8_N1e6_ncu_full.txt: 4.488 GB read + 5.494 GB written).  It is
+# a constant taken from that capture, not measured in this run (ncu cannot run inside the bench); algorithmic bytes
+# are 64 MB -- the rest is the read-modify-write of the per-CTA partial planes after every pair tile (2 x 32 KB x
+# 119 805 tiles + the zeroing of the touched blocks), 0.25 % of DRAM bandwidth: the kernel is FP64-bound.
+NCU_TRAFFIC_SYM8_N1E6 = 9.982e9
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SM x 64 DFMA lanes x 2 flop x 1.965 GHz = 37.2
 NBV = 69                        # ndiv - 1 bound vortices (typedefs.jl:68)
 
