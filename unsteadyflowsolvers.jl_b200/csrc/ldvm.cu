@@ -61,25 +61,66 @@ __global__ void __launch_bounds__(kSolveThreads) k_step_solve(const LdvmDev d, i
 }
 
 // small wakes: a chunk of whole time steps in ONE launch of one thread-block cluster (step_cluster.cuh)
+// StepState <-> global, word by word (all threads of the CTA)
+__device__ __forceinline__ void copy_state(StepState *dst, const StepState *src) {
+    static_assert(sizeof(StepState) % 8 == 0, "StepState is copied as 8-byte words");
+    const long long *s8 = reinterpret_cast<const long long *>(src);
+    long long *d8 = reinterpret_cast<long long *>(dst);
+    for (int k = threadIdx.x; k < (int)(sizeof(StepState) / 8); k += blockDim.x) d8[k] = s8[k];
+}
+
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kSolveThreads, 1) k_cluster_steps(const ClusterArgs a) {
-    // dynamic shared memory: [step_solve workspace | cos / sin tables (optional) | source staging of the roll-up]
+    // dynamic shared memory: [step_solve workspace | cos / sin tables (optional) | surface copy | source staging of the roll-up]
     extern __shared__ __align__(128) double cl_dyn[];
     __shared__ __align__(8) uint64_t tab_bar;
+    __shared__ StepState sst;
     const unsigned rank = cl_rank(), C = cl_size();
     const LdvmDev &d = a.d;
+    const int tid = threadIdx.x, nd = d.ndiv, na = d.naterm, ndp = (nd + 7) / 8 * 8, nap = (na + 7) / 8 * 8;
     double *ws = cl_dyn;
-    double *tab_s = ws + (solve_ws_doubles(d.ndiv, d.naterm) + 15) / 16 * 16;
-    double *stg = tab_s + (a.tabs_in_smem ? (2 * (d.naterm + 1) * d.ndiv + 15) / 16 * 16 : 0);
+    double *tab_s = ws + (solve_ws_doubles(nd, na) + 15) / 16 * 16;
+    double *surf_s = tab_s + (a.tabs_in_smem ? (2 * (na + 1) * nd + 15) / 16 * 16 : 0);
+    double *stg = surf_s + (cluster_surf_doubles(nd, na) + 15) / 16 * 16;
     if (rank == 0 && a.tabs_in_smem) {      // once per chunk, not once per step
         tabs_to_smem(d, tab_s, &tab_bar);
         mbar_wait(&tab_bar, 0);
     }
+    // CTA 0 keeps StepState and the surface arrays in shared memory for the whole chunk (its single-thread sections walk
+    // shared-memory latencies instead of L2 round trips, as an ensemble member does) and publishes what the other CTAs
+    // read -- the live ranges / free stream (StepState) and the bound points -- to global memory before each barrier
+    // (a per-thread copy of the descriptor with the redirected pointers: after inlining, the untouched fields are still
+    // read from the kernel-parameter constant bank -- a descriptor selected at run time or kept in shared memory made
+    // every field access of step_solve a load: 15.8 -> 17.1 us per C1 step)
+    const bool local = rank == 0;
+    LdvmDev d0 = d;
+    d0.st = &sst;
+    d0.bnd_x = surf_s; d0.bnd_z = surf_s + ndp; d0.uind = surf_s + 2 * ndp; d0.wind = surf_s + 3 * ndp;
+    d0.downwash = surf_s + 4 * ndp; d0.theta = surf_s + 5 * ndp; d0.x = surf_s + 6 * ndp; d0.cam = surf_s + 7 * ndp;
+    d0.cam_slope = surf_s + 8 * ndp;
+    d0.aterm = surf_s + 9 * ndp; d0.adot = surf_s + 9 * ndp + nap; d0.aprev = surf_s + 9 * ndp + 2 * nap;
+    if (local) {
+        double *const g[9] = {d.bnd_x, d.bnd_z, d.uind, d.wind, d.downwash, d.theta, d.x, d.cam, d.cam_slope};
+        for (int q = 0; q < 9; q++)
+            for (int k = tid; k < nd; k += blockDim.x) surf_s[q * ndp + k] = g[q][k];
+        double *const ga[3] = {d.aterm, d.adot, d.aprev};
+        for (int q = 0; q < 3; q++)
+            for (int k = tid; k < na; k += blockDim.x) surf_s[9 * ndp + q * nap + k] = ga[q][k];
+        copy_state(&sst, d.st);
+        __syncthreads();
+    }
     const double *ct = a.tabs_in_smem ? tab_s : d.costab;
-    const double *stb = a.tabs_in_smem ? tab_s + (d.naterm + 1) * d.ndiv : d.sintab;
+    const double *stb = a.tabs_in_smem ? tab_s + (na + 1) * nd : d.sintab;
     long long pc[4] = {0, 0, 0, 0}, t0 = clock64();
     for (long long is = 0; is < a.nsteps; is++) {
-        if (rank == 0) step_head(d);
+        if (rank == 0) {
+            step_head(d0);
+            if (local) {
+                __syncthreads();
+                for (int k = tid; k < nd; k += blockDim.x) { d.bnd_x[k] = surf_s[k]; d.bnd_z[k] = surf_s[ndp + k]; }
+                copy_state(d.st, &sst);
+            }
+        }
         cl_sync();
         long long t1 = clock64(); pc[0] += t1 - t0;
         if (d.driver != UNSFLOW_DRIVER_LAUTAT) cl_sweep<UNIFORM>(a, rank, C, stg);
@@ -91,14 +132,28 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_cluster_steps(const Cluste
         for (int r = 0; r < 3; r += 2) { const long long c = d.st->wake.end[r] - d.st->wake.begin[r]; nf_pre += c > 0 ? c : 0; }
         const bool overlap = a.overlap && cl_overlap_ok(d, C, nf_pre);
         ClEarly es;
-        if (rank == 0) step_solve(d, ct, stb, nullptr, ws);
-        else if (overlap) cl_rollup_early<UNIFORM>(a, rank, C, stg, es);      // wake-on-wake part, while CTA 0 solves
+        if (rank == 0) {
+            step_solve(d0, ct, stb, nullptr, ws);
+            if (local) {
+                __syncthreads();
+                copy_state(d.st, &sst);
+            }
+        } else if (overlap) cl_rollup_early<UNIFORM>(a, rank, C, stg, es);      // wake-on-wake part, while CTA 0 solves
         cl_sync();
         t1 = clock64(); pc[2] += t1 - t0;
         if (overlap) cl_rollup_late<UNIFORM>(a, rank, C, stg, es, n1_pre);
         else cl_rollup<UNIFORM>(a, rank, C, stg);
         cl_sync();
         t0 = clock64(); pc[3] += t0 - t1;
+    }
+    if (local) {      // the surface back to global memory (StepState was published after the last solve)
+        __syncthreads();
+        double *const g[5] = {d.bnd_x, d.bnd_z, d.uind, d.wind, d.downwash};
+        for (int q = 0; q < 5; q++)
+            for (int k = tid; k < nd; k += blockDim.x) g[q][k] = surf_s[q * ndp + k];
+        double *const ga[3] = {d.aterm, d.adot, d.aprev};
+        for (int q = 0; q < 3; q++)
+            for (int k = tid; k < na; k += blockDim.x) ga[q][k] = surf_s[9 * ndp + q * nap + k];
     }
     if (a.prof && rank == 0 && threadIdx.x == 0) {
         for (int q = 0; q < 4; q++) atomicAdd((unsigned long long *)a.prof + q, (unsigned long long)pc[q]);

@@ -44,10 +44,15 @@ struct ClusterArgs {
     long long *prof;       // optional [5] cycle counters of CTA 0 (head, sweep, solve, roll-up, steps) or null
 };
 
+// CTA 0's shared-memory copy of the surface: [bnd_x, bnd_z, uind, wind, downwash, theta, x, cam, cam_slope](ndp each)
+// [aterm, adot, aprev](nap each)
+__host__ __device__ inline size_t cluster_surf_doubles(int nd, int na) {
+    return (size_t)(9 * ((nd + 7) / 8 * 8) + 3 * ((na + 7) / 8 * 8));
+}
 __host__ __device__ inline size_t cluster_smem_doubles(int nd, int na, bool tabs, bool uniform) {
     const size_t ws = (size_t)((solve_ws_doubles(nd, na) + 15) / 16 * 16);
     const size_t tab = tabs ? (size_t)((2 * (na + 1) * nd + 15) / 16 * 16) : 0;
-    return ws + tab + (size_t)(uniform ? 3 : 4) * kClCap;
+    return ws + tab + (cluster_surf_doubles(nd, na) + 15) / 16 * 16 + (size_t)(uniform ? 3 : 4) * kClCap;
 }
 
 #ifdef __CUDACC__
