@@ -22,6 +22,8 @@
 //                            and convects (explicit Euler) straight into the slabs -- no partial planes, no finish
 //   barrier
 //
+// CTA 0 keeps StepState and the surface arrays in its shared memory for the whole chunk and publishes the live ranges,
+// the free stream and the bound points before each barrier (k_cluster_steps, ldvm.cu).
 // Everything a CTA needs from another one travels through global memory (L2) between two cluster barriers; the
 // acquire side of the barrier invalidates the SM's L1.  Deterministic: fixed work split, fixed summation orders.
 #pragma once
