@@ -111,40 +111,53 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_cluster_steps(const Cluste
     }
     const double *ct = a.tabs_in_smem ? tab_s : d.costab;
     const double *stb = a.tabs_in_smem ? tab_s + (na + 1) * nd : d.sintab;
+    __shared__ ClIndex s_ix;      // live ranges as published after the last solve (what the next bound sweep walks)
+    __shared__ double hs[4];      // trailing edge + u, from step_head_a to step_head_b
+    const bool lautat = d.driver == UNSFLOW_DRIVER_LAUTAT;
+    // prologue: first half of the first step's head; the helpers note the live ranges before anything is published
+    if (tid == 0) s_ix.load(d.st);
+    if (local) {
+        step_head_a(d0, hs);
+        __syncthreads();
+        for (int k = tid; k < nd; k += blockDim.x) { d.bnd_x[k] = surf_s[k]; d.bnd_z[k] = surf_s[ndp + k]; }
+    }
+    cl_sync();
     long long pc[4] = {0, 0, 0, 0}, t0 = clock64();
     for (long long is = 0; is < a.nsteps; is++) {
-        if (rank == 0) {
-            step_head(d0);
-            if (local) {
-                __syncthreads();
-                for (int k = tid; k < nd; k += blockDim.x) { d.bnd_x[k] = surf_s[k]; d.bnd_z[k] = surf_s[ndp + k]; }
-                copy_state(d.st, &sst);
-            }
+        // ---- bound sweep on the helpers; CTA 0 places the TEV and publishes the step's state meanwhile ----
+        if (local) {
+            step_head_b(d0, hs);
+            __syncthreads();
+            copy_state(d.st, &sst);
+        } else if (!lautat) {
+            cl_sweep<UNIFORM>(a, s_ix, rank - 1, C - 1, stg);
         }
         cl_sync();
-        long long t1 = clock64(); pc[0] += t1 - t0;
-        if (d.driver != UNSFLOW_DRIVER_LAUTAT) cl_sweep<UNIFORM>(a, rank, C, stg);
-        cl_sync();
-        t0 = clock64(); pc[1] += t0 - t1;
+        long long t1 = clock64(); pc[1] += t1 - t0;
         // (counts as the head left them: identical on every CTA)
         const long long n1_pre = d.st->wake.end[1] - d.st->wake.begin[1];
         long long nf_pre = n1_pre;
         for (int r = 0; r < 3; r += 2) { const long long c = d.st->wake.end[r] - d.st->wake.begin[r]; nf_pre += c > 0 ? c : 0; }
         const bool overlap = a.overlap && cl_overlap_ok(d, C, nf_pre);
         ClEarly es;
-        if (rank == 0) {
+        if (local) {
             step_solve(d0, ct, stb, nullptr, ws);
-            if (local) {
-                __syncthreads();
-                copy_state(d.st, &sst);
-            }
+            __syncthreads();
+            copy_state(d.st, &sst);
         } else if (overlap) cl_rollup_early<UNIFORM>(a, rank, C, stg, es);      // wake-on-wake part, while CTA 0 solves
         cl_sync();
-        t1 = clock64(); pc[2] += t1 - t0;
+        t0 = clock64(); pc[2] += t0 - t1;
         if (overlap) cl_rollup_late<UNIFORM>(a, rank, C, stg, es, n1_pre);
         else cl_rollup<UNIFORM>(a, rank, C, stg);
+        if (tid == 0) s_ix.load(d.st);      // as the solve left them; stable until CTA 0 publishes the next head
+        // ---- CTA 0: first half of the NEXT step's head while the others finish the roll-up ----
+        if (local && is + 1 < a.nsteps) {
+            step_head_a(d0, hs);
+            __syncthreads();
+            for (int k = tid; k < nd; k += blockDim.x) { d.bnd_x[k] = surf_s[k]; d.bnd_z[k] = surf_s[ndp + k]; }
+        }
         cl_sync();
-        t0 = clock64(); pc[3] += t0 - t1;
+        t1 = clock64(); pc[3] += t1 - t0; t0 = t1;
     }
     if (local) {      // the surface back to global memory (StepState was published after the last solve)
         __syncthreads();
@@ -836,7 +849,7 @@ static int cluster_size() {
     if (c) return c;
     const char *e = getenv("UNSFLOW_CLUSTER_SIZE");
     const int want = e ? atoi(e) : 0;
-    if (want == 1 || want == 2 || want == 4 || want == 8) return c = want;
+    if (want == 2 || want == 4 || want == 8) return c = want;
     // 16: ask the driver whether one such cluster fits
     void (*kern)(const ClusterArgs) = k_cluster_steps<true>;
     const size_t dyn = cluster_dyn_probe();
@@ -875,7 +888,7 @@ static int launch_cluster_steps(unsflow_ldvm *h, int64_t nsteps, cudaStream_t st
     const size_t tab_bytes = sizeof(double) * 2 * (size_t)(h->naterm + 1) * h->ndiv;
     const bool tabs = tab_bytes <= 64 * 1024;
     const size_t dyn = sizeof(double) * cluster_smem_doubles(h->ndiv, h->naterm, tabs, h->uniform);
-    h->dev.S2 = C;
+    h->dev.S2 = C - 1;      // one bound-sweep plane per helper CTA
     ClusterArgs a;
     a.d = h->dev;
     a.planes_u = h->p2.p; a.planes_w = h->p2.p + (int64_t)h->S2max * h->ndivpad;
@@ -1023,8 +1036,8 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
             int khz = 0;
             cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
             const double us = 1e3 / (double)khz / (double)pc[4];
-            fprintf(stderr, "[unsflow cluster profile] %lld steps; us per step on CTA 0: head %.2f sweep %.2f solve %.2f roll-up %.2f\n",
-                    pc[4], pc[0] * us, pc[1] * us, pc[2] * us, pc[3] * us);
+            fprintf(stderr, "[unsflow cluster profile] %lld steps; us per step on CTA 0: sweep | place_tev %.2f, solve | early roll-up %.2f, late roll-up | next head %.2f\n",
+                    pc[4], pc[1] * us, pc[2] * us, pc[3] * us);
         }
         UF_CUDA(cudaMemset(h->clprof.p, 0, sizeof(pc)));
     }

@@ -7,19 +7,21 @@
 // with hardware cluster barriers (barrier.cluster, release / acquire at cluster scope: ~0.2 us) in place of
 // kernel boundaries:
 //
-//   CTA 0      step_head     kinematics row / 2DOF, update_boundpos, place_tev        (step_single.cuh, unchanged)
-//   barrier
-//   all CTAs   bound sweep   update_indbound (calcs.jl:35-38): CTA c takes the c-th slice of the free vortices,
-//                            8-lane source groups x 9 bound points per lane as in k_sweep -> one plane per CTA
+//   helpers    bound sweep   update_indbound (calcs.jl:35-38): helper c takes the c-th slice of the free vortices,
+//                            8-lane source groups x 9 bound points per lane as in k_sweep -> one plane per helper
+//   CTA 0      step_head_b   place_tev (the second half of step_head), meanwhile
 //   barrier
 //   CTA 0      step_solve    Kelvin / Kelvin-Kutta, LESP, place_lev, A_n, update_bv, Spalart merge, forces,
 //                            mat row (unchanged; the cos / sin tables stay in its shared memory for the whole chunk)
+//   helpers    wakeroll, early part: the wake-on-wake interactions only need what is known before the solve
 //   barrier
-//   all CTAs   wakeroll      (calcs.jl:222-294) every CTA stages ALL sources (free + bound vortices) in shared
-//                            memory; barrier (every CTA holds its snapshot, positions may now change); P = 2^k
-//                            neighbouring lanes share one target and split the sources P ways with 4 independent
-//                            chains each, xor-shuffle sum in a fixed order; lane 0 adds 1/2pi and the free stream
-//                            and convects (explicit Euler) straight into the slabs -- no partial planes, no finish
+//   helpers    wakeroll, late part: the vortices shed in this step and the bound vortices as sources; barrier inside
+//                            (every CTA holds its snapshot, positions may now change); P neighbouring lanes share one
+//                            target and split the sources P ways, shuffle sum in a fixed order; the group's first lane
+//                            adds 1/2pi and the free stream and convects (explicit Euler) straight into the slabs --
+//                            no partial planes, no finish (calcs.jl:222-294)
+//   CTA 0      the LEV shed in this step as a target, then step_head_a of the NEXT step (kinematics row / 2DOF,
+//              update_boundpos: nothing the roll-up reads), meanwhile
 //   barrier
 //
 // CTA 0 keeps StepState and the surface arrays in its shared memory for the whole chunk and publishes the live ranges,
@@ -93,12 +95,11 @@ __device__ __forceinline__ void cl_pair(double xj, double zj, double gj, double 
 }
 
 // update_indbound: slice `rank` of the free vortices against all bound points -> plane `rank`
+// (ix: the live ranges as published after the previous solve -- the TEV the head is placing meanwhile has strength 0)
 template <bool UNIFORM>
-__device__ __forceinline__ void cl_sweep(const ClusterArgs &a, unsigned rank, unsigned C, double *s_red) {
+__device__ __forceinline__ void cl_sweep(const ClusterArgs &a, const ClIndex &ix, unsigned rank, unsigned C, double *s_red) {
     const LdvmDev &d = a.d;
     const int tid = threadIdx.x, lane8 = tid & 7, grp = tid >> 3, warp = tid >> 5, nd = d.ndiv;
-    ClIndex ix;
-    ix.load(d.st);
     const long long Nf = ix.nfree();
     const long long c0 = Nf * rank / C, c1 = Nf * (rank + 1) / C;
     double tx[kClRT], tz[kClRT], u[kClRT], w[kClRT];

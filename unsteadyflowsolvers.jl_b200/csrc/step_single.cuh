@@ -102,6 +102,63 @@ __device__ void step_head(const LdvmDev &d) {
     }
 }
 
+// step_head in two halves for the cluster stepper (step_cluster.cuh), which runs the first half of step k+1 while the
+// other CTAs finish the roll-up of step k.  A: kinematics row / 2DOF update, update_boundpos -- touches nothing the
+// roll-up reads.  B: place_tev -- needs the convected position of the newest TEV.  hs: 4 doubles of shared memory
+// (trailing-edge position and u, handed from A to B).  step_head_a + barrier + step_head_b == step_head.
+__device__ void step_head_a(const LdvmDev &d, double *hs) {
+    StepState *s = d.st;
+    const int tid = threadIdx.x, nd = d.ndiv;
+    __shared__ double sh_kin[6];
+    double bx = 0.0, bz = 0.0, xi = 0.0, ci = 0.0;
+    if (tid < nd) { bx = d.bnd_x[tid]; bz = d.bnd_z[tid]; xi = d.x[tid]; ci = d.cam[tid]; }
+    if (tid == 0) {
+        const long long row = s->step < d.kin_rows ? s->step : d.kin_rows - 1;
+        const double *r = d.kin + 9 * row;
+        s->t = r[0];
+        if (d.driver == UNSFLOW_DRIVER_LDVM2DOF) {
+            s->fs[0] = r[7]; s->fs[1] = r[8];
+            dev_update_kinem2dof(d, s);
+        } else {
+            s->kin[0] = r[1]; s->kin[1] = r[2]; s->kin[2] = r[3]; s->kin[3] = r[4]; s->kin[4] = r[5]; s->kin[5] = r[6];
+            if (d.driver != UNSFLOW_DRIVER_LAUTAT) { s->fs[0] = r[7]; s->fs[1] = r[8]; }
+        }
+        for (int k = 0; k < 6; k++) sh_kin[k] = s->kin[k];
+        hs[2] = s->kin[4];
+    }
+    __syncthreads();
+    const double alpha = sh_kin[0], alphadot = sh_kin[2], hdot = sh_kin[3], u = sh_kin[4];
+    double sa, ca;
+    sincos(alpha, &sa, &ca);
+    if (tid < nd) {      // update_boundpos, calcs.jl:453-459
+        bx = bx + d.dt * ((d.pvt * d.c - xi) * sa * alphadot - u + ci * ca * alphadot);
+        bz = bz + d.dt * (hdot + (d.pvt * d.c - xi) * ca * alphadot - ci * sa * alphadot);
+        d.bnd_x[tid] = bx;
+        d.bnd_z[tid] = bz;
+        if (tid == nd - 1) { hs[0] = bx; hs[1] = bz; }
+    }
+}
+
+__device__ void step_head_b(const LdvmDev &d, const double *hs) {
+    StepState *s = d.st;
+    if (threadIdx.x == 0 && d.driver != UNSFLOW_DRIVER_LDVMLIN) {
+        // place_tev, calcs.jl:375-387
+        const long long b = s->wake.begin[0], e = s->wake.end[0];
+        double xloc, zloc;
+        if (e == b) {
+            xloc = hs[0] + 0.5 * hs[2] * d.dt;
+            zloc = hs[1];
+        } else {
+            xloc = hs[0] + (1. / 3.) * (d.wx[e - 1] - hs[0]);
+            zloc = hs[1] + (1. / 3.) * (d.wz[e - 1] - hs[1]);
+        }
+        d.wx[e] = xloc; d.wz[e] = zloc; d.wg[e] = 0.0;
+        if (d.wvc4) { d.wvc4[e] = d.vc4_new; d.wvc[e] = d.vc_new; }
+        d.wvx[e] = 0.0; d.wvz[e] = 0.0;
+        s->wake.end[0] = e + 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_step_solve helpers
 // ---------------------------------------------------------------------------------------------
