@@ -10,6 +10,9 @@
 //   k_induce_direct        wake roll-up        mutual_ind + ind_vel(bv) (N x (N+69))
 //   k_induce_finish        1/2pi, free stream, explicit-Euler convection
 //
+// Wakes below ~1400 vortices (single surface, ndiv <= 72, one rank) take k_cluster_steps instead: 64 steps per launch of
+// one 16-CTA thread-block cluster, the same phases separated by cluster barriers (step_cluster.cuh).
+//
 // Vortex counts live in device memory (Regions); grids are sized from host-side upper bounds
 // and surplus blocks exit.  Vortex families are slabs of one SoA allocation with a moving
 // head (popfirst! of the Spalart merge = zero the strength and advance the head).
@@ -288,6 +291,7 @@ struct unsflow_ldvm {
     DevBuf<double> kin;       // rows x 9
     DevBuf<double> mat;       // mat_cap x 8
     DevBuf<long long> clprof; // optional phase counters of the cluster stepper
+    bool cluster_off = false; // a cluster launch was refused on this device: five-kernel path only
     DevBuf<double> p2;        // bound-sweep partials [2][S2max][ndivpad]
     DevBuf<double> p1;        // roll-up partials [2][S1max][tot]
     DevBuf<double> planes;    // symmetric kernel partial planes [ctas][2][tot] (allocated on first use)
@@ -880,7 +884,7 @@ static int64_t cluster_max_free() {
 }
 static bool cluster_usable(const unsflow_ldvm *h) {
     const int dr = h->opts.driver;
-    return cluster_max_free() >= 0 && h->nsurf == 1 && h->nranks == 1 && h->ndiv <= 8 * kClRT &&
+    return !h->cluster_off && cluster_max_free() >= 0 && h->nsurf == 1 && h->nranks == 1 && h->ndiv <= 8 * kClRT &&
            (dr == UNSFLOW_DRIVER_LDVM || dr == UNSFLOW_DRIVER_LDVM2DOF || dr == UNSFLOW_DRIVER_LDVMLIN || dr == UNSFLOW_DRIVER_LAUTAT);
 }
 static int launch_cluster_steps(unsflow_ldvm *h, int64_t nsteps, cudaStream_t st) {
@@ -960,10 +964,17 @@ int unsflow_ldvm_run(unsflow_ldvm *h, int64_t nsteps, double *mat_out) {
             step_bounds(h, chunk, &ct_ub, &cl_ub);
             in_cluster = ct_ub + cl_ub + h->nextv <= cluster_max_free();
             if (in_cluster) {
-                if (int rc = launch_cluster_steps(h, chunk, st)) return rc;
-                h->launches += 1;
-                h->steps_done += chunk;
-                is += chunk;
+                if (launch_cluster_steps(h, chunk, st) != 0) {
+                    // the device would not take the cluster launch (no room for a co-scheduled cluster, e.g. a partitioned
+                    // GPU): nothing was enqueued -- this handle keeps to the five-kernel GPU path from here on
+                    cudaGetLastError();
+                    h->cluster_off = true;
+                    in_cluster = false;
+                } else {
+                    h->launches += 1;
+                    h->steps_done += chunk;
+                    is += chunk;
+                }
             }
         }
         if (in_cluster) {
