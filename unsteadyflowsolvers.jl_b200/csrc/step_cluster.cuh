@@ -38,14 +38,14 @@ constexpr int kClMaxFree = 2048;              // staging capacity in free vortic
 constexpr int kClCap = kClMaxFree + kNdMax + 8;   // + bound vortices (+ the two vortices shed in the step)
 
 struct ClusterArgs {
-    LdvmDev d;             // p2u / p2w / p2stride / S2 (= cluster size) set by the host
+    LdvmDev d;             // p2u / p2w / p2stride / S2 (= helper CTAs = bound-sweep planes) set by the host
     double *planes_u, *planes_w;   // the same planes, writable
     long long nsteps;
     int tabs_in_smem;      // cos / sin tables copied once into CTA 0's shared memory
     int overlap;           // 1: helper CTAs run the wake-on-wake part of the roll-up while CTA 0 solves (when possible)
     double vc4u;           // uniform core radius^4 (UNIFORM instantiation)
     double dt;
-    long long *prof;       // optional [5] cycle counters of CTA 0 (head, sweep, solve, roll-up, steps) or null
+    long long *prof;       // optional [5] cycle counters of CTA 0 ([1] sweep, [2] solve, [3] late roll-up phase, [4] steps) or null
 };
 
 // CTA 0's shared-memory copy of the surface: [bnd_x, bnd_z, uind, wind, downwash, theta, x, cam, cam_slope](ndp each)
