@@ -10,7 +10,7 @@
 //   k_induce_direct        wake roll-up        mutual_ind + ind_vel(bv) (N x (N+69))
 //   k_induce_finish        1/2pi, free stream, explicit-Euler convection
 //
-// Wakes below ~1400 vortices (single surface, ndiv <= 72, one rank) take k_cluster_steps instead: 64 steps per launch of
+// Wakes below ~1600 vortices (single surface, ndiv <= 72, one rank) take k_cluster_steps instead: 64 steps per launch of
 // one 16-CTA thread-block cluster, the same phases separated by cluster barriers (step_cluster.cuh).
 //
 // Vortex counts live in device memory (Regions); grids are sized from host-side upper bounds
@@ -879,7 +879,7 @@ static int64_t cluster_max_free() {
     const char *off = getenv("UNSFLOW_NO_CLUSTER");
     if (off && atoi(off) != 0) return -1;
     const char *e = getenv("UNSFLOW_CLUSTER_MAX_N");
-    const int64_t n = e ? atoll(e) : (cluster_size() >= 16 ? 1408 : 1024);
+    const int64_t n = e ? atoll(e) : (cluster_size() >= 16 ? 1664 : 1024);
     return std::min<int64_t>(n, kClMaxFree);
 }
 static bool cluster_usable(const unsflow_ldvm *h) {
